@@ -1,0 +1,654 @@
+/*
+ * kmer_oracle.c -- CPU restatement of the khmer/oxli arithmetic that kevlar's
+ * count -> novel -> filter path calls into.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference leg and __graft_entry__.smoke() may load it.
+ * The product (kevlar_b200/, libkvsketch.so) never links or calls it.
+ *
+ * Parity status: PINNED.  khmer itself (dib-lab/khmer@6c893074, the commit
+ * /root/reference/Dockerfile:36 pins; un-pinned master in requirements.txt:7)
+ * is not vendored under /root/reference and cannot be installed offline, so
+ * the algorithm below is a restatement of its published behaviour, anchored on
+ * the reference's own golden files (tests/golden/, see tests/test_oracle_golden.py):
+ *   - simple-genome-{case,ctrl1,ctrl2,case-band-2-1,case-band-16-7}.ct byte-for-byte
+ *     (kevlar/tests/test_count.py:45-68)
+ *   - test.{counttable,countgraph,smallcounttable,smallcountgraph,nodetable,nodegraph}
+ *     queries (kevlar/tests/test_sketch.py:17-29)
+ *   - the numeric pins of test_novel.py:179-194, test_filter.py:27-87, test_count.py:153-166.
+ *
+ * Call sites in the reference that each function stands in for are cited inline
+ * as kevlar/<file>:<line>.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KO_HASH_MURMUR 0
+#define KO_HASH_TWOBIT 1
+
+typedef struct ko_sketch {
+    int hasher;        /* KO_HASH_* */
+    int bits;          /* 8, 4 or 1 */
+    int ksize;
+    int n_tables;
+    uint64_t sizes[16];   /* buckets per table (primes) */
+    uint64_t nbytes[16];  /* allocated bytes per table */
+    uint8_t *tables[16];
+    uint64_t n_unique;    /* khmer _n_unique_kmers: adds that found >=1 empty bucket */
+    uint64_t n_occupied;  /* khmer _occupied_bins: non-zero buckets in table 0 */
+} ko_sketch;
+
+/* ------------------------------------------------------------------ hashing */
+
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+static inline uint64_t fmix64(uint64_t k)
+{
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+/* MurmurHash3_x64_128 (smhasher, public domain algorithm), low 64 bits only.
+ * khmer hashes table-type sketches with it (seed 0): SURVEY App. A.2. */
+uint64_t ko_murmur3_lo(const uint8_t *data, int len, uint32_t seed)
+{
+    const int nblocks = len / 16;
+    uint64_t h1 = seed, h2 = seed;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    for (int i = 0; i < nblocks; i++) {
+        uint64_t k1, k2;
+        memcpy(&k1, data + 16 * i, 8);
+        memcpy(&k2, data + 16 * i + 8, 8);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    const uint8_t *tail = data + nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    int rem = len & 15;
+    for (int i = rem - 1; i >= 8; i--) k2 ^= (uint64_t)tail[i] << (8 * (i - 8));
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int i = (rem > 8 ? 7 : rem - 1); i >= 0; i--) k1 ^= (uint64_t)tail[i] << (8 * i);
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+
+static inline int comp_base(int c)
+{
+    switch (c) {
+    case 'A': return 'T';
+    case 'T': return 'A';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    }
+    return -1;
+}
+
+/* khmer _hash_murmur: murmur(kmer) ^ murmur(revcomp(kmer)).  Stands in for
+ * Counttable.hash (kevlar/novel.py:145) and every implicit hash in get/add/consume.
+ * Returns 0 and sets *ok = 0 on a non-ACGT byte. */
+uint64_t ko_hash_murmur(const uint8_t *kmer, int k, int *ok)
+{
+    uint8_t rc[256];
+    if (k > 256) { if (ok) *ok = 0; return 0; }
+    for (int i = 0; i < k; i++) {
+        int c = comp_base(kmer[k - 1 - i]);
+        if (c < 0) { if (ok) *ok = 0; return 0; }
+        rc[i] = (uint8_t)c;
+    }
+    if (ok) *ok = 1;
+    return ko_murmur3_lo(kmer, k, 0) ^ ko_murmur3_lo(rc, k, 0);
+}
+
+static inline int twobit(int c)
+{
+    switch (c) {
+    case 'A': return 0;
+    case 'T': return 1;
+    case 'C': return 2;
+    case 'G': return 3;
+    }
+    return -1;
+}
+
+/* khmer _hash (2-bit, graph types): min(fwd, revcomp) with A=0,T=1,C=2,G=3,
+ * first base most significant. */
+uint64_t ko_hash_twobit(const uint8_t *kmer, int k, int *ok)
+{
+    uint64_t f = 0, r = 0;
+    if (k > 32) { if (ok) *ok = 0; return 0; }
+    for (int i = 0; i < k; i++) {
+        int c = twobit(kmer[i]);
+        if (c < 0) { if (ok) *ok = 0; return 0; }
+        f = (f << 2) | (uint64_t)c;
+        r |= (uint64_t)(c ^ 1) << (2 * i);
+    }
+    if (ok) *ok = 1;
+    return f < r ? f : r;
+}
+
+uint64_t ko_hash(int hasher, const uint8_t *kmer, int k, int *ok)
+{
+    return hasher == KO_HASH_TWOBIT ? ko_hash_twobit(kmer, k, ok) : ko_hash_murmur(kmer, k, ok);
+}
+
+/* reverse_hash for the 2-bit hasher (graph types only; kevlar/tests/test_sketch.py:50-52) */
+void ko_reverse_hash_twobit(uint64_t h, int k, char *out)
+{
+    static const char L[4] = {'A', 'T', 'C', 'G'};
+    for (int i = k - 1; i >= 0; i--) { out[i] = L[h & 3]; h >>= 2; }
+    out[k] = 0;
+}
+
+/* -------------------------------------------------------------- table sizes */
+
+static int is_prime(uint64_t n)
+{
+    if (n < 2) return 0;
+    if (n == 2) return 1;
+    if (n % 2 == 0) return 0;
+    for (uint64_t i = 3; i * i <= n; i += 2)
+        if (n % i == 0) return 0;
+    return 1;
+}
+
+/* khmer get_n_primes_near_x(n, x): the n largest primes strictly below x, walking
+ * down over odd numbers from x-1 (ctor called from kevlar/sketch.py:118). */
+int ko_primes_below(uint64_t x, int n, uint64_t *out)
+{
+    if (x < 3) return -1;
+    uint64_t i = x - 1;
+    if (i % 2 == 0) i--;
+    int found = 0;
+    while (found < n && i > 0) {
+        if (is_prime(i)) out[found++] = i;
+        if (i == 1) break;
+        i -= 2;
+    }
+    return found == n ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------ storage */
+
+static uint64_t table_bytes(int bits, uint64_t size)
+{
+    if (bits == 8) return size;
+    if (bits == 4) return size / 2 + 1;
+    return size / 8 + 1;
+}
+
+ko_sketch *ko_create(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes)
+{
+    if (n_tables < 1 || n_tables > 16) return NULL;
+    if (bits != 8 && bits != 4 && bits != 1) return NULL;
+    ko_sketch *s = (ko_sketch *)calloc(1, sizeof(ko_sketch));
+    s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables;
+    for (int t = 0; t < n_tables; t++) {
+        s->sizes[t] = sizes[t];
+        s->nbytes[t] = table_bytes(bits, sizes[t]);
+        s->tables[t] = (uint8_t *)calloc(s->nbytes[t], 1);
+        if (!s->tables[t]) return NULL;
+    }
+    return s;
+}
+
+void ko_destroy(ko_sketch *s)
+{
+    if (!s) return;
+    for (int t = 0; t < s->n_tables; t++) free(s->tables[t]);
+    free(s);
+}
+
+int ko_info(const ko_sketch *s, int *hasher, int *bits, int *ksize, int *n_tables, uint64_t *sizes)
+{
+    *hasher = s->hasher; *bits = s->bits; *ksize = s->ksize; *n_tables = s->n_tables;
+    for (int t = 0; t < s->n_tables; t++) sizes[t] = s->sizes[t];
+    return 0;
+}
+
+uint64_t ko_n_unique(const ko_sketch *s) { return s->n_unique; }
+uint64_t ko_n_occupied(const ko_sketch *s) { return s->n_occupied; }
+uint8_t *ko_table_ptr(ko_sketch *s, int t) { return s->tables[t]; }
+uint64_t ko_table_nbytes(const ko_sketch *s, int t) { return s->nbytes[t]; }
+
+/* recount table-0 occupancy from the bytes (used after load and by tests) */
+uint64_t ko_count_occupied(const ko_sketch *s)
+{
+    uint64_t n = 0;
+    const uint8_t *tb = s->tables[0];
+    for (uint64_t b = 0; b < s->sizes[0]; b++) {
+        if (s->bits == 8) n += tb[b] != 0;
+        else if (s->bits == 4) n += ((tb[b >> 1] >> ((b & 1) ? 0 : 4)) & 15) != 0;
+        else n += (tb[b >> 3] >> (b & 7)) & 1;
+    }
+    return n;
+}
+
+static inline unsigned get_bucket(const ko_sketch *s, int t, uint64_t bin)
+{
+    const uint8_t *tb = s->tables[t];
+    if (s->bits == 8) return tb[bin];
+    if (s->bits == 4) return (tb[bin >> 1] >> ((bin & 1) ? 0 : 4)) & 15; /* even bin -> high nibble */
+    return (tb[bin >> 3] >> (bin & 7)) & 1;
+}
+
+/* khmer Storage::get_count: min over tables (Counttable.get, kevlar/novel.py:38,48) */
+unsigned ko_get_hash(const ko_sketch *s, uint64_t h)
+{
+    unsigned m = 0xffffffffu;
+    for (int t = 0; t < s->n_tables; t++) {
+        unsigned c = get_bucket(s, t, h % s->sizes[t]);
+        if (c < m) m = c;
+    }
+    return m;
+}
+
+/* khmer Storage::add, single-threaded semantics: saturating
+ * increment of one bucket per table; returns 1 if any bucket was empty. */
+int ko_add_hash(ko_sketch *s, uint64_t h)
+{
+    int is_new = 0;
+    for (int t = 0; t < s->n_tables; t++) {
+        uint64_t bin = h % s->sizes[t];
+        uint8_t *tb = s->tables[t];
+        if (s->bits == 8) {
+            if (tb[bin] == 0) { is_new = 1; if (t == 0) s->n_occupied++; }
+            if (tb[bin] < 255) tb[bin]++;
+        } else if (s->bits == 4) {
+            int shift = (bin & 1) ? 0 : 4;
+            unsigned c = (tb[bin >> 1] >> shift) & 15;
+            if (c == 0) { is_new = 1; if (t == 0) s->n_occupied++; }
+            if (c < 15) tb[bin >> 1] = (uint8_t)((tb[bin >> 1] & ~(15u << shift)) | ((c + 1) << shift));
+        } else {
+            uint8_t bit = (uint8_t)(1u << (bin & 7));
+            if (!(tb[bin >> 3] & bit)) { is_new = 1; if (t == 0) s->n_occupied++; }
+            tb[bin >> 3] |= bit;
+        }
+    }
+    if (is_new) s->n_unique++;
+    return is_new;
+}
+
+/* thread-safe variant used by the timed multi-threaded CPU baseline: CAS so the
+ * result stays exact (khmer's own check-then-__sync_add can overshoot at 255). */
+static void add_hash_atomic(ko_sketch *s, uint64_t h)
+{
+    for (int t = 0; t < s->n_tables; t++) {
+        uint64_t bin = h % s->sizes[t];
+        uint8_t *tb = s->tables[t];
+        if (s->bits == 8) {
+            uint8_t old = __atomic_load_n(&tb[bin], __ATOMIC_RELAXED);
+            while (old < 255 &&
+                   !__atomic_compare_exchange_n(&tb[bin], &old, (uint8_t)(old + 1), 1,
+                                                __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { }
+        } else if (s->bits == 4) {
+            int shift = (bin & 1) ? 0 : 4;
+            uint8_t old = __atomic_load_n(&tb[bin >> 1], __ATOMIC_RELAXED);
+            for (;;) {
+                unsigned c = (old >> shift) & 15;
+                if (c >= 15) break;
+                uint8_t nw = (uint8_t)((old & ~(15u << shift)) | ((c + 1) << shift));
+                if (__atomic_compare_exchange_n(&tb[bin >> 1], &old, nw, 1, __ATOMIC_RELAXED,
+                                                __ATOMIC_RELAXED)) break;
+            }
+        } else {
+            __atomic_fetch_or(&tb[bin >> 3], (uint8_t)(1u << (bin & 7)), __ATOMIC_RELAXED);
+        }
+    }
+}
+
+/* ------------------------------------------------------------ banding / mask */
+
+/* khmer compute_band_interval (used by consume_seqfile_banding,
+ * kevlar/count.py:62-66) */
+int ko_band_interval(int num_bands, int band, uint64_t *lo, uint64_t *hi)
+{
+    if (num_bands <= 0 || band < 0 || band >= num_bands) return -1;
+    uint64_t size = UINT64_MAX / (uint64_t)num_bands;
+    *lo = size * (uint64_t)band;
+    *hi = size * (uint64_t)(band + 1);
+    if (band == num_bands - 1) *hi = UINT64_MAX;
+    return 0;
+}
+
+/* with a mask, count the k-mer iff
+ *   consume_masked == 0:  mask.get(h) <= threshold
+ *   consume_masked != 0:  mask.get(h) >= threshold          (kevlar/count.py:44-48) */
+static inline int mask_pass(const ko_sketch *mask, uint64_t h, int threshold, int consume_masked)
+{
+    if (!mask) return 1;
+    int c = (int)ko_get_hash(mask, h);
+    return consume_masked ? (c >= threshold) : (c <= threshold);
+}
+
+/* khmer Read::set_clean_seq: upper-case acgt, everything else -> 'A' */
+static inline uint8_t clean_base(uint8_t c)
+{
+    switch (c) {
+    case 'A': case 'C': case 'G': case 'T': return c;
+    case 'a': return 'A';
+    case 'c': return 'C';
+    case 'g': return 'G';
+    case 't': return 'T';
+    }
+    return 'A';
+}
+
+/* Rolling window hash of one cleaned read; calls cb for each k-mer hash in order. */
+typedef void (*hash_cb)(void *ctx, uint64_t h);
+
+static void for_each_hash(int hasher, int k, const uint8_t *seq, uint64_t len, hash_cb cb, void *ctx)
+{
+    if (len < (uint64_t)k) return;
+    if (hasher == KO_HASH_TWOBIT) {
+        uint64_t f = 0, r = 0, mask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+        for (uint64_t i = 0; i < len; i++) {
+            uint64_t c = (uint64_t)twobit(seq[i]);
+            f = ((f << 2) | c) & mask;
+            r = (r >> 2) | ((c ^ 1) << (2 * (k - 1)));
+            if (i + 1 >= (uint64_t)k) cb(ctx, f < r ? f : r);
+        }
+    } else {
+        for (uint64_t i = 0; i + k <= len; i++) {
+            int ok;
+            cb(ctx, ko_hash_murmur(seq + i, k, &ok));
+        }
+    }
+}
+
+typedef struct {
+    ko_sketch *s;
+    const ko_sketch *mask;
+    int threshold, consume_masked;
+    int banded;
+    uint64_t lo, hi;
+    int atomic;
+    uint64_t n_consumed;
+} consume_ctx;
+
+static void consume_cb(void *vctx, uint64_t h)
+{
+    consume_ctx *c = (consume_ctx *)vctx;
+    if (c->banded && !(h >= c->lo && h < c->hi)) return;
+    if (!mask_pass(c->mask, h, c->threshold, c->consume_masked)) return;
+    if (c->atomic) add_hash_atomic(c->s, h); else ko_add_hash(c->s, h);
+    c->n_consumed++;
+}
+
+/* khmer consume_seqfile / _banding / _with_mask / _banding_with_mask applied to ONE
+ * read's sequence (kevlar/count.py:50-71).  num_bands <= 0 means unbanded.
+ * Returns the number of k-mers counted. */
+uint64_t ko_consume_read(ko_sketch *s, const uint8_t *seq, uint64_t len, int num_bands, int band,
+                         const ko_sketch *mask, int threshold, int consume_masked)
+{
+    consume_ctx c = {s, mask, threshold, consume_masked, 0, 0, 0, 0, 0};
+    if (num_bands > 0) {
+        if (ko_band_interval(num_bands, band, &c.lo, &c.hi)) return 0;
+        c.banded = 1;
+    }
+    if (len < (uint64_t)s->ksize) return 0;
+    uint8_t stackbuf[512];
+    uint8_t *buf = len <= sizeof stackbuf ? stackbuf : (uint8_t *)malloc(len);
+    for (uint64_t i = 0; i < len; i++) buf[i] = clean_base(seq[i]);
+    for_each_hash(s->hasher, s->ksize, buf, len, consume_cb, &c);
+    if (buf != stackbuf) free(buf);
+    return c.n_consumed;
+}
+
+/* A batch = concatenated bases + n_reads+1 offsets (same layout the product's
+ * C-ABI takes).  n_threads == 1 reproduces khmer's single-threaded file order
+ * (the only order for which n_unique_kmers is canonical);
+ * n_threads > 1 mimics kevlar/count.py:40-77 (threads pulling reads off one
+ * parser) and is what the timed CPU baseline uses. */
+typedef struct {
+    ko_sketch *s;
+    const uint8_t *bases;
+    const uint64_t *offs;
+    uint64_t n_reads;
+    int num_bands, band;
+    const ko_sketch *mask;
+    int threshold, consume_masked;
+    uint64_t next;       /* shared cursor */
+    uint64_t consumed;   /* shared total */
+} batch_job;
+
+static void *batch_worker(void *vj)
+{
+    batch_job *j = (batch_job *)vj;
+    consume_ctx c = {j->s, j->mask, j->threshold, j->consume_masked, 0, 0, 0, 1, 0};
+    if (j->num_bands > 0) { ko_band_interval(j->num_bands, j->band, &c.lo, &c.hi); c.banded = 1; }
+    uint8_t *buf = NULL; uint64_t cap = 0;
+    for (;;) {
+        uint64_t r0 = __atomic_fetch_add(&j->next, 256, __ATOMIC_RELAXED);
+        if (r0 >= j->n_reads) break;
+        uint64_t r1 = r0 + 256 < j->n_reads ? r0 + 256 : j->n_reads;
+        for (uint64_t r = r0; r < r1; r++) {
+            uint64_t len = j->offs[r + 1] - j->offs[r];
+            if (len < (uint64_t)j->s->ksize) continue;
+            if (len > cap) { cap = len * 2; buf = (uint8_t *)realloc(buf, cap); }
+            const uint8_t *src = j->bases + j->offs[r];
+            for (uint64_t i = 0; i < len; i++) buf[i] = clean_base(src[i]);
+            for_each_hash(j->s->hasher, j->s->ksize, buf, len, consume_cb, &c);
+        }
+    }
+    free(buf);
+    __atomic_fetch_add(&j->consumed, c.n_consumed, __ATOMIC_RELAXED);
+    return NULL;
+}
+
+uint64_t ko_consume_batch(ko_sketch *s, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
+                          int num_bands, int band, const ko_sketch *mask, int threshold,
+                          int consume_masked, int n_threads)
+{
+    if (n_threads <= 1) {
+        uint64_t n = 0;
+        for (uint64_t r = 0; r < n_reads; r++)
+            n += ko_consume_read(s, bases + offs[r], offs[r + 1] - offs[r], num_bands, band, mask,
+                                 threshold, consume_masked);
+        return n;
+    }
+    batch_job j = {s, bases, offs, n_reads, num_bands, band, mask, threshold, consume_masked, 0, 0};
+    pthread_t th[256];
+    if (n_threads > 256) n_threads = 256;
+    for (int i = 0; i < n_threads; i++) pthread_create(&th[i], NULL, batch_worker, &j);
+    for (int i = 0; i < n_threads; i++) pthread_join(th[i], NULL);
+    s->n_occupied = ko_count_occupied(s);   /* n_unique is not canonical when threaded */
+    return j.consumed;
+}
+
+/* --------------------------------------------------------------- novel scan */
+
+typedef struct {
+    uint64_t read;      /* read index within the batch */
+    uint32_t offset;    /* k-mer offset within the read */
+    uint8_t abund[12];  /* case abundances then control abundances */
+} ko_hit;
+
+/* Restates the per-read body of kevlar.novel.novel (kevlar/novel.py:134-169) and
+ * kmer_is_interesting (kevlar/novel.py:21-53) for one read.
+ *   flags bit0: read skipped (shorter than k or contains [^ACGT])   novel.py:134-139
+ *   flags bit1: read discarded by the abundance screen               novel.py:152-154
+ * Hits found before a discard are still reported (the reference adds their k-mers
+ * to its unique set before breaking, novel.py:157-162).
+ * band_quirk: novel.py:144-147 keeps a k-mer iff (hash & (numbands-1)) == band-1
+ * where band is the already 0-based value; pass numbands<=0 for none.
+ * Returns number of hits written (<= max_hits). */
+uint64_t ko_novel_read(const ko_sketch *const *cases, int n_case, const ko_sketch *const *ctrls,
+                       int n_ctrl, const uint8_t *seq, uint64_t len, int case_min, int ctrl_max,
+                       int screen /* <=0: off */, int numbands, int64_t band_minus_1,
+                       uint64_t read_index, ko_hit *hits, uint64_t max_hits, uint8_t *flags)
+{
+    const ko_sketch *c0 = cases[0];
+    int k = c0->ksize;
+    *flags = 0;
+    if (len < (uint64_t)k) { *flags = 1; return 0; }
+    for (uint64_t i = 0; i < len; i++)
+        if (seq[i] != 'A' && seq[i] != 'C' && seq[i] != 'G' && seq[i] != 'T') { *flags = 1; return 0; }
+    uint64_t nh = 0;
+    for (uint64_t i = 0; i + k <= len; i++) {
+        int ok;
+        uint64_t h = ko_hash(c0->hasher, seq + i, k, &ok);
+        if (numbands > 0) {
+            int64_t lowbits = (int64_t)(h & (uint64_t)(numbands - 1));
+            if (lowbits != band_minus_1) continue;
+        }
+        uint8_t ab[12];
+        int interesting = 1, discard = 0;
+        for (int s = 0; s < n_case; s++) {
+            unsigned a = ko_get_hash(cases[s], h);
+            if ((int)a < case_min) {
+                interesting = 0;
+                if (screen > 0 && (int)a < screen) discard = 1;
+                break;
+            }
+            ab[s] = (uint8_t)a;
+        }
+        if (discard) { *flags |= 2; break; }
+        if (!interesting) continue;
+        for (int s = 0; s < n_ctrl; s++) {
+            unsigned a = ko_get_hash(ctrls[s], h);
+            if ((int)a > ctrl_max) { interesting = 0; break; }
+            ab[n_case + s] = (uint8_t)a;
+        }
+        if (!interesting) continue;
+        if (nh < max_hits) {
+            hits[nh].read = read_index;
+            hits[nh].offset = (uint32_t)i;
+            memcpy(hits[nh].abund, ab, 12);
+        }
+        nh++;
+    }
+    return nh;
+}
+
+typedef struct {
+    const ko_sketch *const *cases; int n_case;
+    const ko_sketch *const *ctrls; int n_ctrl;
+    const uint8_t *bases; const uint64_t *offs; uint64_t n_reads;
+    int case_min, ctrl_max, screen, numbands; int64_t band_minus_1;
+    ko_hit *hits; uint64_t max_hits; uint8_t *flags;
+    uint64_t next; uint64_t n_hits; pthread_mutex_t mu;
+} novel_job;
+
+static void *novel_worker(void *vj)
+{
+    novel_job *j = (novel_job *)vj;
+    ko_hit local[4096];
+    for (;;) {
+        uint64_t r0 = __atomic_fetch_add(&j->next, 128, __ATOMIC_RELAXED);
+        if (r0 >= j->n_reads) break;
+        uint64_t r1 = r0 + 128 < j->n_reads ? r0 + 128 : j->n_reads;
+        for (uint64_t r = r0; r < r1; r++) {
+            uint64_t len = j->offs[r + 1] - j->offs[r];
+            uint64_t nh = ko_novel_read(j->cases, j->n_case, j->ctrls, j->n_ctrl, j->bases + j->offs[r],
+                                        len, j->case_min, j->ctrl_max, j->screen, j->numbands,
+                                        j->band_minus_1, r, local, 4096, &j->flags[r]);
+            if (nh > 4096) nh = 4096;
+            if (nh) {
+                pthread_mutex_lock(&j->mu);
+                for (uint64_t i = 0; i < nh; i++) {
+                    if (j->n_hits < j->max_hits) j->hits[j->n_hits] = local[i];
+                    j->n_hits++;
+                }
+                pthread_mutex_unlock(&j->mu);
+            }
+        }
+    }
+    return NULL;
+}
+
+/* Whole-batch scan; hits come back unordered when n_threads > 1 (sort by (read, offset)). */
+uint64_t ko_novel_batch(const ko_sketch *const *cases, int n_case, const ko_sketch *const *ctrls,
+                        int n_ctrl, const uint8_t *bases, const uint64_t *offs, uint64_t n_reads,
+                        int case_min, int ctrl_max, int screen, int numbands, int64_t band_minus_1,
+                        ko_hit *hits, uint64_t max_hits, uint8_t *flags, int n_threads)
+{
+    novel_job j = {cases, n_case, ctrls, n_ctrl, bases, offs, n_reads, case_min, ctrl_max, screen,
+                   numbands, band_minus_1, hits, max_hits, flags, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads == 1) { novel_worker(&j); return j.n_hits; }
+    pthread_t th[256];
+    for (int i = 0; i < n_threads; i++) pthread_create(&th[i], NULL, novel_worker, &j);
+    for (int i = 0; i < n_threads; i++) pthread_join(th[i], NULL);
+    return j.n_hits;
+}
+
+/* ------------------------------------------------------------- OXLI v4 file */
+
+/* khmer Storage::save, called from kevlar/count.py:95, novel.py:92. */
+int ko_save(const ko_sketch *s, const char *path)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    uint8_t version = 4, type = s->bits == 8 ? 1 : (s->bits == 4 ? 7 : 2);
+    fwrite("OXLI", 1, 4, f);
+    fwrite(&version, 1, 1, f);
+    fwrite(&type, 1, 1, f);
+    if (s->bits == 8) { uint8_t big = 0; fwrite(&big, 1, 1, f); }
+    uint32_t k = (uint32_t)s->ksize;
+    uint8_t nt = (uint8_t)s->n_tables;
+    fwrite(&k, 4, 1, f);
+    fwrite(&nt, 1, 1, f);
+    uint64_t occ = s->n_occupied;
+    fwrite(&occ, 8, 1, f);
+    for (int t = 0; t < s->n_tables; t++) {
+        fwrite(&s->sizes[t], 8, 1, f);
+        fwrite(s->tables[t], 1, s->nbytes[t], f);
+    }
+    if (s->bits == 8) { uint64_t nbig = 0; fwrite(&nbig, 8, 1, f); }
+    int rc = ferror(f) ? -1 : 0;
+    fclose(f);
+    return rc;
+}
+
+/* khmer Storage::load (kevlar/sketch.py:14-27,77-92).  The file does not record
+ * table-vs-graph, so the caller supplies the hasher (kevlar infers it from the
+ * extension).  Returns NULL and fills err on failure. */
+ko_sketch *ko_load(const char *path, int hasher, int expect_bits, char *err, int errlen)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) { snprintf(err, errlen, "cannot open %s", path); return NULL; }
+    uint8_t head[6];
+    if (fread(head, 1, 6, f) != 6 || memcmp(head, "OXLI", 4)) {
+        snprintf(err, errlen, "%s: not an OXLI file", path); fclose(f); return NULL;
+    }
+    if (head[4] != 4) { snprintf(err, errlen, "%s: unsupported version %d", path, head[4]); fclose(f); return NULL; }
+    int bits = head[5] == 1 ? 8 : head[5] == 7 ? 4 : head[5] == 2 ? 1 : 0;
+    if (!bits || (expect_bits && bits != expect_bits)) {
+        snprintf(err, errlen, "%s: unexpected table type %d", path, head[5]); fclose(f); return NULL;
+    }
+    if (bits == 8) { uint8_t big; if (fread(&big, 1, 1, f) != 1) goto trunc; }
+    uint32_t k; uint8_t nt; uint64_t occ;
+    if (fread(&k, 4, 1, f) != 1 || fread(&nt, 1, 1, f) != 1 || fread(&occ, 8, 1, f) != 1) goto trunc;
+    if (nt < 1 || nt > 16) { snprintf(err, errlen, "%s: bad table count", path); fclose(f); return NULL; }
+    {
+        ko_sketch *s = (ko_sketch *)calloc(1, sizeof(ko_sketch));
+        s->hasher = hasher; s->bits = bits; s->ksize = (int)k; s->n_tables = nt; s->n_occupied = occ;
+        for (int t = 0; t < nt; t++) {
+            if (fread(&s->sizes[t], 8, 1, f) != 1) { ko_destroy(s); goto trunc; }
+            s->nbytes[t] = table_bytes(bits, s->sizes[t]);
+            s->tables[t] = (uint8_t *)malloc(s->nbytes[t]);
+            if (fread(s->tables[t], 1, s->nbytes[t], f) != s->nbytes[t]) { ko_destroy(s); goto trunc; }
+        }
+        fclose(f);
+        return s;
+    }
+trunc:
+    snprintf(err, errlen, "%s: truncated file", path);
+    fclose(f);
+    return NULL;
+}
