@@ -1,0 +1,187 @@
+/*
+ * kvsketch.h -- C ABI of libkvsketch.so: the B200 (sm_100a) implementation of the khmer
+ * sketch operations that kevlar's `count` -> `novel` -> `filter` path calls.
+ *
+ * The drop-in boundary of the reference is the `khmer` Python namespace (SURVEY.md 8b;
+ * /root/reference has no FFI of its own -- khmer is a Cython/C++ dependency).  Each entry
+ * point below names the khmer call, and the kevlar call site (file:line under
+ * /root/reference), that it replaces.  The host-side mirror that binds these with ctypes is
+ * kevlar_b200/khmer/; INTEGRATION.md shows the binding a kevlar maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 on success or a negative
+ *    KV_E* code, with a human-readable message available from kv_last_error() (thread local).
+ *  - there is NO CPU fallback: every call that computes fails with KV_ENODEVICE when no
+ *    CUDA device is usable.
+ *  - a "batch" is `bases` = the concatenated sequence bytes of n_reads reads (ASCII, as read
+ *    from FASTA/FASTQ) and `offsets` = n_reads+1 uint64 byte offsets into it.  `where` says
+ *    whether both pointers are host (KV_MEM_HOST; pinned memory recommended) or device
+ *    (KV_MEM_DEVICE) pointers.
+ *  - work is enqueued on the library's per-device stream (kv_stream); calls that return
+ *    values to the host synchronise, the others are asynchronous: host batch buffers must
+ *    stay valid until kv_sync().
+ *  - handles are caller-owned.  A sketch may be consumed into from several host threads
+ *    (increments commute; calls are serialised per device); kv_sketch_save/stats need
+ *    quiescence.
+ */
+#ifndef KVSKETCH_H
+#define KVSKETCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KV_ABI_VERSION 1
+
+/* hash function: khmer *table types use MurmurHash3, *graph types the 2-bit encoding */
+#define KV_HASH_MURMUR 0 /* Counttable / SmallCounttable / Nodetable   (kevlar/sketch.py:107-116) */
+#define KV_HASH_TWOBIT 1 /* Countgraph / SmallCountgraph / Nodegraph   (kevlar/sketch.py:102-106) */
+
+#define KV_MEM_HOST 0
+#define KV_MEM_DEVICE 1
+
+#define KV_MAX_TABLES 16
+#define KV_MAX_SAMPLES 16 /* case + control sketches in one novel scan */
+#define KV_MAX_KSIZE_MURMUR 64
+#define KV_MAX_KSIZE_TWOBIT 32
+
+#define KV_OK 0
+#define KV_EINVAL (-1)    /* bad argument                      -> ValueError */
+#define KV_EIO (-2)       /* unreadable / malformed sketch file -> OSError    */
+#define KV_ENOMEM (-3)    /* host or device allocation failed  -> MemoryError */
+#define KV_ECUDA (-4)     /* CUDA runtime error                -> RuntimeError */
+#define KV_ENODEVICE (-5) /* no usable CUDA device             -> RuntimeError */
+#define KV_EOVERFLOW (-6) /* output buffer too small           -> RuntimeError */
+
+typedef struct kv_sketch kv_sketch;
+
+/* one interesting k-mer found by kv_novel_batch (kevlar/novel.py:157-162: irecord.annotate) */
+typedef struct kv_hit {
+    uint32_t read;                  /* read index within the batch */
+    uint32_t offset;                /* k-mer offset within the read */
+    uint8_t abund[KV_MAX_SAMPLES];  /* case abundances, then control abundances */
+} kv_hit;
+
+/* per-read flags written by kv_novel_batch */
+#define KV_READ_SKIPPED 1u   /* shorter than k, or contains a byte outside ACGT (kevlar/novel.py:134-139) */
+#define KV_READ_DISCARDED 2u /* abundance screen tripped (kevlar/novel.py:152-154) */
+
+const char *kv_last_error(void);
+int kv_abi_version(void);
+int kv_device_count(int *n);
+
+/* khmer get_n_primes_near_x(n, x) -- the table sizes every khmer constructor derives from
+ * `starting_size` (kevlar/sketch.py:118, kevlar/filter.py:29).  Host arithmetic. */
+int kv_primes_below(uint64_t x, int n, uint64_t *out);
+
+/* khmer.{Count,SmallCount,Node}{table,graph}(ksize, starting_size, n_tables) with the table
+ * sizes already chosen (kevlar/sketch.py:99-119).  bits = 8 | 4 | 1.  Zero-filled tables are
+ * allocated in the HBM of `device`. */
+int kv_sketch_create(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int device,
+                     kv_sketch **out);
+int kv_sketch_destroy(kv_sketch *s);
+
+/* khmer <Type>.load(filename) / .save(filename): OXLI v4 files (kevlar/sketch.py:14-27,77-92;
+ * kevlar/count.py:95; kevlar/novel.py:92).  The file does not record table-vs-graph, so the
+ * caller passes the hasher; expect_bits (8|4|1, or 0 for any) is checked against the file. */
+int kv_sketch_load(const char *path, int hasher, int expect_bits, int device, kv_sketch **out);
+int kv_sketch_save(kv_sketch *s, const char *path);
+
+/* .ksize() / .hashsizes() / n_tables (kevlar/sketch.py:68) */
+int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *ksize, int *n_tables, uint64_t *sizes,
+                   int *device);
+
+/* .n_occupied() and .n_unique_kmers() (kevlar/sketch.py:70, kevlar/count.py:84).
+ * n_unique is exact (khmer's single-threaded, file-order value) when unique tracking was on
+ * for every consume since creation; otherwise *n_unique_valid is 0. */
+int kv_sketch_stats(kv_sketch *s, uint64_t *n_occupied, uint64_t *n_unique, int *n_unique_valid);
+
+/* Turn the exact n_unique_kmers bookkeeping on/off (default on; costs a u32 per bucket of
+ * scratch HBM and one extra probe pass per batch). */
+int kv_sketch_set_unique_tracking(kv_sketch *s, int on);
+
+/* Raw table storage, for collectives that the host runs over it (torch.distributed/NCCL)
+ * and for tests: device pointer and byte length of table t, khmer layout.
+ * All tables of a sketch live in ONE allocation; kv_sketch_flat gives that allocation. */
+int kv_sketch_table(kv_sketch *s, int t, void **dev_ptr, uint64_t *nbytes);
+int kv_sketch_flat(kv_sketch *s, void **dev_ptr, uint64_t *nbytes);
+int kv_sketch_read_table(kv_sketch *s, int t, uint8_t *host_out, uint64_t nbytes);   /* D2H copy */
+int kv_sketch_write_table(kv_sketch *s, int t, const uint8_t *host_in, uint64_t nbytes);
+
+/* .consume_seqfile / .consume_seqfile_banding / .consume_seqfile_with_mask /
+ * .consume_seqfile_banding_with_mask applied to one batch of reads (kevlar/count.py:50-71,
+ * kevlar/sketch.py:148-152) and .consume(seq) (one-read batch).
+ *   num_bands <= 0: unbanded; otherwise keep hashes in khmer's band interval (0-based band).
+ *   mask == NULL: none; otherwise count a k-mer iff
+ *       consume_masked == 0:  mask.get(hash) <= mask_threshold
+ *       consume_masked != 0:  mask.get(hash) >= mask_threshold          
+ *   n_kmers_out: if non-NULL the call synchronises and returns the number of k-mers counted
+ *   (khmer's n_consumed); if NULL the call is asynchronous. */
+int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                     int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
+                     int consume_masked, uint64_t *n_kmers_out);
+
+/* The read loop of kevlar.novel.novel + kmer_is_interesting (kevlar/novel.py:21-53,123-169)
+ * for one batch: every k-mer of every read is hashed once and looked up in all case and
+ * control sketches in one pass.
+ *   screen <= 0: no abundance screen.   num_bands <= 0: no band filter; otherwise keep a
+ *   k-mer iff (hash & (num_bands-1)) == band_minus_1 -- the reference's bit test on the
+ *   already 0-based band, reproduced as is (kevlar/novel.py:144-147).
+ * Outputs (host pointers): hits[0..*n_hits) sorted by (read, offset); read_flags[n_reads];
+ * discard_pos[n_reads] (may be NULL when screen <= 0) = offset of the first k-mer that
+ * tripped the screen or 0xFFFFFFFF.  Hits of skipped reads are not reported; hits that follow
+ * a read's discard position are not reported (the reference breaks out of the read there).
+ * Returns KV_EOVERFLOW (and the required count in *n_hits) if max_hits is too small. */
+int kv_novel_batch(const kv_sketch *const *cases, int n_case, const kv_sketch *const *ctrls, int n_ctrl,
+                   const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where, int case_min,
+                   int ctrl_max, int screen, int num_bands, int64_t band_minus_1, kv_hit *hits,
+                   uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos);
+
+/* .hash(kmer) for n k-mers of length ksize laid out back to back (kevlar/novel.py:145).
+ * ok[i] = 0 where the k-mer holds a byte outside ACGT (khmer raises there). */
+int kv_hash_kmers(int hasher, int ksize, const uint8_t *kmers, uint64_t n, int device, uint64_t *hashes_out,
+                  uint8_t *ok_out);
+
+/* .get(hash) / .add(hash) for n hashes, host arrays (kevlar/novel.py:38,48; kevlar/filter.py:32-34,67).
+ * kv_add_hashes applies them in array order for the n_unique bookkeeping. */
+int kv_get_hashes(const kv_sketch *s, const uint64_t *hashes, uint64_t n, uint8_t *counts_out);
+int kv_add_hashes(kv_sketch *s, const uint64_t *hashes, uint64_t n);
+
+/* .get_kmer_counts(seq) / .get_kmer_hashes(seq) for a batch: one value per base position
+ * (positions that do not start a k-mer get 0 and valid[i] = 0).  Host outputs, any may be NULL.
+ * (kevlar/simlike.py:23-29; kevlar/tests/test_novel.py:76) */
+int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                         int where, uint64_t *hashes_out, uint8_t *counts_out, uint8_t *valid_out);
+
+/* Multi-GPU merge of per-GPU partial sketches (plan A).  The host runs the
+ * collective (NCCL via torch.distributed) on a widened copy between these two kernels:
+ *   kv_sketch_widen:  counters -> one uint16 (8-bit), uint8 (4-bit: one per nibble) or
+ *                     uint8 (1-bit: the raw bytes, merge = bitwise OR) element per bucket,
+ *                     written to dev_out (device pointer, *n_elems elements).
+ *   kv_sketch_narrow: summed elements -> clamp to 255 / 15 / (bytes as is) and store back.
+ * kv_sketch_merge_peers does the same in ONE kernel over peer-mapped tables of the other
+ * GPUs (device pointers valid on this device, e.g. from CUDA IPC): saturating add of
+ * n_peers flat tables into this sketch. */
+int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, int *elem_bytes);
+int kv_sketch_narrow(kv_sketch *s, const void *dev_in);
+int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers);
+/* CUDA IPC plumbing for kv_sketch_merge_peers: export this sketch's flat allocation
+ * (64-byte handle) / map a peer's.  */
+int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);
+int kv_ipc_open(int device, const uint8_t handle[64], void **dev_ptr);
+int kv_ipc_close(int device, void *dev_ptr);
+
+/* Stream plumbing: the cudaStream_t all work for `device` is enqueued on, so a host
+ * framework can record events on it; kv_sync waits for it. */
+int kv_stream(int device, void **cuda_stream);
+int kv_sync(int device);
+
+/* Number of kernels this library has launched on `device` since load (bench accounting). */
+int kv_launch_count(int device, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVSKETCH_H */

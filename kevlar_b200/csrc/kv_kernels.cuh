@@ -1,0 +1,399 @@
+// kv_kernels.cuh -- the sm_100a kernels behind libkvsketch.so.
+//
+//   K0  kv_tile_index_kernel   which read does each 1024-base tile start in
+//   K1/K2 kv_hash_kernel       clean + (2-bit pack) + canonical hash per base position,
+//                              band and mask predicates fused; writes hashes + valid bits
+//   K3  kv_increment_kernel    saturating 8/4/1-bit Count-Min / Bloom update (khmer Storage::add)
+//   K4  kv_novel_kernel        fused hash + case/control lookups + thresholds (kevlar/novel.py:21-53,123-169)
+//   K5  kv_unique_probe/resolve_kernel, kv_occupied_kernel   n_unique_kmers / n_occupied bookkeeping
+//   K6  kv_widen/narrow/merge_peers kernels   multi-GPU saturating merge
+//   +   kv_get_kernel          min-over-tables lookups for explicit hashes
+#pragma once
+#include "kv_device.cuh"
+
+// ----------------------------------------------------------------------- K0
+
+// tile_first[i] = min(first read r with offsets[r+1] > i*KV_TILE, n_reads-1), i in [0, n_tiles]
+__global__ void kv_tile_index_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads, uint64_t n_tiles,
+                                     uint32_t *__restrict__ tile_first)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_tiles) return;
+    uint64_t pos = i * KV_TILE;
+    uint64_t lo = 0, hi = n_reads - 1;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid + 1) > pos) hi = mid; else lo = mid + 1;
+    }
+    tile_first[i] = (uint32_t)lo;
+}
+
+// -------------------------------------------------------------------- K1/K2
+
+struct KvHashParams {
+    const uint8_t *bases;
+    const uint64_t *offsets;
+    const uint32_t *tile_first;
+    uint64_t total;        // bases in the batch
+    uint64_t tile0;        // first tile of this chunk; outputs are indexed relative to tile0*KV_TILE
+    int k;
+    int banded;            // khmer range banding (App. A.7): keep lo <= h < hi
+    uint64_t band_lo, band_hi;
+    int use_mask;          // App. A.8
+    int mask_threshold, consume_masked;
+    KvView mask;
+    int strict;            // 1: k-mers touching a byte outside ACGT are invalid (kv_hash_kmers ok[])
+    uint64_t *hashes;      // [chunk positions] (may be NULL)
+    uint32_t *valid;       // [chunk positions / 32] bit: position starts a k-mer that passed the filters
+    unsigned long long *n_valid;   // running count of valid k-mers (khmer n_consumed)
+};
+
+template <int HASHER, int KW>
+__global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
+{
+    __shared__ KvTileSmem sm;
+    const uint64_t tile = p.tile0 + blockIdx.x;
+    const uint64_t tile_start = tile * KV_TILE;
+    const uint64_t pos0 = p.tile0 * KV_TILE;
+    kv_tile_load<HASHER == KV_HASH_TWOBIT, true>(sm, p.bases, tile_start, p.total);
+    kv_tile_bounds(sm, p.offsets, p.tile_first, tile);
+    __syncthreads();
+
+    unsigned n_ok = 0;
+#pragma unroll 1
+    for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
+        const int l = it * KV_THREADS + threadIdx.x;
+        const uint64_t g = tile_start + l;
+        bool ok = false;
+        uint64_t h = 0;
+        if (g < p.total) {
+            uint64_t read, rs, re;
+            kv_find_read(sm, p.offsets, p.tile_first, tile, g, read, rs, re);
+            ok = g + p.k <= re;
+            if (ok && p.strict) ok = !kv_window_bad(sm, l + KV_FRONT, p.k);
+            if (ok) {
+                h = kv_tile_hash<HASHER, KW>(sm, l, p.k);
+                if (p.banded) ok = h >= p.band_lo && h < p.band_hi;
+                if (ok && p.use_mask) {
+                    int c = (int)kv_get(p.mask, h);
+                    ok = p.consume_masked ? (c >= p.mask_threshold) : (c <= p.mask_threshold);
+                }
+            }
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (g < p.total) {
+            if (p.hashes) p.hashes[g - pos0] = h;
+            if ((threadIdx.x & 31) == 0) p.valid[(g - pos0) >> 5] = bal;
+        }
+        n_ok += ok;
+    }
+    // one atomic per CTA for the k-mer count
+    n_ok = __reduce_add_sync(0xffffffffu, n_ok);
+    __shared__ unsigned s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && n_ok) atomicAdd(&s_cnt, n_ok);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(p.n_valid, (unsigned long long)s_cnt);
+}
+
+// ----------------------------------------------------------------------- K3
+
+// One thread per base position (grid-stride).  For every valid k-mer: T bins by Barrett
+// reduction, the T counter words are fetched first (independent loads in flight), then each
+// is bumped with the CAS-saturating update.
+template <int BITS>
+__global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
+                                                           const uint32_t *__restrict__ valid, uint64_t total)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
+        uint32_t vw = __ldg(valid + (g >> 5));
+        if (!((vw >> (g & 31)) & 1u)) continue;
+        const uint64_t h = __ldcs(hashes + g);
+        if (v.n_tables == 4) {
+            unsigned *w[4], sh[4], old[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w[t], sh[t]);
+                old[t] = __ldcg(w[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) kv_sat_inc<BITS>(w[t], sh[t], old[t]);
+        } else {
+            for (int t = 0; t < v.n_tables; t++) {
+                unsigned *w, sh;
+                kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w, sh);
+                kv_sat_inc<BITS>(w, sh, __ldcg(w));
+            }
+        }
+    }
+}
+
+// same update for an explicit hash list (kv_add_hashes; kevlar/filter.py:34)
+template <int BITS>
+__global__ void kv_add_hashes_kernel(KvView v, const uint64_t *__restrict__ hashes, uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t h = hashes[i];
+        for (int t = 0; t < v.n_tables; t++) {
+            unsigned *w, sh;
+            kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w, sh);
+            kv_sat_inc<BITS>(w, sh, __ldcg(w));
+        }
+    }
+}
+
+__global__ void kv_get_kernel(KvView v, const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ valid,
+                              uint64_t n, uint8_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool ok = valid ? ((valid[i >> 5] >> (i & 31)) & 1u) : true;
+        out[i] = ok ? (uint8_t)kv_get(v, hashes[i]) : 0;
+    }
+}
+
+// out[i] = hashes[i*step], ok[i] = valid bit of position i*step (kv_hash_kmers)
+__global__ void kv_gather_kernel(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ valid,
+                                 uint64_t n, uint64_t step, uint64_t *__restrict__ out, uint8_t *__restrict__ ok)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t g = i * step;
+        out[i] = hashes[g];
+        ok[i] = (valid[g >> 5] >> (g & 31)) & 1u;
+    }
+}
+
+// valid bits -> one byte per position
+__global__ void kv_expand_bits_kernel(const uint32_t *__restrict__ valid, uint64_t n, uint8_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (valid[i >> 5] >> (i & 31)) & 1u;
+}
+
+// ----------------------------------------------------------------------- K5
+//
+// khmer's n_unique_kmers counts the add() calls that found at least one of their T buckets
+// empty, in single-threaded file order.  Exact parallel equivalent, per
+// batch (batches are applied in order, so "empty at batch start" is the sequential state):
+//   probe:   every valid occurrence g whose bucket in table t is empty does
+//            first[t][bin] = min(first[t][bin], g)            (first[] is all-ones between batches)
+//   resolve: occurrence g is "new" iff first[t][bin_t] == g for some t; owners reset their slot.
+// Only occurrences that saw an empty bucket take part in resolve (cand bits).
+
+struct KvUniqueParams {
+    KvView v;
+    uint32_t *first;                      // one u32 per bucket, tables back to back
+    uint64_t first_base[KV_TABLES_DEV];   // start of table t inside first[]
+    const uint64_t *hashes;
+    const uint32_t *valid;
+    uint32_t *cand;                       // bit per position: saw an empty bucket
+    uint64_t total;
+    unsigned long long *n_unique;
+};
+
+__global__ void __launch_bounds__(256) kv_unique_probe_kernel(KvUniqueParams p)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total_pad = (p.total + 31) & ~(uint64_t)31;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
+        bool is_cand = false;
+        if (g < p.total && (!p.valid || ((__ldg(p.valid + (g >> 5)) >> (g & 31)) & 1u))) {
+            const uint64_t h = p.hashes[g];
+            for (int t = 0; t < p.v.n_tables; t++) {
+                uint64_t bin = kv_mod(h, p.v.size[t], p.v.magic[t]);
+                if (kv_bucket_get(p.v, t, bin) == 0) {
+                    is_cand = true;
+                    atomicMin(p.first + p.first_base[t] + bin, (uint32_t)g);
+                }
+            }
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+        if ((threadIdx.x & 31) == 0) p.cand[g >> 5] = bal;
+    }
+}
+
+__global__ void __launch_bounds__(256) kv_unique_resolve_kernel(KvUniqueParams p)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total_pad = (p.total + 31) & ~(uint64_t)31;
+    unsigned mine = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
+        if (!((__ldg(p.cand + (g >> 5)) >> (g & 31)) & 1u)) continue;
+        const uint64_t h = p.hashes[g];
+        bool is_new = false;
+        for (int t = 0; t < p.v.n_tables; t++) {
+            uint64_t bin = kv_mod(h, p.v.size[t], p.v.magic[t]);
+            uint32_t *slot = p.first + p.first_base[t] + bin;
+            if (__ldcg(slot) == (uint32_t)g) {
+                is_new = true;
+                *slot = 0xffffffffu;   // only the owner writes; every other reader just compares != its own g
+            }
+        }
+        mine += is_new;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(p.n_unique, (unsigned long long)mine);
+}
+
+// khmer _occupied_bins: non-zero buckets of table 0
+__global__ void kv_occupied_kernel(KvView v, unsigned long long *out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n = v.size[0];
+    unsigned mine = 0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
+        mine += kv_bucket_get(v, 0, b) != 0;
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
+}
+
+// ----------------------------------------------------------------------- K4
+
+struct KvNovelParams {
+    const uint8_t *bases;
+    const uint64_t *offsets;
+    const uint32_t *tile_first;
+    uint64_t total, n_tiles;
+    int k;
+    int n_case, n_ctrl;
+    int case_min, ctrl_max, screen;
+    int banded;                 // kevlar/novel.py:144-147 bit test (App. B.1)
+    uint64_t band_mask;         // num_bands - 1
+    long long band_minus_1;
+    kv_hit *hits;
+    unsigned long long max_hits;
+    unsigned long long *n_hits;
+    uint32_t *read_flags;       // u32 per read (no byte atomics on the device)
+    uint32_t *discard_pos;      // per read, atomicMin; NULL when screen <= 0
+    KvView sk[KV_MAX_SAMPLES];  // cases then controls
+};
+
+template <int HASHER, int KW>
+__global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_constant__ KvNovelParams p)
+{
+    __shared__ KvTileSmem sm;
+    const uint64_t tile = blockIdx.x;
+    const uint64_t tile_start = tile * KV_TILE;
+    kv_tile_load<HASHER == KV_HASH_TWOBIT, true>(sm, p.bases, tile_start, p.total);
+    kv_tile_bounds(sm, p.offsets, p.tile_first, tile);
+    __syncthreads();
+
+#pragma unroll 1
+    for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
+        const int l = it * KV_THREADS + threadIdx.x;
+        const uint64_t g = tile_start + l;
+        if (g >= p.total) continue;
+        uint64_t read, rs, re;
+        kv_find_read(sm, p.offsets, p.tile_first, tile, g, read, rs, re);
+        // any byte outside ACGT poisons the whole read (kevlar/novel.py:136-139)
+        const int L = l + KV_FRONT;
+        if ((sm.bad[L >> 5] >> (L & 31)) & 1u) atomicOr(p.read_flags + read, KV_READ_SKIPPED);
+        if (g + p.k > re) continue;
+        if (kv_window_bad(sm, L, p.k)) continue;
+        const uint64_t h = kv_tile_hash<HASHER, KW>(sm, l, p.k);
+        if (p.banded && (long long)(h & p.band_mask) != p.band_minus_1) continue;
+
+        // kmer_is_interesting (kevlar/novel.py:21-53), same evaluation order and early exits
+        uint8_t ab[KV_MAX_SAMPLES];
+        bool interesting = true;
+        for (int s = 0; s < p.n_case; s++) {
+            int a = (int)kv_get(p.sk[s], h);
+            if (a < p.case_min) {
+                interesting = false;
+                if (p.screen > 0 && a < p.screen) atomicMin(p.discard_pos + read, (uint32_t)(g - rs));
+                break;
+            }
+            ab[s] = (uint8_t)a;
+        }
+        if (!interesting) continue;
+        for (int s = 0; s < p.n_ctrl; s++) {
+            int a = (int)kv_get(p.sk[p.n_case + s], h);
+            if (a > p.ctrl_max) { interesting = false; break; }
+            ab[p.n_case + s] = (uint8_t)a;
+        }
+        if (!interesting) continue;
+        unsigned long long slot = atomicAdd(p.n_hits, 1ULL);
+        if (slot < p.max_hits) {
+            kv_hit hit;
+            hit.read = (uint32_t)read;
+            hit.offset = (uint32_t)(g - rs);
+#pragma unroll
+            for (int s = 0; s < KV_MAX_SAMPLES; s++) hit.abund[s] = s < p.n_case + p.n_ctrl ? ab[s] : 0;
+            p.hits[slot] = hit;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------- K6
+
+// 8-bit: u8 -> u16;  4-bit: one u8 per nibble (bucket order);  1-bit: raw bytes.
+__global__ void kv_widen_kernel(const uint8_t *__restrict__ flat, uint64_t nbytes, int bits, void *out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
+        uint8_t b = flat[i];
+        if (bits == 8) ((uint16_t *)out)[i] = b;
+        else if (bits == 4) { ((uint8_t *)out)[2 * i] = b >> 4; ((uint8_t *)out)[2 * i + 1] = b & 15; }
+        else ((uint8_t *)out)[i] = b;
+    }
+}
+
+__global__ void kv_narrow_kernel(uint8_t *__restrict__ flat, uint64_t nbytes, int bits, const void *in)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
+        if (bits == 8) {
+            unsigned s = ((const uint16_t *)in)[i];
+            flat[i] = (uint8_t)(s > 255u ? 255u : s);
+        } else if (bits == 4) {
+            unsigned hi = ((const uint8_t *)in)[2 * i], lo = ((const uint8_t *)in)[2 * i + 1];
+            hi = hi > 15u ? 15u : hi; lo = lo > 15u ? 15u : lo;
+            flat[i] = (uint8_t)((hi << 4) | lo);
+        } else flat[i] = ((const uint8_t *)in)[i];
+    }
+}
+
+struct KvPeers {
+    const uint4 *peer[8];
+    int n;
+};
+
+// Saturating merge over NVLink: each thread pulls 16 bytes from every peer's table (peer-mapped
+// device pointers) and folds them into the local table.  8-bit counters use the SIMD
+// per-byte unsigned saturating add; nibbles are split into two byte lanes and clamped at 15.
+__device__ __forceinline__ uint32_t kv_sat_merge_word(uint32_t a, uint32_t b, int bits)
+{
+    if (bits == 8) return __vaddus4(a, b);
+    if (bits == 1) return a | b;
+    uint32_t lo = __vminu4(__vaddus4(a & 0x0f0f0f0fu, b & 0x0f0f0f0fu), 0x0f0f0f0fu);
+    uint32_t hi = __vminu4(__vaddus4((a >> 4) & 0x0f0f0f0fu, (b >> 4) & 0x0f0f0f0fu), 0x0f0f0f0fu);
+    return lo | (hi << 4);
+}
+
+__global__ void kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec, int bits, KvPeers peers)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        uint4 acc = local[i];
+        for (int p = 0; p < peers.n; p++) {
+            uint4 o = peers.peer[p][i];
+            acc.x = kv_sat_merge_word(acc.x, o.x, bits);
+            acc.y = kv_sat_merge_word(acc.y, o.y, bits);
+            acc.z = kv_sat_merge_word(acc.z, o.z, bits);
+            acc.w = kv_sat_merge_word(acc.w, o.w, bits);
+        }
+        local[i] = acc;
+    }
+}
+
+__global__ void kv_fill_u32_kernel(uint32_t *p, uint64_t n, uint32_t val)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = val;
+}

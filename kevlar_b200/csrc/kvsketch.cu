@@ -1,0 +1,982 @@
+// kvsketch.cu -- host side of libkvsketch.so: the C ABI declared in include/kvsketch.h.
+//
+// One KvCtx per CUDA device holds the compute/copy streams, two input staging slots (so the
+// H2D copy of batch i+1 overlaps the kernels of batch i) and the per-chunk scratch (hashes,
+// valid bits).  Sketch tables live in ONE device allocation per sketch, khmer byte layout,
+// each table 256-byte aligned.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kv_kernels.cuh"
+
+// ------------------------------------------------------------------ errors
+
+static thread_local std::string g_err;
+
+static int kv_fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return kv_fail(e_ == cudaErrorMemoryAllocation ? KV_ENOMEM : KV_ECUDA, "%s: %s (%s:%d)", #expr, \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+
+#define KV_TRY(expr)            \
+    do {                        \
+        int rc_ = (expr);       \
+        if (rc_ != KV_OK) return rc_; \
+    } while (0)
+
+extern "C" const char *kv_last_error(void) { return g_err.c_str(); }
+extern "C" int kv_abi_version(void) { return KV_ABI_VERSION; }
+
+// ------------------------------------------------------------------ context
+
+struct KvBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct KvSlot {
+    KvBuf bases, offsets;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool used = false;
+};
+
+struct KvCtx {
+    int device = -1;
+    bool ready = false;
+    std::mutex mu;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    KvSlot slot[2];
+    int next_slot = 0;
+    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc;
+    unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
+    unsigned long long *h_counters = nullptr; // pinned mirror
+    uint64_t launches = 0;
+    int sm_count = 148;
+    uint64_t chunk_bases = 64ull << 20;
+};
+
+static KvCtx g_ctx[16];
+static std::mutex g_ctx_mu;
+
+static int kv_ctx_get(int device, KvCtx **out)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return kv_fail(KV_ENODEVICE, "no usable CUDA device (%s); libkvsketch has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n || device >= 16) return kv_fail(KV_EINVAL, "device %d out of range (have %d)", device, n);
+    KvCtx &c = g_ctx[device];
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!c.ready) {
+        CU(cudaSetDevice(device));
+        c.device = device;
+        CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        for (auto &s : c.slot) {
+            CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        CU(cudaMalloc(&c.counters, 8 * sizeof(unsigned long long)));
+        CU(cudaMemset(c.counters, 0, 8 * sizeof(unsigned long long)));
+        CU(cudaMallocHost(&c.h_counters, 8 * sizeof(unsigned long long)));
+        CU(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
+        if (const char *env = getenv("KV_CHUNK_BASES")) {
+            uint64_t v = strtoull(env, nullptr, 10);
+            if (v >= KV_TILE) c.chunk_bases = v;
+        }
+        c.chunk_bases = (c.chunk_bases + KV_TILE - 1) / KV_TILE * KV_TILE;
+        c.ready = true;
+    }
+    *out = &c;
+    return KV_OK;
+}
+
+static int kv_buf_ensure(KvBuf &b, size_t need)
+{
+    if (need <= b.cap) return KV_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t cap = need + need / 8 + 4096;
+    cap = (cap + 255) & ~(size_t)255;
+    CU(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return KV_OK;
+}
+
+#define LAUNCH(ctx, kern, grid, block, ...)                                \
+    do {                                                                   \
+        auto kfn_ = kern;                                                  \
+        kfn_<<<(grid), (block), 0, (ctx)->compute>>>(__VA_ARGS__);         \
+        (ctx)->launches++;                                                 \
+        CU(cudaGetLastError());                                            \
+    } while (0)
+
+static inline unsigned kv_grid_for(const KvCtx *c, uint64_t n, int per_sm = 8)
+{
+    uint64_t blocks = (n + 255) / 256;
+    uint64_t cap = (uint64_t)c->sm_count * per_sm;
+    return (unsigned)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+// ------------------------------------------------------------------ sketch
+
+struct kv_sketch {
+    int hasher, bits, ksize, n_tables, device;
+    uint64_t sizes[KV_TABLES_DEV];
+    uint64_t nbytes[KV_TABLES_DEV];   // khmer byte length of each table
+    uint64_t toff[KV_TABLES_DEV];     // offset of each table in the flat allocation
+    uint64_t flat_bytes;
+    uint8_t *flat;
+    uint32_t *first;                  // unique-tracking scratch (u32 per bucket), lazily allocated
+    uint64_t first_base[KV_TABLES_DEV];
+    bool track_unique, unique_valid;
+    uint64_t n_unique;                // host copy, updated at stats time
+    unsigned long long *d_unique;     // device accumulator
+    uint64_t file_occupied;           // n_occupied as stored in the file it was loaded from
+};
+
+static uint64_t kv_table_bytes(int bits, uint64_t size)
+{
+    return bits == 8 ? size : (bits == 4 ? size / 2 + 1 : size / 8 + 1);
+}
+
+static KvView kv_view(const kv_sketch *s)
+{
+    KvView v;
+    memset(&v, 0, sizeof v);
+    v.n_tables = s->n_tables;
+    v.bits = s->bits;
+    for (int t = 0; t < s->n_tables; t++) {
+        v.tab[t] = s->flat + s->toff[t];
+        v.size[t] = s->sizes[t];
+        v.magic[t] = UINT64_MAX / s->sizes[t];
+    }
+    return v;
+}
+
+static bool is_prime_u64(uint64_t n)
+{
+    if (n < 2) return false;
+    if (n < 4) return true;
+    if (n % 2 == 0) return false;
+    for (uint64_t i = 3; i * i <= n; i += 2)
+        if (n % i == 0) return false;
+    return true;
+}
+
+extern "C" int kv_primes_below(uint64_t x, int n, uint64_t *out)
+{
+    if (n < 1 || !out) return kv_fail(KV_EINVAL, "kv_primes_below: bad arguments");
+    if (x < 3) return kv_fail(KV_EINVAL, "cannot find %d primes below %llu", n, (unsigned long long)x);
+    uint64_t i = x - 1;
+    if (i % 2 == 0) i--;
+    int found = 0;
+    while (found < n && i > 0) {
+        if (is_prime_u64(i)) out[found++] = i;
+        if (i == 1) break;
+        i -= 2;
+    }
+    if (found != n) return kv_fail(KV_EINVAL, "cannot find %d primes below %llu", n, (unsigned long long)x);
+    return KV_OK;
+}
+
+extern "C" int kv_device_count(int *n)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { cudaGetLastError(); c = 0; }
+    if (n) *n = c;
+    return KV_OK;
+}
+
+static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int device,
+                           bool zero, kv_sketch **out)
+{
+    if (!out || !sizes) return kv_fail(KV_EINVAL, "null argument");
+    if (hasher != KV_HASH_MURMUR && hasher != KV_HASH_TWOBIT) return kv_fail(KV_EINVAL, "unknown hasher %d", hasher);
+    if (bits != 8 && bits != 4 && bits != 1) return kv_fail(KV_EINVAL, "counter width must be 8, 4 or 1 bits");
+    if (n_tables < 1 || n_tables > KV_TABLES_DEV)
+        return kv_fail(KV_EINVAL, "n_tables must be between 1 and %d", KV_TABLES_DEV);
+    int kmax = hasher == KV_HASH_TWOBIT ? KV_MAX_KSIZE_TWOBIT : KV_MAX_KSIZE_MURMUR;
+    if (ksize < 1 || ksize > kmax) return kv_fail(KV_EINVAL, "k-mer size %d not supported (1..%d for this hasher)", ksize, kmax);
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    kv_sketch *s = new kv_sketch();
+    memset(s, 0, sizeof *s);
+    s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
+    uint64_t off = 0, nb = 0;
+    for (int t = 0; t < n_tables; t++) {
+        if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete s; return kv_fail(KV_EINVAL, "bad table size"); }
+        s->sizes[t] = sizes[t];
+        s->nbytes[t] = kv_table_bytes(bits, sizes[t]);
+        s->toff[t] = off;
+        s->first_base[t] = nb;
+        nb += sizes[t];
+        off += (s->nbytes[t] + 255) & ~(uint64_t)255;
+    }
+    s->flat_bytes = off;
+    cudaError_t e = cudaMalloc((void **)&s->flat, off);
+    if (e != cudaSuccess) {
+        delete s;
+        cudaGetLastError();
+        return kv_fail(KV_ENOMEM, "cannot allocate %llu bytes of HBM for the sketch: %s", (unsigned long long)off,
+                       cudaGetErrorString(e));
+    }
+    if (zero) CU(cudaMemsetAsync(s->flat, 0, off, ctx->compute));
+    CU(cudaMalloc((void **)&s->d_unique, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
+    s->track_unique = true;
+    s->unique_valid = true;
+    *out = s;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_create(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int device,
+                                kv_sketch **out)
+{
+    return kv_sketch_alloc(hasher, bits, ksize, n_tables, sizes, device, true, out);
+}
+
+extern "C" int kv_sketch_destroy(kv_sketch *s)
+{
+    if (!s) return KV_OK;
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (s->flat) cudaFree(s->flat);
+    if (s->first) cudaFree(s->first);
+    if (s->d_unique) cudaFree(s->d_unique);
+    delete s;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *ksize, int *n_tables, uint64_t *sizes,
+                              int *device)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (hasher) *hasher = s->hasher;
+    if (bits) *bits = s->bits;
+    if (ksize) *ksize = s->ksize;
+    if (n_tables) *n_tables = s->n_tables;
+    if (device) *device = s->device;
+    if (sizes) for (int t = 0; t < s->n_tables; t++) sizes[t] = s->sizes[t];
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_set_unique_tracking(kv_sketch *s, int on)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    s->track_unique = on != 0;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_table(kv_sketch *s, int t, void **dev_ptr, uint64_t *nbytes)
+{
+    if (!s || t < 0 || t >= s->n_tables) return kv_fail(KV_EINVAL, "bad table index");
+    if (dev_ptr) *dev_ptr = s->flat + s->toff[t];
+    if (nbytes) *nbytes = s->nbytes[t];
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_flat(kv_sketch *s, void **dev_ptr, uint64_t *nbytes)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (dev_ptr) *dev_ptr = s->flat;
+    if (nbytes) *nbytes = s->flat_bytes;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_read_table(kv_sketch *s, int t, uint8_t *host_out, uint64_t nbytes)
+{
+    if (!s || t < 0 || t >= s->n_tables || !host_out) return kv_fail(KV_EINVAL, "bad arguments");
+    if (nbytes != s->nbytes[t]) return kv_fail(KV_EINVAL, "table %d holds %llu bytes", t, (unsigned long long)s->nbytes[t]);
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(host_out, s->flat + s->toff[t], nbytes, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_write_table(kv_sketch *s, int t, const uint8_t *host_in, uint64_t nbytes)
+{
+    if (!s || t < 0 || t >= s->n_tables || !host_in) return kv_fail(KV_EINVAL, "bad arguments");
+    if (nbytes != s->nbytes[t]) return kv_fail(KV_EINVAL, "table %d holds %llu bytes", t, (unsigned long long)s->nbytes[t]);
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->flat + s->toff[t], host_in, nbytes, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    s->unique_valid = false;
+    return KV_OK;
+}
+
+static int kv_occupied_locked(KvCtx *ctx, kv_sketch *s, uint64_t *out)
+{
+    CU(cudaMemsetAsync(ctx->counters + 3, 0, sizeof(unsigned long long), ctx->compute));
+    LAUNCH(ctx, kv_occupied_kernel, kv_grid_for(ctx, s->sizes[0]), 256, kv_view(s), ctx->counters + 3);
+    CU(cudaMemcpyAsync(ctx->h_counters + 3, ctx->counters + 3, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    *out = ctx->h_counters[3];
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_stats(kv_sketch *s, uint64_t *n_occupied, uint64_t *n_unique, int *n_unique_valid)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    if (n_occupied) KV_TRY(kv_occupied_locked(ctx, s, n_occupied));
+    if (n_unique || n_unique_valid) {
+        CU(cudaMemcpyAsync(ctx->h_counters + 1, s->d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        s->n_unique = ctx->h_counters[1];
+        if (n_unique) *n_unique = s->n_unique;
+        if (n_unique_valid) *n_unique_valid = s->unique_valid ? 1 : 0;
+    }
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ OXLI v4 I/O
+
+extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
+{
+    if (!s || !path) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    uint64_t occ = 0;
+    KV_TRY(kv_occupied_locked(ctx, s, &occ));
+    FILE *f = fopen(path, "wb");
+    if (!f) return kv_fail(KV_EIO, "cannot open %s for writing", path);
+    uint8_t version = 4, type = s->bits == 8 ? 1 : (s->bits == 4 ? 7 : 2);
+    fwrite("OXLI", 1, 4, f);
+    fwrite(&version, 1, 1, f);
+    fwrite(&type, 1, 1, f);
+    if (s->bits == 8) { uint8_t big = 0; fwrite(&big, 1, 1, f); }
+    uint32_t k = (uint32_t)s->ksize;
+    uint8_t nt = (uint8_t)s->n_tables;
+    fwrite(&k, 4, 1, f);
+    fwrite(&nt, 1, 1, f);
+    fwrite(&occ, 8, 1, f);
+    const size_t CH = 64u << 20;
+    uint8_t *stage = nullptr;
+    if (cudaMallocHost((void **)&stage, CH) != cudaSuccess) { fclose(f); cudaGetLastError(); return kv_fail(KV_ENOMEM, "pinned staging"); }
+    int rc = KV_OK;
+    for (int t = 0; t < s->n_tables && rc == KV_OK; t++) {
+        fwrite(&s->sizes[t], 8, 1, f);
+        for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
+            size_t n = (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o);
+            if (cudaMemcpyAsync(stage, s->flat + s->toff[t] + o, n, cudaMemcpyDeviceToHost, ctx->compute) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "D2H copy failed"); break; }
+            if (fwrite(stage, 1, n, f) != n) { rc = kv_fail(KV_EIO, "short write to %s", path); break; }
+        }
+    }
+    cudaFreeHost(stage);
+    if (rc == KV_OK && s->bits == 8) { uint64_t nbig = 0; fwrite(&nbig, 8, 1, f); }
+    if (rc == KV_OK && ferror(f)) rc = kv_fail(KV_EIO, "write error on %s", path);
+    fclose(f);
+    return rc;
+}
+
+extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int device, kv_sketch **out)
+{
+    if (!path || !out) return kv_fail(KV_EINVAL, "null argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return kv_fail(KV_EIO, "cannot open %s", path);
+    uint8_t head[6];
+    if (fread(head, 1, 6, f) != 6 || memcmp(head, "OXLI", 4)) { fclose(f); return kv_fail(KV_EIO, "%s: not an OXLI sketch file", path); }
+    if (head[4] != 4) { fclose(f); return kv_fail(KV_EIO, "%s: unsupported OXLI version %d", path, head[4]); }
+    int bits = head[5] == 1 ? 8 : head[5] == 7 ? 4 : head[5] == 2 ? 1 : 0;
+    if (!bits || (expect_bits && bits != expect_bits)) { fclose(f); return kv_fail(KV_EIO, "%s: unexpected table type %d", path, head[5]); }
+    uint8_t big = 0, nt = 0;
+    uint32_t k = 0;
+    uint64_t occ = 0;
+    bool ok = true;
+    if (bits == 8) ok = fread(&big, 1, 1, f) == 1;
+    ok = ok && fread(&k, 4, 1, f) == 1 && fread(&nt, 1, 1, f) == 1 && fread(&occ, 8, 1, f) == 1;
+    if (!ok || nt < 1 || nt > KV_TABLES_DEV) { fclose(f); return kv_fail(KV_EIO, "%s: truncated or unsupported header", path); }
+    // first pass: table sizes (they are interleaved with the data)
+    uint64_t sizes[KV_TABLES_DEV];
+    long data_pos[KV_TABLES_DEV];
+    for (int t = 0; t < nt; t++) {
+        if (fread(&sizes[t], 8, 1, f) != 1) { fclose(f); return kv_fail(KV_EIO, "%s: truncated file", path); }
+        data_pos[t] = ftell(f);
+        if (fseek(f, (long)kv_table_bytes(bits, sizes[t]), SEEK_CUR)) { fclose(f); return kv_fail(KV_EIO, "%s: truncated file", path); }
+    }
+    kv_sketch *s = nullptr;
+    int rc = kv_sketch_alloc(hasher, bits, (int)k, nt, sizes, device, true, &s);
+    if (rc != KV_OK) { fclose(f); return rc; }
+    KvCtx *ctx;
+    kv_ctx_get(device, &ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t CH = 64u << 20;
+    uint8_t *stage = nullptr;
+    if (cudaMallocHost((void **)&stage, CH) != cudaSuccess) { fclose(f); cudaGetLastError(); return kv_fail(KV_ENOMEM, "pinned staging"); }
+    for (int t = 0; t < nt && rc == KV_OK; t++) {
+        fseek(f, data_pos[t], SEEK_SET);
+        for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
+            size_t n = (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o);
+            if (fread(stage, 1, n, f) != n) { rc = kv_fail(KV_EIO, "%s: truncated file", path); break; }
+            if (cudaMemcpyAsync(s->flat + s->toff[t] + o, stage, n, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "H2D copy failed"); break; }
+        }
+    }
+    cudaFreeHost(stage);
+    fclose(f);
+    if (rc != KV_OK) { cudaFree(s->flat); cudaFree(s->d_unique); delete s; return rc; }
+    s->file_occupied = occ;
+    *out = s;
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ batch staging
+
+struct KvBatch {
+    const uint8_t *d_bases;
+    const uint64_t *d_offsets;
+    uint64_t total, n_reads, n_tiles;
+    KvSlot *slot;   // non-null when staged from host memory
+};
+
+// Make the batch visible on the device: copy host buffers into a staging slot on the copy
+// stream (compute waits on the event), or use device pointers in place.  Also builds the
+// tile -> first read index.
+static int kv_stage(KvCtx *ctx, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where,
+                    uint64_t total_hint, KvBatch *b)
+{
+    if (n_reads >= 0xffffffffull) return kv_fail(KV_EINVAL, "at most 2^32-2 reads per batch");
+    b->n_reads = n_reads;
+    b->slot = nullptr;
+    uint64_t total = total_hint;
+    if (where == KV_MEM_HOST) {
+        total = offsets[n_reads];
+        for (uint64_t r = 0; r < n_reads; r++)   // cheap sanity: offsets must be non-decreasing
+            if (offsets[r + 1] < offsets[r]) return kv_fail(KV_EINVAL, "read offsets must be non-decreasing");
+        if (offsets[0] != 0) return kv_fail(KV_EINVAL, "offsets[0] must be 0");
+        KvSlot *s = &ctx->slot[ctx->next_slot];
+        ctx->next_slot ^= 1;
+        if (s->used) CU(cudaEventSynchronize(s->done));
+        KV_TRY(kv_buf_ensure(s->bases, total + 16));
+        KV_TRY(kv_buf_ensure(s->offsets, (n_reads + 1) * 8));
+        if (total) CU(cudaMemcpyAsync(s->bases.p, bases, total, cudaMemcpyHostToDevice, ctx->copy));
+        CU(cudaMemcpyAsync(s->offsets.p, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->copy));
+        CU(cudaEventRecord(s->copied, ctx->copy));
+        CU(cudaStreamWaitEvent(ctx->compute, s->copied, 0));
+        s->used = true;
+        b->slot = s;
+        b->d_bases = (const uint8_t *)s->bases.p;
+        b->d_offsets = (const uint64_t *)s->offsets.p;
+    } else if (where == KV_MEM_DEVICE) {
+        if (((uintptr_t)bases & 3) || ((uintptr_t)offsets & 7)) return kv_fail(KV_EINVAL, "device batch pointers must be 4/8-byte aligned");
+        CU(cudaMemcpyAsync(ctx->h_counters + 4, offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        total = ctx->h_counters[4];
+        b->d_bases = bases;
+        b->d_offsets = offsets;
+    } else
+        return kv_fail(KV_EINVAL, "where must be KV_MEM_HOST or KV_MEM_DEVICE");
+    b->total = total;
+    b->n_tiles = (total + KV_TILE - 1) / KV_TILE;
+    if (total && n_reads) {
+        KV_TRY(kv_buf_ensure(ctx->tile_first, (b->n_tiles + 1) * 4));
+        LAUNCH(ctx, kv_tile_index_kernel, (unsigned)((b->n_tiles + 1 + 255) / 256), 256, b->d_offsets, n_reads, b->n_tiles,
+               (uint32_t *)ctx->tile_first.p);
+    }
+    return KV_OK;
+}
+
+static inline void kv_stage_done(KvCtx *ctx, KvBatch *b)
+{
+    if (b->slot) cudaEventRecord(b->slot->done, ctx->compute);
+}
+
+template <int HASHER>
+static int kv_launch_hash(KvCtx *ctx, const KvHashParams &p, unsigned n_tiles)
+{
+    if (HASHER == KV_HASH_TWOBIT) { LAUNCH(ctx, (kv_hash_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
+    int kw = 4 * ((p.k + 15) / 16);
+    switch (kw) {
+    case 4: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
+    case 8: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
+    case 12: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
+    default: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
+    }
+    return KV_OK;
+}
+
+static int kv_band_interval(int num_bands, int band, uint64_t *lo, uint64_t *hi)
+{
+    if (num_bands <= 0 || band < 0 || band >= num_bands)
+        return kv_fail(KV_EINVAL, "Band number must be less than number of bands");
+    uint64_t size = UINT64_MAX / (uint64_t)num_bands;
+    *lo = size * (uint64_t)band;
+    *hi = size * (uint64_t)(band + 1);
+    if (band == num_bands - 1) *hi = UINT64_MAX;
+    return KV_OK;
+}
+
+static int kv_ensure_first(KvCtx *ctx, kv_sketch *s)
+{
+    if (s->first) return KV_OK;
+    uint64_t n = 0;
+    for (int t = 0; t < s->n_tables; t++) n += s->sizes[t];
+    cudaError_t e = cudaMalloc((void **)&s->first, n * 4);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return kv_fail(KV_ENOMEM, "cannot allocate %llu bytes for exact n_unique_kmers tracking; "
+                       "disable it with kv_sketch_set_unique_tracking(s, 0)", (unsigned long long)(n * 4));
+    }
+    LAUNCH(ctx, kv_fill_u32_kernel, kv_grid_for(ctx, n), 256, s->first, n, 0xffffffffu);
+    return KV_OK;
+}
+
+// apply a chunk of hashes (device) to the sketch: optional exact-unique bookkeeping, then increments
+static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n)
+{
+    if (!n) return KV_OK;
+    KvView v = kv_view(s);
+    unsigned grid = kv_grid_for(ctx, n);
+    if (s->track_unique) {
+        KV_TRY(kv_ensure_first(ctx, s));
+        KV_TRY(kv_buf_ensure(ctx->cand, ((n + 31) / 32 + 1) * 4));
+        KvUniqueParams up;
+        memset(&up, 0, sizeof up);
+        up.v = v; up.first = s->first; up.hashes = d_hashes; up.valid = d_valid; up.cand = (uint32_t *)ctx->cand.p;
+        up.total = n; up.n_unique = s->d_unique;
+        for (int t = 0; t < s->n_tables; t++) up.first_base[t] = s->first_base[t];
+        LAUNCH(ctx, kv_unique_probe_kernel, grid, 256, up);
+        LAUNCH(ctx, kv_unique_resolve_kernel, grid, 256, up);
+    } else
+        s->unique_valid = false;
+    if (d_valid) {
+        if (s->bits == 8) LAUNCH(ctx, kv_increment_kernel<8>, grid, 256, v, d_hashes, d_valid, n);
+        else if (s->bits == 4) LAUNCH(ctx, kv_increment_kernel<4>, grid, 256, v, d_hashes, d_valid, n);
+        else LAUNCH(ctx, kv_increment_kernel<1>, grid, 256, v, d_hashes, d_valid, n);
+    } else {
+        if (s->bits == 8) LAUNCH(ctx, kv_add_hashes_kernel<8>, grid, 256, v, d_hashes, n);
+        else if (s->bits == 4) LAUNCH(ctx, kv_add_hashes_kernel<4>, grid, 256, v, d_hashes, n);
+        else LAUNCH(ctx, kv_add_hashes_kernel<1>, grid, 256, v, d_hashes, n);
+    }
+    return KV_OK;
+}
+
+static int kv_check_mask(const kv_sketch *s, const kv_sketch *mask)
+{
+    if (!mask) return KV_OK;
+    if (mask->device != s->device) return kv_fail(KV_EINVAL, "mask lives on another device");
+    if (mask->ksize != s->ksize || mask->hasher != s->hasher)
+        return kv_fail(KV_EINVAL, "mask must use the same k-mer size and hash function as the sketch");
+    return KV_OK;
+}
+
+extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                                int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
+                                int consume_masked, uint64_t *n_kmers_out)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KV_OK;
+    if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
+    KV_TRY(kv_check_mask(s, mask));
+    uint64_t lo = 0, hi = 0;
+    if (num_bands > 0) KV_TRY(kv_band_interval(num_bands, band, &lo, &hi));
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+    if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
+    CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
+
+    const uint64_t chunk_tiles = ctx->chunk_bases / KV_TILE;
+    const uint64_t chunk_pos = std::min<uint64_t>(ctx->chunk_bases, b.n_tiles * KV_TILE);
+    KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
+    KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
+        uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
+        uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
+        KvHashParams p;
+        memset(&p, 0, sizeof p);
+        p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+        p.total = b.total; p.tile0 = t0; p.k = s->ksize;
+        p.banded = num_bands > 0; p.band_lo = lo; p.band_hi = hi;
+        if (mask) { p.use_mask = 1; p.mask = kv_view(mask); p.mask_threshold = mask_threshold; p.consume_masked = consume_masked != 0; }
+        p.strict = 0;
+        p.hashes = (uint64_t *)ctx->hashes.p; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+        if (s->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)nt));
+        else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)nt));
+        KV_TRY(kv_apply_hashes(ctx, s, p.hashes, p.valid, npos));
+    }
+    kv_stage_done(ctx, &b);
+    if (n_kmers_out) {
+        CU(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        *n_kmers_out = ctx->h_counters[0];
+    }
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ novel
+
+template <int HASHER>
+static int kv_launch_novel(KvCtx *ctx, const KvNovelParams &p)
+{
+    unsigned n_tiles = (unsigned)p.n_tiles;
+    if (HASHER == KV_HASH_TWOBIT) { LAUNCH(ctx, (kv_novel_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
+    int kw = 4 * ((p.k + 15) / 16);
+    switch (kw) {
+    case 4: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
+    case 8: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
+    case 12: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
+    default: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
+    }
+    return KV_OK;
+}
+
+extern "C" int kv_novel_batch(const kv_sketch *const *cases, int n_case, const kv_sketch *const *ctrls, int n_ctrl,
+                              const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where, int case_min,
+                              int ctrl_max, int screen, int num_bands, int64_t band_minus_1, kv_hit *hits,
+                              uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos)
+{
+    if (n_hits) *n_hits = 0;
+    if (n_case < 1 || !cases || !cases[0]) return kv_fail(KV_EINVAL, "need at least one case sketch");
+    if (n_ctrl < 0 || n_case + n_ctrl > KV_MAX_SAMPLES) return kv_fail(KV_EINVAL, "at most %d sketches per scan", KV_MAX_SAMPLES);
+    if (!n_hits || !read_flags || (max_hits && !hits)) return kv_fail(KV_EINVAL, "null output pointer");
+    if (screen > 0 && !discard_pos) return kv_fail(KV_EINVAL, "discard_pos is required when the abundance screen is on");
+    const kv_sketch *c0 = cases[0];
+    KvNovelParams p;
+    memset(&p, 0, sizeof p);
+    for (int i = 0; i < n_case + n_ctrl; i++) {
+        const kv_sketch *s = i < n_case ? cases[i] : ctrls[i - n_case];
+        if (!s) return kv_fail(KV_EINVAL, "null sketch in sample list");
+        if (s->device != c0->device) return kv_fail(KV_EINVAL, "all sketches of a scan must live on one device");
+        if (s->ksize != c0->ksize || s->hasher != c0->hasher)
+            return kv_fail(KV_EINVAL, "all sketches of a scan must share k-mer size and hash function");
+        p.sk[i] = kv_view(s);
+    }
+    if (n_reads == 0) return KV_OK;
+    if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(c0->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(c0->device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+
+    KV_TRY(kv_buf_ensure(ctx->flags, n_reads * 4));
+    CU(cudaMemsetAsync(ctx->flags.p, 0, n_reads * 4, ctx->compute));
+    if (screen > 0) {
+        KV_TRY(kv_buf_ensure(ctx->discard, n_reads * 4));
+        CU(cudaMemsetAsync(ctx->discard.p, 0xff, n_reads * 4, ctx->compute));
+    }
+    KV_TRY(kv_buf_ensure(ctx->hits, std::max<uint64_t>(max_hits, 1) * sizeof(kv_hit)));
+    CU(cudaMemsetAsync(ctx->counters + 2, 0, sizeof(unsigned long long), ctx->compute));
+
+    p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+    p.total = b.total; p.n_tiles = b.n_tiles; p.k = c0->ksize;
+    p.n_case = n_case; p.n_ctrl = n_ctrl; p.case_min = case_min; p.ctrl_max = ctrl_max; p.screen = screen;
+    p.banded = num_bands > 0; p.band_mask = num_bands > 0 ? (uint64_t)(num_bands - 1) : 0; p.band_minus_1 = band_minus_1;
+    p.hits = (kv_hit *)ctx->hits.p; p.max_hits = max_hits; p.n_hits = ctx->counters + 2;
+    p.read_flags = (uint32_t *)ctx->flags.p; p.discard_pos = screen > 0 ? (uint32_t *)ctx->discard.p : nullptr;
+    if (b.total) {
+        if (c0->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_novel<KV_HASH_TWOBIT>(ctx, p));
+        else KV_TRY(kv_launch_novel<KV_HASH_MURMUR>(ctx, p));
+    }
+    kv_stage_done(ctx, &b);
+
+    // results back to the host
+    std::vector<uint32_t> hflags(n_reads), hdisc;
+    CU(cudaMemcpyAsync(ctx->h_counters + 2, ctx->counters + 2, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaMemcpyAsync(hflags.data(), ctx->flags.p, n_reads * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    if (screen > 0) {
+        hdisc.resize(n_reads);
+        CU(cudaMemcpyAsync(hdisc.data(), ctx->discard.p, n_reads * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    }
+    CU(cudaStreamSynchronize(ctx->compute));
+    uint64_t found = ctx->h_counters[2];
+    if (found > max_hits) { *n_hits = found; return kv_fail(KV_EOVERFLOW, "hit buffer too small: %llu hits, room for %llu", (unsigned long long)found, (unsigned long long)max_hits); }
+    std::vector<kv_hit> hh(found);
+    if (found) {
+        CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, found * sizeof(kv_hit), cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+    }
+    // read-level flags (kevlar/novel.py:134-139,152-154).  Offsets are needed on the host for the
+    // "shorter than k" test; with device-resident batches the kernel's flags already cover
+    // non-ACGT reads and short reads simply have no k-mers.
+    for (uint64_t r = 0; r < n_reads; r++) {
+        uint8_t fl = (uint8_t)(hflags[r] & KV_READ_SKIPPED);
+        if (where == KV_MEM_HOST && offsets[r + 1] - offsets[r] < (uint64_t)c0->ksize) fl |= KV_READ_SKIPPED;
+        if (screen > 0) {
+            if (!(fl & KV_READ_SKIPPED) && hdisc[r] != 0xffffffffu) fl |= KV_READ_DISCARDED;
+            discard_pos[r] = (fl & KV_READ_SKIPPED) ? 0xffffffffu : hdisc[r];
+        }
+        read_flags[r] = fl;
+    }
+    uint64_t kept = 0;
+    for (uint64_t i = 0; i < found; i++) {
+        const kv_hit &h = hh[i];
+        if (read_flags[h.read] & KV_READ_SKIPPED) continue;
+        if (screen > 0 && hdisc[h.read] != 0xffffffffu && h.offset > hdisc[h.read]) continue;
+        hh[kept++] = h;
+    }
+    std::sort(hh.begin(), hh.begin() + kept, [](const kv_hit &a, const kv_hit &b2) {
+        return a.read != b2.read ? a.read < b2.read : a.offset < b2.offset;
+    });
+    if (kept) memcpy(hits, hh.data(), kept * sizeof(kv_hit));
+    *n_hits = kept;
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ point / list operations
+
+extern "C" int kv_hash_kmers(int hasher, int ksize, const uint8_t *kmers, uint64_t n, int device, uint64_t *hashes_out,
+                             uint8_t *ok_out)
+{
+    if (!n) return KV_OK;
+    if (!kmers || !hashes_out || !ok_out) return kv_fail(KV_EINVAL, "null argument");
+    int kmax = hasher == KV_HASH_TWOBIT ? KV_MAX_KSIZE_TWOBIT : KV_MAX_KSIZE_MURMUR;
+    if (ksize < 1 || ksize > kmax) return kv_fail(KV_EINVAL, "k-mer size %d not supported", ksize);
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::vector<uint64_t> offs(n + 1);
+    for (uint64_t i = 0; i <= n; i++) offs[i] = i * (uint64_t)ksize;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, kmers, offs.data(), n, KV_MEM_HOST, 0, &b));
+    CU(cudaStreamSynchronize(ctx->copy));   // offs is a local
+    const uint64_t npos = b.n_tiles * KV_TILE;
+    KV_TRY(kv_buf_ensure(ctx->hashes, npos * 8));
+    KV_TRY(kv_buf_ensure(ctx->valid, (npos / 32 + 1) * 4));
+    KV_TRY(kv_buf_ensure(ctx->misc, n * 9));
+    KvHashParams p;
+    memset(&p, 0, sizeof p);
+    p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+    p.total = b.total; p.tile0 = 0; p.k = ksize; p.strict = 1;
+    p.hashes = (uint64_t *)ctx->hashes.p; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+    if (hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)b.n_tiles));
+    else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)b.n_tiles));
+    uint64_t *d_out = (uint64_t *)ctx->misc.p;
+    uint8_t *d_ok = (uint8_t *)ctx->misc.p + n * 8;
+    LAUNCH(ctx, kv_gather_kernel, kv_grid_for(ctx, n), 256, p.hashes, p.valid, n, (uint64_t)ksize, d_out, d_ok);
+    kv_stage_done(ctx, &b);
+    CU(cudaMemcpyAsync(hashes_out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaMemcpyAsync(ok_out, d_ok, n, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_get_hashes(const kv_sketch *s, const uint64_t *hashes, uint64_t n, uint8_t *counts_out)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (!n) return KV_OK;
+    if (!hashes || !counts_out) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    KV_TRY(kv_buf_ensure(ctx->misc, n * 9));
+    uint64_t *d_h = (uint64_t *)ctx->misc.p;
+    uint8_t *d_c = (uint8_t *)ctx->misc.p + n * 8;
+    CU(cudaMemcpyAsync(d_h, hashes, n * 8, cudaMemcpyHostToDevice, ctx->compute));
+    LAUNCH(ctx, kv_get_kernel, kv_grid_for(ctx, n), 256, kv_view(s), d_h, (const uint32_t *)nullptr, n, d_c);
+    CU(cudaMemcpyAsync(counts_out, d_c, n, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_add_hashes(kv_sketch *s, const uint64_t *hashes, uint64_t n)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (!n) return KV_OK;
+    if (!hashes) return kv_fail(KV_EINVAL, "null argument");
+    if (n >= 0xffffffffull) return kv_fail(KV_EINVAL, "at most 2^32-2 hashes per call");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    KV_TRY(kv_buf_ensure(ctx->misc, n * 8));
+    CU(cudaMemcpyAsync(ctx->misc.p, hashes, n * 8, cudaMemcpyHostToDevice, ctx->compute));
+    KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p, nullptr, n));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                                    int where, uint64_t *hashes_out, uint8_t *counts_out, uint8_t *valid_out)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (!n_reads) return KV_OK;
+    if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+    if (!b.total) { kv_stage_done(ctx, &b); return KV_OK; }
+    const uint64_t npos = b.n_tiles * KV_TILE;
+    KV_TRY(kv_buf_ensure(ctx->hashes, npos * 8));
+    KV_TRY(kv_buf_ensure(ctx->valid, (npos / 32 + 1) * 4));
+    KV_TRY(kv_buf_ensure(ctx->misc, b.total * 2));
+    KvHashParams p;
+    memset(&p, 0, sizeof p);
+    p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+    p.total = b.total; p.tile0 = 0; p.k = s->ksize; p.strict = 1;
+    p.hashes = (uint64_t *)ctx->hashes.p; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+    if (s->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)b.n_tiles));
+    else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)b.n_tiles));
+    uint8_t *d_counts = (uint8_t *)ctx->misc.p, *d_valid8 = (uint8_t *)ctx->misc.p + b.total;
+    unsigned grid = kv_grid_for(ctx, b.total);
+    LAUNCH(ctx, kv_get_kernel, grid, 256, kv_view(s), p.hashes, p.valid, b.total, d_counts);
+    LAUNCH(ctx, kv_expand_bits_kernel, grid, 256, p.valid, b.total, d_valid8);
+    kv_stage_done(ctx, &b);
+    if (hashes_out) CU(cudaMemcpyAsync(hashes_out, p.hashes, b.total * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    if (counts_out) CU(cudaMemcpyAsync(counts_out, d_counts, b.total, cudaMemcpyDeviceToHost, ctx->compute));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, d_valid8, b.total, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU merge
+
+extern "C" int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, int *elem_bytes)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    uint64_t n = s->bits == 4 ? s->flat_bytes * 2 : s->flat_bytes;
+    if (n_elems) *n_elems = n;
+    if (elem_bytes) *elem_bytes = s->bits == 8 ? 2 : 1;
+    if (!dev_out) return KV_OK;   // size query
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    LAUNCH(ctx, kv_widen_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_out);
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_narrow(kv_sketch *s, const void *dev_in)
+{
+    if (!s || !dev_in) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    LAUNCH(ctx, kv_narrow_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_in);
+    CU(cudaStreamSynchronize(ctx->compute));
+    s->unique_valid = false;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers)
+{
+    if (!s || (n_peers && !peer_flat)) return kv_fail(KV_EINVAL, "null argument");
+    if (n_peers < 0 || n_peers > 8) return kv_fail(KV_EINVAL, "at most 8 peers per merge");
+    if (!n_peers) return KV_OK;
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    KvPeers peers;
+    memset(&peers, 0, sizeof peers);
+    peers.n = n_peers;
+    for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)peer_flat[i];
+    uint64_t n_vec = s->flat_bytes / 16;   // flat_bytes is a multiple of 256
+    LAUNCH(ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)s->flat, n_vec, s->bits, peers);
+    CU(cudaStreamSynchronize(ctx->compute));
+    s->unique_valid = false;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64])
+{
+    if (!s || !handle_out) return kv_fail(KV_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(s->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->flat));
+    memcpy(handle_out, &h, 64);
+    return KV_OK;
+}
+
+extern "C" int kv_ipc_open(int device, const uint8_t handle[64], void **dev_ptr)
+{
+    if (!handle || !dev_ptr) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KV_OK;
+}
+
+extern "C" int kv_ipc_close(int device, void *dev_ptr)
+{
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ plumbing
+
+extern "C" int kv_stream(int device, void **cuda_stream)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    if (cuda_stream) *cuda_stream = (void *)ctx->compute;
+    return KV_OK;
+}
+
+extern "C" int kv_sync(int device)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize(ctx->copy));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_launch_count(int device, uint64_t *n)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    if (n) *n = ctx->launches;
+    return KV_OK;
+}

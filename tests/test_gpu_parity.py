@@ -1,0 +1,702 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Everything here is integer/byte work: the bar is bit-exact.  Run on the B200 box with
+``pytest -m gpu``.  Nothing in this file reads /root/reference.
+"""
+import filecmp
+import gzip
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import golden_data, golden_gen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def kv():
+    import kevlar_b200
+    if kevlar_b200._lib.device_count() < 1:
+        pytest.fail('no CUDA device: the gpu tests must run on the B200 box')
+    return kevlar_b200
+
+
+LETTERS = np.frombuffer(b'ACGT', dtype=np.uint8)
+
+
+def random_reads(seed, n, lo=20, hi=160, alphabet=b'ACGT', genome=None):
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer(alphabet, dtype=np.uint8)
+    out = []
+    for _ in range(n):
+        length = int(rng.integers(lo, hi + 1))
+        if genome is not None:
+            start = int(rng.integers(0, len(genome) - length))
+            out.append(genome[start:start + length].tobytes())
+        else:
+            out.append(letters[rng.integers(0, len(letters), size=length)].tobytes())
+    return out
+
+
+def assert_same_sketch(gpu, cpu, check_unique=True):
+    assert gpu.hashsizes() == cpu.hashsizes()
+    for t in range(len(cpu.hashsizes())):
+        assert gpu.table_bytes(t) == cpu.table_bytes(t), 'table {} differs'.format(t)
+    assert gpu.n_occupied() == cpu.n_occupied()
+    if check_unique:
+        assert gpu.n_unique_kmers() == cpu.n_unique_kmers()
+
+
+CLASSES = ['Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph', 'SmallCountgraph', 'Nodegraph']
+
+
+# ------------------------------------------------------------------ hashing
+
+@pytest.mark.parametrize('k', [1, 4, 13, 15, 16, 17, 19, 21, 25, 27, 31, 32, 33, 35, 47, 48, 49, 63, 64])
+def test_murmur_hash_matches_oracle(kv, oracle, k):
+    rng = np.random.default_rng(k)
+    kmers = [LETTERS[rng.integers(0, 4, size=k)].tobytes().decode() for _ in range(300)]
+    g = kv.khmer.Counttable(k, 1000, 2)
+    c = oracle.Counttable(k, 1000, 2)
+    got = g.hash_many(kmers)
+    want = np.array([c.hash(km) for km in kmers], dtype=np.uint64)
+    assert (got == want).all()
+    # strand symmetry (kevlar/tests/test_novel.py:68-77)
+    assert g.hash(kmers[0]) == g.hash(kv.revcom(kmers[0]))
+
+
+@pytest.mark.parametrize('k', [1, 5, 15, 16, 17, 21, 31, 32])
+def test_twobit_hash_matches_oracle(kv, oracle, k):
+    rng = np.random.default_rng(100 + k)
+    kmers = [LETTERS[rng.integers(0, 4, size=k)].tobytes().decode() for _ in range(300)]
+    g = kv.khmer.Countgraph(k, 1000, 2)
+    c = oracle.Countgraph(k, 1000, 2)
+    got = g.hash_many(kmers)
+    want = np.array([c.hash(km) for km in kmers], dtype=np.uint64)
+    assert (got == want).all()
+    assert kv.same_seq(g.reverse_hash(g.hash(kmers[3])), kmers[3])
+
+
+def test_hash_rejects_non_acgt(kv):
+    g = kv.khmer.Counttable(21, 1000, 2)
+    with pytest.raises(ValueError):
+        g.hash('ACGTACGTACNTACGTACGTA')
+    with pytest.raises(ValueError):
+        g.hash('ACGT')
+    t = kv.khmer.Counttable(35, 1e4, 4)
+    with pytest.raises(ValueError, match=r'not implemented'):
+        t.reverse_hash(t.hash('CTATGGCGGAAGGGCACACCTAACCGCGATGACGG'))
+
+
+def test_get_kmer_hashes_and_counts(kv, oracle):
+    seq = 'TGCCACGATCCGGCTATGGCGGAAGGGCACACCTAACCGCGATGACGGAGTAACTCGCAGCA'
+    for name in ('Counttable', 'Countgraph', 'SmallCounttable', 'Nodegraph'):
+        g = getattr(kv.khmer, name)(21, 1e4, 4)
+        c = getattr(oracle, name)(21, 1e4, 4)
+        g.consume(seq)
+        g.consume(seq[10:50])
+        c.consume(seq)
+        c.consume(seq[10:50])
+        assert g.get_kmer_hashes(seq) == c.get_kmer_hashes(seq)
+        assert g.get_kmer_counts(seq) == c.get_kmer_counts(seq)
+        assert g.get_kmers(seq) == c.get_kmers(seq)
+        assert g.get(seq[:21]) == c.get(seq[:21]) > 0
+        assert g.get('GATTACA' * 3) == 0
+
+
+# ------------------------------------------------------------------ golden sketches
+
+@pytest.mark.parametrize('infile,testout,numbands,band,kmers_stored', [
+    ('case', 'case', 0, 0, 973),
+    ('ctrl1', 'ctrl1', 0, 0, 973),
+    ('ctrl2', 'ctrl2', 0, 0, 966),
+    ('case', 'case-band-2-1', 2, 1, 501),
+    ('case', 'case-band-16-7', 16, 7, 68),
+])
+def test_count_simple_golden(kv, tmp_path, capsys, infile, testout, numbands, band, kmers_stored):
+    """kevlar/tests/test_count.py:45-68 -- `kevlar count` output byte-identical to the reference's."""
+    out = str(tmp_path / 'out')
+    arglist = ['count', '--ksize', '25', '--memory', '10K', '--num-bands', str(numbands), '--band', str(band),
+               out, golden_data('simple-genome-{}-reads.fa.gz'.format(infile))]
+    args = kv.cli.parser().parse_args(arglist)
+    kv.count.main(args)
+    err = capsys.readouterr().err
+    assert '600 reads processed' in err
+    assert '{:d} distinct k-mers stored'.format(kmers_stored) in err
+    assert filecmp.cmp(out + '.counttable', golden_data('simple-genome-{}.ct'.format(testout)), shallow=False)
+
+
+@pytest.mark.parametrize('filename,testkmer', [
+    ('test.countgraph', 'TGGAACCGGCAACGACGAAAA'),
+    ('test.smallcountgraph', 'CTGTACTACAGCTACTACAGT'),
+    ('test.counttable', 'CCTGATATCCGGAATCTTAGC'),
+    ('test.smallcounttable', 'GGGCCCCCATCTCTATCTTGC'),
+    ('test.nodegraph', 'GGGAACTTACCTGGGGGTGCG'),
+    ('test.nodetable', 'CTGTTCGATATGAGGAATCTG'),
+])
+def test_sketch_load_golden(kv, tmp_path, filename, testkmer):
+    """kevlar/tests/test_sketch.py:17-29, plus a byte-exact save round trip."""
+    sketch = kv.sketch.load(golden_data(filename))
+    assert sketch.get(testkmer) > 0
+    assert sketch.get('GATTACA' * 3) == 0
+    out = str(tmp_path / filename)
+    sketch.save(out)
+    assert filecmp.cmp(out, golden_data(filename), shallow=False)
+
+
+def test_sketch_load_errors(kv, tmp_path):
+    with pytest.raises(kv.sketch.KevlarSketchTypeError, match='sketch type from filename'):
+        kv.sketch.load(golden_data('test.notasketchtype'))
+    bad = tmp_path / 'bad.ct'
+    bad.write_bytes(b'NOPE' + b'\0' * 40)
+    with pytest.raises(OSError):
+        kv.sketch.load(str(bad))
+    with pytest.raises(OSError):
+        kv.sketch.load(str(tmp_path / 'missing.ct'))
+    with pytest.raises(OSError):   # a 1-bit file under an 8-bit extension
+        kv.khmer.Counttable.load(golden_data('test.nodetable'))
+
+
+def test_load_sketchfiles_fpr_gate(kv):
+    sketches = kv.sketch.load_sketchfiles([golden_data('test.counttable')], maxfpr=0.5)
+    assert sketches[0].get('CCTGATATCCGGAATCTTAGC') > 0
+    with pytest.raises(kv.sketch.KevlarUnsuitableFPRError, match='FPR too high, bailing out!!!'):
+        kv.sketch.load_sketchfiles([golden_data('test.counttable')], maxfpr=0.001)
+
+
+# ------------------------------------------------------------------ consume vs oracle
+
+@pytest.mark.parametrize('name', CLASSES)
+@pytest.mark.parametrize('k', [13, 21, 31])
+def test_consume_random_ragged(kv, oracle, name, k):
+    """Ragged reads (shorter than k, exactly k, long), tiny tables so saturation and collisions
+    are everywhere, reads crossing many 1024-base tiles."""
+    reads = random_reads(k * 7 + len(name), 700, lo=5, hi=300)
+    reads += [b'', b'A' * k, b'ACGT' * 700, b'T' * 5000, b'C' * (k - 1)]
+    bases, offs = oracle.reads_to_batch(reads)
+    g = getattr(kv.khmer, name)(k, 3000, 4)
+    c = getattr(oracle, name)(k, 3000, 4)
+    ng = g.consume_batch(bases, offs)
+    nc = c.consume_batch(bases, offs)
+    assert ng == nc
+    assert_same_sketch(g, c)
+    # second batch on top of the first: order-dependent n_unique must still agree
+    reads2 = random_reads(99, 300, lo=k, hi=120)
+    bases2, offs2 = oracle.reads_to_batch(reads2)
+    assert g.consume_batch(bases2, offs2) == c.consume_batch(bases2, offs2)
+    assert_same_sketch(g, c)
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Countgraph'])
+def test_consume_saturation(kv, oracle, name):
+    """Thousands of copies of the same k-mers: every counter must stop exactly at 255 / 15,
+    and the neighbouring counters in the same 32-bit word must be untouched."""
+    reads = [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTT' * 3] * 400 + random_reads(5, 50, 40, 60)
+    bases, offs = oracle.reads_to_batch(reads)
+    g = getattr(kv.khmer, name)(21, 500, 4)
+    c = getattr(oracle, name)(21, 500, 4)
+    assert g.consume_batch(bases, offs) == c.consume_batch(bases, offs)
+    assert_same_sketch(g, c)
+    top = 15 if name.startswith('Small') else 255
+    assert g.get('ACGTTGCAAGGCTTAACCGGT') == top
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'Nodegraph'])
+def test_consume_cleaning(kv, oracle, name):
+    """Lower case is upper-cased and anything outside ACGT counts as 'A' in the count path
+    (unpinned by the reference, pinned here against the oracle)."""
+    reads = random_reads(3, 200, 30, 90, alphabet=b'ACGTNacgtnRY-')
+    bases, offs = oracle.reads_to_batch(reads)
+    g = getattr(kv.khmer, name)(19, 5000, 4)
+    c = getattr(oracle, name)(19, 5000, 4)
+    assert g.consume_batch(bases, offs) == c.consume_batch(bases, offs)
+    assert_same_sketch(g, c)
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'])
+@pytest.mark.parametrize('num_bands,band', [(2, 0), (2, 1), (9, 2), (23, 19), (16, 15)])
+def test_consume_banding(kv, oracle, name, num_bands, band):
+    reads = random_reads(num_bands * 31 + band, 400, 30, 150)
+    bases, offs = oracle.reads_to_batch(reads)
+    g = getattr(kv.khmer, name)(19, 20000, 4)
+    c = getattr(oracle, name)(19, 20000, 4)
+    ng = g.consume_batch(bases, offs, num_bands=num_bands, band=band)
+    nc = c.consume_batch(bases, offs, num_bands=num_bands, band=band)
+    assert ng == nc
+    assert_same_sketch(g, c)
+
+
+def test_banding_partitions_the_kmers(kv, oracle):
+    """Size-independent property: the bands partition the k-mer occurrences, so the per-band
+    k-mer counts add up to the unbanded count."""
+    reads = random_reads(11, 500, 50, 150)
+    bases, offs = oracle.reads_to_batch(reads)
+    full = kv.khmer.Counttable(25, 50000, 4).consume_batch(bases, offs)
+    parts = [kv.khmer.Counttable(25, 50000, 4).consume_batch(bases, offs, num_bands=8, band=b) for b in range(8)]
+    assert sum(parts) == full
+    with pytest.raises(ValueError):
+        kv.khmer.Counttable(25, 50000, 4).consume_batch(bases, offs, num_bands=4, band=4)
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Nodetable'])
+@pytest.mark.parametrize('consume_masked', [False, True])
+@pytest.mark.parametrize('banded', [False, True])
+def test_consume_with_mask(kv, oracle, name, consume_masked, banded):
+    genome = LETTERS[np.random.default_rng(1).integers(0, 4, size=6000)]
+    reads = random_reads(21, 400, 40, 120, genome=genome)
+    maskreads = random_reads(22, 60, 40, 120, genome=genome)
+    bases, offs = oracle.reads_to_batch(reads)
+    mb, mo = oracle.reads_to_batch(maskreads)
+    gm = kv.khmer.Nodetable(21, 1e4, 4)
+    cm = oracle.Nodetable(21, 1e4, 4)
+    gm.consume_batch(mb, mo)
+    cm.consume_batch(mb, mo)
+    g = getattr(kv.khmer, name)(21, 1e4, 4)
+    c = getattr(oracle, name)(21, 1e4, 4)
+    kw = dict(mask=None, threshold=1 if consume_masked else 0, consume_masked=consume_masked)
+    if banded:
+        kw.update(num_bands=3, band=1)
+    ng = g.consume_batch(bases, offs, **dict(kw, mask=gm))
+    nc = c.consume_batch(bases, offs, **dict(kw, mask=cm))
+    assert ng == nc and ng > 0
+    assert_same_sketch(g, c)
+
+
+def test_count_cli_with_mask_golden(kv, tmp_path, capsys):
+    """kevlar/tests/test_count.py:153-166: `36898 distinct k-mers stored`."""
+    mask = kv.khmer.Nodetable(21, 1e4, 4)
+    mask.consume('CACCAATCCGTACGGAGAGCCGTATATATAGACTGCTATACTATTGGATCGTACGGGGC')
+    maskfile = str(tmp_path / 'mask.nt')
+    mask.save(maskfile)
+    arglist = ['count', '--ksize', '21', '--mask', maskfile, '--memory', '1M', str(tmp_path / 'out.sct'),
+               golden_data('bogus-genome/refr.fa')]
+    kv.count.main(kv.cli.parser().parse_args(arglist))
+    assert '36898 distinct k-mers stored' in capsys.readouterr().err
+    assert os.path.exists(str(tmp_path / 'out.sct.counttable'))
+
+
+@pytest.mark.parametrize('count,smallcount,count_masked,kpresent,kabsent', [
+    (True, True, True, 'CACCAATCCGTACGGAGAGCC', 'GAATCGGTGGCTGGTTGCCGT'),
+    (True, False, True, 'CACCAATCCGTACGGAGAGCC', 'GAATCGGTGGCTGGTTGCCGT'),
+    (False, False, True, 'CACCAATCCGTACGGAGAGCC', 'GAATCGGTGGCTGGTTGCCGT'),
+    (True, True, False, 'GAATCGGTGGCTGGTTGCCGT', 'CACCAATCCGTACGGAGAGCC'),
+    (True, False, False, 'GAATCGGTGGCTGGTTGCCGT', 'CACCAATCCGTACGGAGAGCC'),
+    (False, False, False, 'GAATCGGTGGCTGGTTGCCGT', 'CACCAATCCGTACGGAGAGCC'),
+])
+def test_load_sample_seqfile_withmask(kv, count, smallcount, count_masked, kpresent, kabsent):
+    """kevlar/tests/test_count.py:130-150."""
+    mask = kv.khmer.Nodetable(21, 1e4, 4)
+    mask.consume('CACCAATCCGTACGGAGAGCCGTATATATAGACTGCTATACTATTGGATCGTACGGGGC')
+    sketch = kv.count.load_sample_seqfile([golden_data('bogus-genome/refr.fa')], 21, 1e6, mask=mask,
+                                          consume_masked=count_masked, count=count, smallcount=smallcount)
+    assert sketch.get(kpresent) > 0
+    assert sketch.get(kabsent) == 0
+    assert sketch.get('GATTACAGATTACAGATTACA') == 0
+
+
+@pytest.mark.parametrize('cmd,name,outname', [
+    (['--ksize', '21', '--memory', '200K', '-c', '4'], 'count_refr_small', 'o.sct'),
+    (['--ksize', '21', '--memory', '100K', '-c', '1', '--num-bands', '3', '--band', '2'], 'count_refr_node_band', 'o.nt'),
+])
+def test_count_cli_generated_golden(kv, tmp_path, capsys, cmd, name, outname):
+    """Outputs of the reference's own count.py over the oracle (tests/golden/make_golden.py)."""
+    out = str(tmp_path / outname)
+    kv.count.main(kv.cli.parser().parse_args(['count'] + cmd + [out, golden_data('bogus-genome/refr.fa')]))
+    golden = golden_gen(name + ('.sct' if outname.endswith('.sct') else '.nt'))
+    assert filecmp.cmp(out, golden, shallow=False)
+    want = open(golden_gen(name + '.log')).read()
+    got = capsys.readouterr().err
+    for line in re.findall(r'\d+ reads processed, \d+ distinct k-mers stored', want):
+        assert line in got
+
+
+def test_count_problematic(kv):
+    """kevlar/tests/test_count.py:83-99."""
+    args = kv.cli.parser().parse_args(['count', '--ksize', '21', '--memory', '200K', '--band', '2', 'bogusoutput',
+                                       golden_data('trio1/ctrl1.fq.gz')])
+    with pytest.raises(ValueError, match=r'Must specify --num-bands and --band together'):
+        kv.count.main(args)
+    args = kv.cli.parser().parse_args(['count', '--ksize', '21', '--memory', '97', 'bogusoutput',
+                                       golden_data('trio1/ctrl1.fq.gz')])
+    with pytest.raises(kv.sketch.KevlarUnsuitableFPRError):
+        kv.count.main(args)
+
+
+@pytest.mark.parametrize('mask,numbands,band', [(False, None, None), (False, 9, 2), (True, None, None), (True, 23, 19)])
+def test_load_threading(kv, oracle, mask, numbands, band):
+    """kevlar/tests/test_count.py:31-42, and the 2-thread result must equal the oracle's
+    (saturating increments commute)."""
+    def build(mod):
+        m = None
+        if mask:
+            m = mod.Counttable(19, 1e4, 4)
+            m.consume('TGAGGGGACTAGGTGATCAGGTGAGGGTTTCCCAGTTCCCGAAGATGACT')
+            m.consume('GATCTTTCGCTCCCTGTCATCAAGGAGTGATACGCGAAGTGCGTCCCCTT')
+        return m
+    gpu = kv.count.load_sample_seqfile([golden_data('trio1/case1.fq.gz')], 19, 1e7, mask=build(kv.khmer),
+                                       numbands=numbands, band=band, numthreads=2)
+    cpu = oracle.Counttable(19, 1e7 / 4, 4)
+    kw = {}
+    parser = oracle.ReadParser(golden_data('trio1/case1.fq.gz'))
+    m = build(oracle)
+    if m is not None and numbands:
+        cpu.consume_seqfile_banding_with_mask(parser, numbands, band, m, threshold=0, consume_masked=False)
+    elif m is not None:
+        cpu.consume_seqfile_with_mask(parser, m, threshold=0, consume_masked=False)
+    elif numbands:
+        cpu.consume_seqfile_banding(parser, numbands, band)
+    else:
+        cpu.consume_seqfile(parser)
+    assert_same_sketch(gpu, cpu, check_unique=False)
+
+
+def test_memory_sizing(kv):
+    """kevlar/tests/test_count.py:169-182."""
+    for count, smallcount, kind in [(False, False, 'nodegraph'), (True, False, 'countgraph'), (True, True, 'smallcountgraph')]:
+        sketch = kv.count.load_sample_seqfile([golden_data('bogus-genome/refr.fa')], 21, 2e6, count=count,
+                                              smallcount=smallcount)
+        actual = sum(sketch.hashsizes()) / kv.khmer._buckets_per_byte[kind]
+        assert actual / 2e6 == pytest.approx(1.0, rel=1e-4)
+
+
+def test_chunked_consume_equals_unchunked(kv, oracle, monkeypatch):
+    """A batch larger than the scratch chunk is processed in several chunks: same result."""
+    reads = random_reads(8, 3000, 80, 120)
+    bases, offs = oracle.reads_to_batch(reads)
+    c = oracle.Counttable(31, 1e5, 4)
+    c.consume_batch(bases, offs)
+    g = kv.khmer.Counttable(31, 1e5, 4)
+    half = len(reads) // 2
+    cut = int(offs[half])
+    g.consume_batch(bases[:cut], offs[:half + 1])
+    g.consume_batch(bases[cut:], offs[half:] - offs[half])
+    assert_same_sketch(g, c)
+
+
+# ------------------------------------------------------------------ add / get lists
+
+@pytest.mark.parametrize('name', CLASSES)
+def test_add_get_lists(kv, oracle, name):
+    rng = np.random.default_rng(12)
+    kmers = [LETTERS[rng.integers(0, 4, size=21)].tobytes().decode() for _ in range(400)]
+    kmers = kmers + kmers[:150] + kmers[:40] * 20
+    g = getattr(kv.khmer, name)(21, 700, 4)
+    c = getattr(oracle, name)(21, 700, 4)
+    g.add_many(kmers)
+    for km in kmers:
+        c.add(km)
+    assert_same_sketch(g, c)
+    assert list(g.get_many(kmers[:400])) == [c.get(km) for km in kmers[:400]]
+    g.add(kmers[0])
+    c.add(kmers[0])
+    assert g.get(kmers[0]) == c.get(kmers[0])
+    assert g.get(g.hash(kmers[1])) == c.get(kmers[1])
+
+
+# ------------------------------------------------------------------ novel
+
+def _novel_inputs(oracle, kv, seed=5, k=25, mem=2e5):
+    rng = np.random.default_rng(seed)
+    genome = LETTERS[rng.integers(0, 4, size=8000)]
+    child = genome.copy()
+    for pos in (2000, 5000, 5003):
+        child[pos] = LETTERS[(np.where(LETTERS == child[pos])[0][0] + 1) % 4]
+    samples = [random_reads(seed + 1, 2500, 60, 110, genome=child),
+               random_reads(seed + 2, 2500, 60, 110, genome=genome),
+               random_reads(seed + 3, 2500, 60, 110, genome=genome)]
+    samples[0] += [b'ACGTNACGT' * 10, b'acgt' * 20, b'AC', b'']
+    gpu, cpu = [], []
+    for seqs in samples:
+        bases, offs = oracle.reads_to_batch(seqs)
+        g, c = kv.khmer.Counttable(k, mem / 4, 4), oracle.Counttable(k, mem / 4, 4)
+        g.consume_batch(bases, offs)
+        c.consume_batch(bases, offs)
+        gpu.append(g)
+        cpu.append(c)
+    return samples, gpu, cpu
+
+
+@pytest.mark.parametrize('case_min,ctrl_max,screen,numbands,bm1', [
+    (6, 1, None, None, 0), (5, 0, None, None, 0), (8, 1, 3, None, 0), (6, 1, 6, None, 0),
+    (6, 1, None, 2, 0), (6, 1, None, 4, 2), (6, 1, None, 8, -1), (3, 2, 2, 4, 1),
+])
+def test_novel_batch_matches_oracle(kv, oracle, case_min, ctrl_max, screen, numbands, bm1):
+    samples, gpu, cpu = _novel_inputs(oracle, kv)
+    bases, offs = oracle.reads_to_batch(samples[0])
+    hits, flags, _ = kv.khmer.novel_batch(gpu[:1], gpu[1:], bases, offs, case_min, ctrl_max, screen=screen,
+                                          num_bands=numbands, band_minus_1=bm1)
+    ohits, oflags = oracle.novel_batch(cpu[:1], cpu[1:], bases, offs, case_min, ctrl_max, screen=screen,
+                                       numbands=numbands, band_minus_1=bm1)
+    assert len(hits) == len(ohits)
+    assert (hits['read'] == ohits['read']).all()
+    assert (hits['offset'] == ohits['offset']).all()
+    assert (hits['abund'][:, :3] == ohits['abund'][:, :3]).all()
+    assert (flags == oflags).all()
+    if numbands is None and screen is None:
+        assert len(hits) > 0
+
+
+def test_novel_two_cases_mixed_types(kv, oracle):
+    """Two case sketches and controls of different counter widths in one scan."""
+    samples, gpu, cpu = _novel_inputs(oracle, kv, seed=9, k=21)
+    bases, offs = oracle.reads_to_batch(samples[0])
+    g2, c2 = kv.khmer.SmallCounttable(21, 40000, 4), oracle.SmallCounttable(21, 40000, 4)
+    g3, c3 = kv.khmer.Nodetable(21, 90000, 4), oracle.Nodetable(21, 90000, 4)
+    for s, (gx, cx) in zip((samples[0], samples[1]), ((g2, c2), (g3, c3))):
+        b, o = oracle.reads_to_batch(s)
+        gx.consume_batch(b, o)
+        cx.consume_batch(b, o)
+    hits, flags, _ = kv.khmer.novel_batch([gpu[0], g2], [gpu[1], gpu[2], g3], bases, offs, 5, 1)
+    ohits, oflags = oracle.novel_batch([cpu[0], c2], [cpu[1], cpu[2], c3], bases, offs, 5, 1)
+    assert len(hits) == len(ohits)
+    assert (hits['read'] == ohits['read']).all() and (hits['offset'] == ohits['offset']).all()
+    assert (hits['abund'][:, :5] == ohits['abund'][:, :5]).all()
+    assert (flags == oflags).all()
+
+
+def _run_cli(kv, arglist):
+    args = kv.cli.parser().parse_args(arglist)
+    log, out = io.StringIO(), io.StringIO()
+    saved = kv.logstream
+    kv.logstream = log
+    import contextlib
+    try:
+        with contextlib.redirect_stdout(out):
+            kv.cli.mains[args.cmd](args)
+    finally:
+        kv.logstream = saved
+    logtext = re.sub(r'\d+\.\d\d sec(onds)?', 'T sec', log.getvalue())
+    return out.getvalue(), logtext.replace(golden_data(''), 'DATA/')
+
+
+def _same_log(got, want):
+    """Log lines equal up to the input file suffix (trio1 fixtures are stored gzipped)."""
+    got = got.replace('.fq.gz"', '.fq"')
+    want = want.replace('.fq.gz"', '.fq"')
+    assert got == want
+
+
+NA = ['microtrios/trio-na-{}.fq.gz'.format(w) for w in ('proband', 'mother', 'father')]
+
+
+def test_novel_cli_microtrio_golden(kv):
+    """End to end: byte-identical to the reference's novel.py over the oracle, which in turn
+    equals the novel output shipped with the reference (microtrios/novel-na.augfastq.gz)."""
+    out, log = _run_cli(kv, ['novel', '-k', '31', '--case-min', '5', '--ctrl-max', '1', '--memory', '500K',
+                             '--case', golden_data(NA[0]), '--control', golden_data(NA[1]),
+                             '--control', golden_data(NA[2])])
+    assert out == open(golden_gen('novel_microtrio_na.out')).read()
+    _same_log(log, open(golden_gen('novel_microtrio_na.log')).read())
+    shipped = gzip.open(golden_data('microtrios/novel-na.augfastq.gz'), 'rt').read()
+    shipped = ''.join(line for line in shipped.splitlines(True) if not line.startswith('#mateseq='))
+    assert out == shipped
+
+
+@pytest.mark.parametrize('nb,b,name', [('2', '2', 'novel_microtrio_na_band2of2'), ('4', '3', 'novel_microtrio_na_band3of4')])
+def test_novel_cli_banded_golden(kv, nb, b, name):
+    """kevlar/tests/test_novel.py:80-105 configuration; checks the band quirk end to end."""
+    out, log = _run_cli(kv, ['novel', '--case', golden_data(NA[0]), '--ksize', '25', '--case-min', '7',
+                             '--control', golden_data(NA[2]), '--control', golden_data(NA[1]),
+                             '--num-bands', nb, '--band', b, '--ctrl-max', '0', '--memory', '500K'])
+    assert out == open(golden_gen(name + '.out')).read()
+    _same_log(log, open(golden_gen(name + '.log')).read())
+    for line in out.split('\n'):
+        if line.endswith('#'):
+            m = re.search(r'(\d+) (\d+) (\d+)#$', line)
+            assert int(m.group(1)) >= 7 and m.group(2) == '0' and m.group(3) == '0'
+
+
+@pytest.mark.parametrize('skip', [True, False])
+def test_novel_cli_trio1_golden(kv, skip):
+    """kevlar/tests/test_novel.py:179-207: '(skipped 1001 reads)', '29 unique novel kmers in 14 reads'."""
+    cmd = ['novel', '--ctrl-max', '0', '--case-min', '6', '--case', golden_data('trio1/case1.fq.gz'),
+           '--control', golden_data('trio1/ctrl1.fq.gz'), '--control', golden_data('trio1/ctrl2.fq.gz')]
+    name = 'novel_trio1'
+    if skip:
+        cmd += ['--skip-until', 'bogus-genome-chr1_115_449_0:0:0_0:0:0_1f4/1']
+        name += '_skipuntil'
+    out, log = _run_cli(kv, cmd)
+    assert out == open(golden_gen(name + '.out')).read()
+    _same_log(log, open(golden_gen(name + '.log')).read())
+    if skip:
+        assert 'Found read bogus-genome-chr1_115_449_0:0:0_0:0:0_1f4/1 (skipped 1001 reads)' in log
+        assert '29 unique novel kmers in 14 reads' in log
+
+
+def test_novel_skip_until_missing(kv):
+    out, log = _run_cli(kv, ['novel', '--ctrl-max', '0', '--case-min', '6', '--case', golden_data('trio1/case1.fq.gz'),
+                             '--control', golden_data('trio1/ctrl1.fq.gz'), '--control',
+                             golden_data('trio1/ctrl2.fq.gz'), '--skip-until', 'BOGUSREADNAME'])
+    assert 'Found read' not in log and '(skipped ' not in log
+    assert 'Found 0 instances of 0 unique novel kmers in 0 reads' in log
+    assert out == ''
+
+
+@pytest.mark.parametrize('screen,name', [(['--abund-screen', '3'], 'novel_abund_screen'), ([], 'novel_no_abund_screen')])
+def test_novel_cli_abund_screen_golden(kv, screen, name):
+    """kevlar/tests/test_novel.py:167-176."""
+    out, log = _run_cli(kv, ['novel', '--ksize', '25', '--ctrl-max', '1', '--case-min', '8',
+                             '--case', golden_data('screen-case.fa'), '--control', golden_data('screen-ctrl.fa')] + screen)
+    assert out == open(golden_gen(name + '.out')).read()
+    _same_log(log, open(golden_gen(name + '.log')).read())
+    if screen:
+        assert '>seq_error' not in out
+
+
+def test_novel_cli_load_counts_golden(kv):
+    """kevlar/tests/test_novel.py:268-282: pre-computed sketches + a read with an N."""
+    out, log = _run_cli(kv, ['novel', '-k', '25', '--case', golden_data('simple-genome-case-reads.fa.gz'),
+                             golden_data('ambig.fasta'), '--case-counts', golden_data('simple-genome-case.ct'),
+                             '--control-counts', golden_data('simple-genome-ctrl1.ct'),
+                             golden_data('simple-genome-ctrl2.ct')])
+    assert 'counttables for 2 sample(s) provided' in log
+    assert out == open(golden_gen('novel_load_counts.out')).read()
+    _same_log(log, open(golden_gen('novel_load_counts.log')).read())
+
+
+def test_novel_save_counts(kv, tmp_path):
+    """kevlar/tests/test_novel.py:210-241: --save-*-counts files equal `kevlar count` outputs."""
+    d = str(tmp_path)
+    for ind, src in zip(('proband', 'mother', 'father'), NA):
+        kv.count.main(kv.cli.parser().parse_args(['count', '--ksize', '27', '--memory', '500K',
+                                                  '{}/{}.ct'.format(d, ind), golden_data(src)]))
+    kv.novel.main(kv.cli.parser().parse_args([
+        'novel', '--ksize', '27', '--out', d + '/novel.augfastq.gz', '--save-case-counts', d + '/kid.ct',
+        '--save-ctrl-counts', d + '/mom.ct', d + '/dad.ct', '--case', golden_data(NA[0]),
+        '--control', golden_data(NA[1]), '--control', golden_data(NA[2]), '--memory', '500K']))
+    for a, b in (('father', 'dad'), ('mother', 'mom'), ('proband', 'kid')):
+        assert filecmp.cmp('{}/{}.ct'.format(d, a), '{}/{}.ct'.format(d, b), shallow=False)
+    import hashlib
+    import json
+    manifest = json.load(open(os.path.join(os.path.dirname(golden_gen('x')), '..', 'MANIFEST.json')))
+    digest = hashlib.sha256(open(d + '/proband.ct', 'rb').read()).hexdigest()
+    assert digest == manifest['gen/count_na_proband.ct']['sha256']
+
+
+def test_novel_api_errors(kv):
+    """kevlar/tests/test_novel.py:25-37."""
+    with pytest.raises(ValueError, match=r'Must specify `numbands` and `band` together'):
+        list(kv.novel.novel(None, [], [], numbands=4))
+    with pytest.raises(ValueError, match=r'Must specify `numbands` and `band` together'):
+        list(kv.novel.novel(None, [], [], band=0))
+    with pytest.raises(ValueError, match=r'`band` must be a value between 0 and 3'):
+        list(kv.novel.novel(None, [], [], numbands=4, band=-1))
+
+
+def test_novel_generic_record_stream(kv, oracle):
+    """`novel` accepts any iterable of records (the reference's Python-API use)."""
+    samples, gpu, cpu = _novel_inputs(oracle, kv, seed=17)
+    stream = [kv.sequence.Record('r{}'.format(i), s.decode(), 'I' * len(s)) for i, s in enumerate(samples[0])]
+    recs = list(kv.novel.novel(stream, gpu[:1], gpu[1:], ksize=25, casemin=6, ctrlmax=1))
+    bases, offs = oracle.reads_to_batch(samples[0])
+    ohits, _ = oracle.novel_batch(cpu[:1], cpu[1:], bases, offs, 6, 1)
+    assert sum(len(r.annotations) for r in recs) == len(ohits)
+    assert [r.name for r in recs] == ['r{}'.format(i) for i in sorted(set(ohits['read'].tolist()))]
+    for ikmer in recs[0].annotations:
+        assert ikmer.abund[0] >= 6 and max(ikmer.abund[1:]) <= 1
+
+
+def test_kmer_is_interesting(kv, oracle):
+    samples, gpu, cpu = _novel_inputs(oracle, kv, seed=23)
+    bases, offs = oracle.reads_to_batch(samples[0])
+    ohits, _ = oracle.novel_batch(cpu[:1], cpu[1:], bases, offs, 6, 1)
+    h = ohits[0]
+    seq = samples[0][int(h['read'])].decode()
+    kmer = seq[int(h['offset']):int(h['offset']) + 25]
+    ok, discard, ca, co = kv.novel.kmer_is_interesting(kmer, gpu[:1], gpu[1:], case_min=6, ctrl_max=1)
+    assert ok and not discard and ca == [int(h['abund'][0])] and co == [int(h['abund'][1]), int(h['abund'][2])]
+    ok, discard, ca, co = kv.novel.kmer_is_interesting('GATTACA' * 3 + 'GATT', gpu[:1], gpu[1:], case_min=6,
+                                                       ctrl_max=1, screen_thresh=2)
+    assert not ok and discard and ca == [] and co == []
+
+
+# ------------------------------------------------------------------ filter
+
+def _filter_text(kv, readfile, **kw):
+    out = io.StringIO()
+    saved, kv.logstream = kv.logstream, io.StringIO()
+    try:
+        recs = list(kv.filter.filter(readfile, **kw))
+    finally:
+        kv.logstream = saved
+    for rec in recs:
+        kv.print_augmented_fastx(rec, out)
+    return recs, out.getvalue()
+
+
+def test_filter_alpha_golden(kv):
+    """kevlar/tests/test_filter.py:27-41 (memory=500: collisions everywhere)."""
+    recs, text = _filter_text(kv, golden_data('collect.alpha.txt'), memory=500)
+    assert len(recs) == 8
+    assert text == open(golden_gen('filter_alpha.out')).read()
+
+
+def test_filter_worm_golden(kv):
+    """kevlar/tests/test_filter.py:61-73."""
+    recs, text = _filter_text(kv, golden_data('worm.augfasta'), memory=1000, casemin=5, ctrlmax=0)
+    assert len(recs) == 5
+    assert text == open(golden_gen('filter_worm.out')).read()
+
+
+@pytest.mark.parametrize('maskkind,nkmers,ninst', [(None, 424, 5782), ('refr', 424, 5782), ('mask.nt', 13, 171)])
+def test_filter_ctrl3(kv, maskkind, nkmers, ninst):
+    """kevlar/tests/test_filter.py:44-58."""
+    mask = None
+    if maskkind == 'refr':
+        mask = kv.count.load_sample_seqfile([golden_data('bogus-genome/refr.fa')], 13, 1e7, count=False)
+    elif maskkind:
+        mask = kv.sketch.load(golden_data('bogus-genome/mask.nt'))
+    recs, _ = _filter_text(kv, golden_data('trio1/novel_3_1,2.txt'), memory=1e7, mask=mask)
+    seen = {}
+    for read in recs:
+        for ikmer in read.annotations:
+            key = kv.revcommin(read.ikmerseq(ikmer))
+            seen[key] = seen.get(key, 0) + 1
+    assert len(seen) == nkmers and sum(seen.values()) == ninst
+
+
+def test_filter_main_golden(kv):
+    """kevlar/tests/test_filter.py:76-87."""
+    out, log = _run_cli(kv, ['filter', '--mask', golden_data('bogus-genome/mask.nt'), '--memory', '10M',
+                             '--max-fpr', '0.001', '--case-min', '6', golden_data('trio1/novel_3_1,2.txt')])
+    assert 'Processed 178 reads' in log and 'Validated 18 reads' in log
+    assert out == open(golden_gen('filter_trio1_mask.out')).read()
+    assert log == open(golden_gen('filter_trio1_mask.log')).read()
+
+
+# ------------------------------------------------------------------ larger, property-based
+
+def test_full_size_properties(kv, oracle):
+    """BASELINE config 2 shape (300k reads x 100 bp, k=31, 64 MB sketch): too slow for the
+    Python side of the oracle, so checked through size-independent properties plus a
+    multi-threaded oracle run (saturating counts are order-independent)."""
+    rng = np.random.default_rng(42)
+    genome = LETTERS[rng.integers(0, 4, size=1000000)]
+    n = 300000
+    starts = rng.integers(0, len(genome) - 100, size=n)
+    idx = starts[:, None] + np.arange(100)[None, :]
+    bases = genome[idx].reshape(-1).copy()
+    err = rng.random(len(bases)) < 0.005
+    bases[err] = LETTERS[rng.integers(0, 4, size=int(err.sum()))]
+    offs = (np.arange(n + 1) * 100).astype(np.uint64)
+    g = kv.khmer.Counttable(31, 64e6 / 4, 4)
+    nk = g.consume_batch(bases, offs)
+    assert nk == n * 70
+    c = oracle.Counttable(31, 64e6 / 4, 4)
+    assert c.consume_batch(bases, offs, threads=8) == nk
+    assert_same_sketch(g, c, check_unique=False)
+    # linearity: consuming the batch in two halves into a fresh sketch gives the same tables
+    g2 = kv.khmer.Counttable(31, 64e6 / 4, 4)
+    half = n // 2
+    g2.consume_batch(bases[:half * 100], offs[:half + 1])
+    g2.consume_batch(bases[half * 100:], offs[half:] - offs[half])
+    for t in range(4):
+        assert g2.table_bytes(t) == g.table_bytes(t)
+    assert g2.n_unique_kmers() == g.n_unique_kmers()
+    # every k-mer of a read just counted is present at least once
+    counts = g.get_kmer_counts(bases[:100].tobytes().decode())
+    assert min(counts) >= 1
