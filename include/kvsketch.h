@@ -162,11 +162,15 @@ int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, const uint64_
  *                     written to dev_out (device pointer, *n_elems elements).
  *   kv_sketch_narrow: summed elements -> clamp to 255 / 15 / (bytes as is) and store back.
  * kv_sketch_merge_peers does the same in ONE kernel over peer-mapped tables of the other
- * GPUs (device pointers valid on this device, e.g. from CUDA IPC): saturating add of
- * n_peers flat tables into this sketch. */
+ * GPUs (device pointers valid on this device, e.g. from CUDA IPC): saturating add of bytes
+ * [byte_lo, byte_hi) of n_peers flat tables into this sketch (multiples of 256; hi = 0 means
+ * the whole table).  With each rank merging only its own 1/N slice and then pulling the
+ * finished slices of its peers with kv_sketch_copy_from_peer, this is a reduce-scatter +
+ * all-gather made of plain NVLink loads, with no staging copy. */
 int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, int *elem_bytes);
 int kv_sketch_narrow(kv_sketch *s, const void *dev_in);
-int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers);
+int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi);
+int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uint64_t byte_lo, uint64_t byte_hi);
 /* CUDA IPC plumbing for kv_sketch_merge_peers: export this sketch's flat allocation
  * (64-byte handle) / map a peer's.  */
 int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);

@@ -62,7 +62,8 @@ SYMBOLS = [
     ('kv_kmer_counts_batch', c_int, [_P, _P, _P, c_uint64, c_int, _P, _P, _P]),
     ('kv_sketch_widen', c_int, [_P, _P, POINTER(c_uint64), POINTER(c_int)]),
     ('kv_sketch_narrow', c_int, [_P, _P]),
-    ('kv_sketch_merge_peers', c_int, [_P, POINTER(_P), c_int]),
+    ('kv_sketch_merge_peers', c_int, [_P, POINTER(_P), c_int, c_uint64, c_uint64]),
+    ('kv_sketch_copy_from_peer', c_int, [_P, _P, c_uint64, c_uint64]),
     ('kv_sketch_ipc_export', c_int, [_P, _P]),
     ('kv_ipc_open', c_int, [c_int, _P, POINTER(_P)]),
     ('kv_ipc_close', c_int, [c_int, _P]),

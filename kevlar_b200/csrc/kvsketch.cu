@@ -903,11 +903,21 @@ extern "C" int kv_sketch_narrow(kv_sketch *s, const void *dev_in)
     return KV_OK;
 }
 
-extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers)
+static int kv_check_range(const kv_sketch *s, uint64_t &lo, uint64_t &hi)
+{
+    if (hi == 0) hi = s->flat_bytes;
+    if (lo > hi || hi > s->flat_bytes || (lo & 255) || (hi & 255))
+        return kv_fail(KV_EINVAL, "byte range must be 256-byte aligned and inside the table storage");
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo,
+                                     uint64_t byte_hi)
 {
     if (!s || (n_peers && !peer_flat)) return kv_fail(KV_EINVAL, "null argument");
     if (n_peers < 0 || n_peers > 8) return kv_fail(KV_EINVAL, "at most 8 peers per merge");
-    if (!n_peers) return KV_OK;
+    KV_TRY(kv_check_range(s, byte_lo, byte_hi));
+    if (!n_peers || byte_lo == byte_hi) return KV_OK;
     KvCtx *ctx;
     KV_TRY(kv_ctx_get(s->device, &ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -915,9 +925,25 @@ extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat,
     KvPeers peers;
     memset(&peers, 0, sizeof peers);
     peers.n = n_peers;
-    for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)peer_flat[i];
-    uint64_t n_vec = s->flat_bytes / 16;   // flat_bytes is a multiple of 256
-    LAUNCH(ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)s->flat, n_vec, s->bits, peers);
+    for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)((const uint8_t *)peer_flat[i] + byte_lo);
+    uint64_t n_vec = (byte_hi - byte_lo) / 16;
+    LAUNCH(ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
+    CU(cudaStreamSynchronize(ctx->compute));
+    s->unique_valid = false;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uint64_t byte_lo, uint64_t byte_hi)
+{
+    if (!s || !peer_flat) return kv_fail(KV_EINVAL, "null argument");
+    KV_TRY(kv_check_range(s, byte_lo, byte_hi));
+    if (byte_lo == byte_hi) return KV_OK;
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->flat + byte_lo, (const uint8_t *)peer_flat + byte_lo, byte_hi - byte_lo,
+                       cudaMemcpyDeviceToDevice, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;

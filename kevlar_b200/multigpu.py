@@ -1,0 +1,206 @@
+"""Multi-GPU count + novel: one process per GPU (torchrun), reads sharded across ranks.
+
+SURVEY.md 8(e), plan A.  Reads are independent units and saturating increments commute, so
+
+    final[bucket] = min(MAX, sum over ranks of partial[bucket])
+
+holds exactly (each partial is itself clamped at MAX, which does not change the clamped sum).
+Every rank counts its shard of reads into a full-size partial sketch, then the partial
+sketches are merged -- the one real exchange step of the path -- and every rank holds the
+complete sketch.  The novel scan then runs shard-local against the replicated sketches with
+no further communication; ranks only exchange their (tiny) hit lists at the end.
+
+Merge strategies (`merge_sketch(..., how=)`):
+  'allreduce'  widen counters on the GPU (kv_sketch_widen: u8->u16, nibble->u8, bits->bytes),
+               NCCL all-reduce (SUM; MAX-free OR for bit tables via all-gather), clamp + repack
+               (kv_sketch_narrow).  Transport by NCCL over NVLink/NVSwitch, arithmetic by our kernels.
+  'allgather'  NCCL all-gather of the raw tables, then ONE saturating-merge kernel
+               (kv_sketch_merge_peers, per-byte __vaddus4) over the gathered copies.
+  'p2p'        no NCCL on the data path: ranks exchange CUDA IPC handles once and the merge kernel
+               reads the peers' tables directly over NVLink (peer-mapped loads).
+
+torch / torch.distributed are plumbing here (rendezvous, NCCL communicator, device buffers).
+"""
+import ctypes
+import os
+from ctypes import byref, c_int, c_uint64, c_void_p
+
+import numpy as np
+
+from kevlar_b200 import _lib
+from kevlar_b200._lib import check, lib
+
+
+def dist():
+    import torch.distributed as td
+    return td
+
+
+def init_from_env(backend=None):
+    """Join the torchrun rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).  Returns
+    (rank, world).  Single-process runs need no rendezvous."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if world > 1:
+        import torch
+        td = dist()
+        if not td.is_initialized():
+            if backend is None:
+                backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+            if backend == 'nccl':
+                torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+            td.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world
+
+
+def shard_bounds(n_items, rank, world):
+    """Contiguous, near-equal split of n_items over `world` ranks: [lo, hi) for `rank`."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(bases, offsets, rank, world):
+    """The slice of a (bases, offsets) batch that `rank` owns: reads [lo, hi) with offsets
+    rebased to start at 0.  Every read lands on exactly one rank."""
+    offsets = np.asarray(offsets, dtype=np.uint64)
+    lo, hi = shard_bounds(len(offsets) - 1, rank, world)
+    b0, b1 = int(offsets[lo]), int(offsets[hi])
+    return np.asarray(bases)[b0:b1], np.ascontiguousarray(offsets[lo:hi + 1] - offsets[lo])
+
+
+class GpuSketchAdapter(object):
+    """What merge_sketch needs from a sketch, implemented with the CUDA library."""
+
+    def __init__(self, sketch):
+        import torch
+        self.torch = torch
+        self.sketch = sketch
+        self.bits = sketch._bits
+        self.device = torch.device('cuda', sketch.device)
+
+    def widen(self):
+        n, eb = c_uint64(), c_int()
+        check(lib().kv_sketch_widen(self.sketch._h, None, byref(n), byref(eb)))
+        dtype = self.torch.int16 if eb.value == 2 else self.torch.uint8
+        buf = self.torch.empty(n.value, dtype=dtype, device=self.device)
+        check(lib().kv_sketch_widen(self.sketch._h, buf.data_ptr(), byref(n), byref(eb)))
+        return buf
+
+    def narrow(self, buf):
+        self.torch.cuda.synchronize(self.device)
+        check(lib().kv_sketch_narrow(self.sketch._h, buf.data_ptr()))
+
+    def flat_tensor(self):
+        """The sketch's own table storage viewed as a torch uint8 tensor (no copy)."""
+        ptr, nbytes = self.sketch.flat_device_buffer()
+
+        class _Raw(object):
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 3}
+        raw._keepalive = self.sketch
+        return self.torch.as_tensor(raw, device=self.device)
+
+    def merge_from(self, tensors):
+        self.torch.cuda.synchronize(self.device)
+        for i in range(0, len(tensors), 8):
+            group = tensors[i:i + 8]
+            ptrs = (c_void_p * len(group))(*[t.data_ptr() for t in group])
+            check(lib().kv_sketch_merge_peers(self.sketch._h, ptrs, len(group), 0, 0))
+
+
+def merge_allreduce(adapter, group=None):
+    """widen -> all-reduce(SUM) -> clamp.  Bit tables (merge = OR) go through all-gather since
+    NCCL has no bitwise reduction."""
+    td = dist()
+    if adapter.bits == 1:
+        return merge_allgather(adapter, group)
+    wide = adapter.widen()
+    td.all_reduce(wide, op=td.ReduceOp.SUM, group=group)
+    adapter.narrow(wide)
+
+
+def merge_allgather(adapter, group=None):
+    td = dist()
+    mine = adapter.flat_tensor()
+    world, rank = td.get_world_size(group), td.get_rank(group)
+    gathered = [mine.new_empty(mine.shape) for _ in range(world)]
+    td.all_gather(gathered, mine, group=group)
+    adapter.merge_from([g for r, g in enumerate(gathered) if r != rank])
+
+
+def slice_bounds(nbytes, rank, world, align=256):
+    """Byte range of the table storage that `rank` reduces in the p2p merge (aligned)."""
+    units = nbytes // align
+    lo, hi = shard_bounds(units, rank, world)
+    return lo * align, hi * align
+
+
+def merge_p2p(sketch, group=None):
+    """Peer-to-peer merge with no NCCL on the data path.  Ranks exchange CUDA IPC handles of
+    their table storage; then
+      phase 1 (reduce-scatter): rank r folds bytes slice(r) of every peer's table into its own
+               table with one kernel of NVLink loads (kv_sketch_merge_peers) -- peers only ever
+               write their OWN slice, so nobody reads bytes that are being written;
+      phase 2 (all-gather): rank r pulls the finished slice(p) from every peer p.
+    Barriers separate the phases."""
+    td = dist()
+    world, rank = td.get_world_size(group), td.get_rank(group)
+    handle = (ctypes.c_uint8 * 64)()
+    check(lib().kv_sketch_ipc_export(sketch._h, handle))
+    handles = [None] * world
+    td.all_gather_object(handles, bytes(handle), group=group)
+    _, nbytes = sketch.flat_device_buffer()
+    peers = {}
+    for r, h in enumerate(handles):
+        if r != rank:
+            ptr = c_void_p()
+            check(lib().kv_ipc_open(sketch.device, (ctypes.c_uint8 * 64)(*h), byref(ptr)))
+            peers[r] = ptr
+    _lib.sync(sketch.device)
+    td.barrier(group=group)                           # every partial table is complete and mapped
+    lo, hi = slice_bounds(nbytes, rank, world)
+    order = [peers[r] for r in sorted(peers)]
+    for i in range(0, len(order), 8):
+        grp = order[i:i + 8]
+        ptrs = (c_void_p * len(grp))(*[p.value for p in grp])
+        check(lib().kv_sketch_merge_peers(sketch._h, ptrs, len(grp), lo, hi))
+    td.barrier(group=group)                           # every slice is reduced
+    for r in sorted(peers):
+        plo, phi = slice_bounds(nbytes, r, world)
+        check(lib().kv_sketch_copy_from_peer(sketch._h, peers[r], plo, phi))
+    td.barrier(group=group)                           # nobody still reads my table
+    for ptr in peers.values():
+        check(lib().kv_ipc_close(sketch.device, ptr))
+
+
+def merge_sketch(sketch, how='allreduce', group=None):
+    """Combine per-rank partial sketches in place; afterwards every rank holds the full sketch."""
+    td = dist()
+    if not td.is_initialized() or td.get_world_size(group) == 1:
+        return sketch
+    if how == 'p2p':
+        merge_p2p(sketch, group)
+    elif how == 'allgather':
+        merge_allgather(GpuSketchAdapter(sketch), group)
+    elif how == 'allreduce':
+        merge_allreduce(GpuSketchAdapter(sketch), group)
+    else:
+        raise ValueError('unknown merge strategy ' + how)
+    return sketch
+
+
+def gather_hits(hits, read_base, group=None):
+    """Collect every rank's novel hits on rank 0 with batch-global read indices."""
+    td = dist()
+    hits = hits.copy()
+    local = np.zeros(len(hits), dtype=[('read', '<u8'), ('offset', '<u4'), ('abund', 'u1', (_lib.MAX_SAMPLES,))])
+    local['read'] = hits['read'].astype(np.uint64) + np.uint64(read_base)
+    local['offset'] = hits['offset']
+    local['abund'] = hits['abund']
+    if not td.is_initialized() or td.get_world_size(group) == 1:
+        return local
+    parts = [None] * td.get_world_size(group)
+    td.all_gather_object(parts, local, group=group)
+    return np.concatenate(parts)
