@@ -82,6 +82,8 @@ int kv_primes_below(uint64_t x, int n, uint64_t *out);
 int kv_sketch_create(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int device,
                      kv_sketch **out);
 int kv_sketch_destroy(kv_sketch *s);
+/* Zero every counter and the n_unique bookkeeping (a fresh sketch without a reallocation; asynchronous). */
+int kv_sketch_clear(kv_sketch *s);
 
 /* khmer <Type>.load(filename) / .save(filename): OXLI v4 files (kevlar/sketch.py:14-27,77-92;
  * kevlar/count.py:95; kevlar/novel.py:92).  The file does not record table-vs-graph, so the
@@ -181,6 +183,13 @@ int kv_ipc_close(int device, void *dev_ptr);
  * framework can record events on it; kv_sync waits for it. */
 int kv_stream(int device, void **cuda_stream);
 int kv_sync(int device);
+
+/* Per-kernel-class device timing, measured with CUDA events on the launching stream.
+ * enable: 1 = start (and reset), 0 = stop (and reset), 2 = read only.  ms_out / n_out receive
+ * KV_PROF_CLASSES totals accumulated since the last reset: milliseconds and launch counts for
+ * [0] other, [1] hash, [2] increment, [3] unique-tracking, [4] novel, [5] merge kernels. */
+#define KV_PROF_CLASSES 6
+int kv_profile(int device, int enable, double *ms_out, uint64_t *n_out);
 
 /* Number of kernels this library has launched on `device` since load (bench accounting). */
 int kv_launch_count(int device, uint64_t *n);

@@ -43,6 +43,7 @@ SYMBOLS = [
     ('kv_primes_below', c_int, [c_uint64, c_int, POINTER(c_uint64)]),
     ('kv_sketch_create', c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64), c_int, POINTER(_P)]),
     ('kv_sketch_destroy', c_int, [_P]),
+    ('kv_sketch_clear', c_int, [_P]),
     ('kv_sketch_load', c_int, [c_char_p, c_int, c_int, c_int, POINTER(_P)]),
     ('kv_sketch_save', c_int, [_P, c_char_p]),
     ('kv_sketch_info', c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
@@ -70,6 +71,7 @@ SYMBOLS = [
     ('kv_stream', c_int, [c_int, POINTER(_P)]),
     ('kv_sync', c_int, [c_int]),
     ('kv_launch_count', c_int, [c_int, POINTER(c_uint64)]),
+    ('kv_profile', c_int, [c_int, c_int, POINTER(ctypes.c_double), POINTER(c_uint64)]),
 ]
 
 
@@ -147,6 +149,17 @@ def launch_count(device=None):
     n = c_uint64()
     check(lib().kv_launch_count(current_device() if device is None else device, byref(n)))
     return n.value
+
+
+PROF_CLASSES = ('other', 'hash', 'increment', 'unique', 'novel', 'merge')
+
+
+def profile(enable, device=None):
+    """Start (1) / stop (0) / read (2) per-kernel-class timing; returns {class: (ms, launches)}."""
+    ms = (ctypes.c_double * len(PROF_CLASSES))()
+    n = (c_uint64 * len(PROF_CLASSES))()
+    check(lib().kv_profile(current_device() if device is None else device, int(enable), ms, n))
+    return {name: (ms[i], n[i]) for i, name in enumerate(PROF_CLASSES)}
 
 
 def as_u8(a):

@@ -49,6 +49,9 @@ extern "C" int kv_abi_version(void) { return KV_ABI_VERSION; }
 
 // ------------------------------------------------------------------ context
 
+enum { KV_PROF_OTHER = 0, KV_PROF_HASH = 1, KV_PROF_INCREMENT = 2, KV_PROF_UNIQUE = 3, KV_PROF_NOVEL = 4,
+       KV_PROF_MERGE = 5 };   // KV_PROF_CLASSES (= 6) comes from kvsketch.h
+
 struct KvBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -71,6 +74,11 @@ struct KvCtx {
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
     unsigned long long *h_counters = nullptr; // pinned mirror
     uint64_t launches = 0;
+    // optional per-kernel-class timing (kv_profile): event pairs around launches
+    bool profiling = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+    double prof_ms[KV_PROF_CLASSES] = {0};
+    uint64_t prof_n[KV_PROF_CLASSES] = {0};
     int sm_count = 148;
     uint64_t chunk_bases = 64ull << 20;
 };
@@ -126,13 +134,23 @@ static int kv_buf_ensure(KvBuf &b, size_t need)
     return KV_OK;
 }
 
-#define LAUNCH(ctx, kern, grid, block, ...)                                \
+#define LAUNCH_C(cls, ctx, kern, grid, block, ...)                         \
     do {                                                                   \
         auto kfn_ = kern;                                                  \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                          \
+        if ((ctx)->profiling) {                                            \
+            cudaEventCreate(&e0_); cudaEventCreate(&e1_);                  \
+            cudaEventRecord(e0_, (ctx)->compute);                          \
+        }                                                                  \
         kfn_<<<(grid), (block), 0, (ctx)->compute>>>(__VA_ARGS__);         \
+        if ((ctx)->profiling) {                                            \
+            cudaEventRecord(e1_, (ctx)->compute);                          \
+            (ctx)->prof_events.push_back({cls, {e0_, e1_}});               \
+        }                                                                  \
         (ctx)->launches++;                                                 \
         CU(cudaGetLastError());                                            \
     } while (0)
+#define LAUNCH(ctx, kern, grid, block, ...) LAUNCH_C(KV_PROF_OTHER, ctx, kern, grid, block, __VA_ARGS__)
 
 static inline unsigned kv_grid_for(const KvCtx *c, uint64_t n, int per_sm = 8)
 {
@@ -274,6 +292,20 @@ extern "C" int kv_sketch_destroy(kv_sketch *s)
     if (s->first) cudaFree(s->first);
     if (s->d_unique) cudaFree(s->d_unique);
     delete s;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_clear(kv_sketch *s)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemsetAsync(s->flat, 0, s->flat_bytes, ctx->compute));
+    CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
+    s->unique_valid = true;   // first[] is all-ones between batches by construction
+    s->n_unique = 0;
     return KV_OK;
 }
 
@@ -501,8 +533,10 @@ static int kv_stage(KvCtx *ctx, const uint8_t *bases, const uint64_t *offsets, u
         b->d_offsets = (const uint64_t *)s->offsets.p;
     } else if (where == KV_MEM_DEVICE) {
         if (((uintptr_t)bases & 3) || ((uintptr_t)offsets & 7)) return kv_fail(KV_EINVAL, "device batch pointers must be 4/8-byte aligned");
-        CU(cudaMemcpyAsync(ctx->h_counters + 4, offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->compute));
-        CU(cudaStreamSynchronize(ctx->compute));
+        // the batch is caller-owned input, not produced on the compute stream: fetch the total on
+        // the copy stream so queued kernels keep running
+        CU(cudaMemcpyAsync(ctx->h_counters + 4, offsets + n_reads, 8, cudaMemcpyDeviceToHost, ctx->copy));
+        CU(cudaStreamSynchronize(ctx->copy));
         total = ctx->h_counters[4];
         b->d_bases = bases;
         b->d_offsets = offsets;
@@ -526,13 +560,13 @@ static inline void kv_stage_done(KvCtx *ctx, KvBatch *b)
 template <int HASHER>
 static int kv_launch_hash(KvCtx *ctx, const KvHashParams &p, unsigned n_tiles)
 {
-    if (HASHER == KV_HASH_TWOBIT) { LAUNCH(ctx, (kv_hash_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
+    if (HASHER == KV_HASH_TWOBIT) { LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
     int kw = 4 * ((p.k + 15) / 16);
     switch (kw) {
-    case 4: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
-    case 8: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
-    case 12: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
-    default: LAUNCH(ctx, (kv_hash_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
+    case 4: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
+    case 8: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
+    case 12: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
+    default: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
     }
     return KV_OK;
 }
@@ -577,14 +611,14 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
         up.v = v; up.first = s->first; up.hashes = d_hashes; up.valid = d_valid; up.cand = (uint32_t *)ctx->cand.p;
         up.total = n; up.n_unique = s->d_unique;
         for (int t = 0; t < s->n_tables; t++) up.first_base[t] = s->first_base[t];
-        LAUNCH(ctx, kv_unique_probe_kernel, grid, 256, up);
-        LAUNCH(ctx, kv_unique_resolve_kernel, grid, 256, up);
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_unique_probe_kernel, grid, 256, up);
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_unique_resolve_kernel, grid, 256, up);
     } else
         s->unique_valid = false;
     if (d_valid) {
-        if (s->bits == 8) LAUNCH(ctx, kv_increment_kernel<8>, grid, 256, v, d_hashes, d_valid, n);
-        else if (s->bits == 4) LAUNCH(ctx, kv_increment_kernel<4>, grid, 256, v, d_hashes, d_valid, n);
-        else LAUNCH(ctx, kv_increment_kernel<1>, grid, 256, v, d_hashes, d_valid, n);
+        if (s->bits == 8) LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_increment_kernel<8>, grid, 256, v, d_hashes, d_valid, n);
+        else if (s->bits == 4) LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_increment_kernel<4>, grid, 256, v, d_hashes, d_valid, n);
+        else LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_increment_kernel<1>, grid, 256, v, d_hashes, d_valid, n);
     } else {
         if (s->bits == 8) LAUNCH(ctx, kv_add_hashes_kernel<8>, grid, 256, v, d_hashes, n);
         else if (s->bits == 4) LAUNCH(ctx, kv_add_hashes_kernel<4>, grid, 256, v, d_hashes, n);
@@ -656,13 +690,13 @@ template <int HASHER>
 static int kv_launch_novel(KvCtx *ctx, const KvNovelParams &p)
 {
     unsigned n_tiles = (unsigned)p.n_tiles;
-    if (HASHER == KV_HASH_TWOBIT) { LAUNCH(ctx, (kv_novel_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
+    if (HASHER == KV_HASH_TWOBIT) { LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
     int kw = 4 * ((p.k + 15) / 16);
     switch (kw) {
-    case 4: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
-    case 8: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
-    case 12: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
-    default: LAUNCH(ctx, (kv_novel_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
+    case 4: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
+    case 8: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
+    case 12: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
+    default: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
     }
     return KV_OK;
 }
@@ -885,7 +919,7 @@ extern "C" int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, i
     KV_TRY(kv_ctx_get(s->device, &ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
-    LAUNCH(ctx, kv_widen_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_out);
+    LAUNCH_C(KV_PROF_MERGE, ctx, kv_widen_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_out);
     CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }
@@ -897,7 +931,7 @@ extern "C" int kv_sketch_narrow(kv_sketch *s, const void *dev_in)
     KV_TRY(kv_ctx_get(s->device, &ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
-    LAUNCH(ctx, kv_narrow_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_in);
+    LAUNCH_C(KV_PROF_MERGE, ctx, kv_narrow_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_in);
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -927,7 +961,7 @@ extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat,
     peers.n = n_peers;
     for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)((const uint8_t *)peer_flat[i] + byte_lo);
     uint64_t n_vec = (byte_hi - byte_lo) / 16;
-    LAUNCH(ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
+    LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -996,6 +1030,32 @@ extern "C" int kv_sync(int device)
     CU(cudaSetDevice(device));
     CU(cudaStreamSynchronize(ctx->copy));
     CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_profile(int device, int enable, double *ms_out, uint64_t *n_out)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize(ctx->compute));
+    for (auto &ev : ctx->prof_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev.second.first, ev.second.second) == cudaSuccess) {
+            ctx->prof_ms[ev.first] += ms;
+            ctx->prof_n[ev.first]++;
+        }
+        cudaEventDestroy(ev.second.first);
+        cudaEventDestroy(ev.second.second);
+    }
+    ctx->prof_events.clear();
+    for (int c = 0; c < KV_PROF_CLASSES; c++) {
+        if (ms_out) ms_out[c] = ctx->prof_ms[c];
+        if (n_out) n_out[c] = ctx->prof_n[c];
+        if (enable != 2) { ctx->prof_ms[c] = 0; ctx->prof_n[c] = 0; }   // 2 = read without resetting
+    }
+    if (enable != 2) ctx->profiling = enable != 0;
     return KV_OK;
 }
 

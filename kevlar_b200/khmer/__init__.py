@@ -90,6 +90,10 @@ class _Sketch(object):
                                '(or the sketch was merged across GPUs)')
         return n.value
 
+    def clear(self):
+        """Reset to an empty sketch in place (no reallocation)."""
+        check(lib().kv_sketch_clear(self._h))
+
     def set_unique_tracking(self, on):
         check(lib().kv_sketch_set_unique_tracking(self._h, int(bool(on))))
 
