@@ -159,9 +159,11 @@ int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, const uint64_
 
 /* Multi-GPU merge of per-GPU partial sketches (plan A).  The host runs the
  * collective (NCCL via torch.distributed) on a widened copy between these two kernels:
- *   kv_sketch_widen:  counters -> one uint16 (8-bit), uint8 (4-bit: one per nibble) or
- *                     uint8 (1-bit: the raw bytes, merge = bitwise OR) element per bucket,
- *                     written to dev_out (device pointer, *n_elems elements).
+ *   kv_sketch_widen:  counters -> one IEEE half (8-bit counters; NCCL has no 16-bit integer
+ *                     type and integers <= 2048 are exact in fp16, so sums are exact for up to
+ *                     8 ranks), uint8 (4-bit: one per nibble) or uint8 (1-bit: the raw bytes,
+ *                     merge = bitwise OR) element per bucket, written to dev_out (device
+ *                     pointer, *n_elems elements of *elem_bytes bytes).
  *   kv_sketch_narrow: summed elements -> clamp to 255 / 15 / (bytes as is) and store back.
  * kv_sketch_merge_peers does the same in ONE kernel over peer-mapped tables of the other
  * GPUs (device pointers valid on this device, e.g. from CUDA IPC): saturating add of bytes

@@ -9,6 +9,8 @@
 //   K6  kv_widen/narrow/merge_peers kernels   multi-GPU saturating merge
 //   +   kv_get_kernel          min-over-tables lookups for explicit hashes
 #pragma once
+#include <cuda_fp16.h>
+
 #include "kv_device.cuh"
 
 // ----------------------------------------------------------------------- K0
@@ -332,13 +334,16 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
 
 // ----------------------------------------------------------------------- K6
 
-// 8-bit: u8 -> u16;  4-bit: one u8 per nibble (bucket order);  1-bit: raw bytes.
+// Widened copies for an NCCL sum.  NCCL has no 16-bit integer type, so 8-bit counters travel as
+// IEEE half: integers up to 2048 are exact in fp16 and 8 ranks x 255 = 2040, so the sum is exact
+// for up to 8 ranks (larger worlds use the all-gather / peer-to-peer merge).
+// 8-bit: u8 -> half;  4-bit: one u8 per nibble (sums <= 15 x 17 fit);  1-bit: raw bytes.
 __global__ void kv_widen_kernel(const uint8_t *__restrict__ flat, uint64_t nbytes, int bits, void *out)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
         uint8_t b = flat[i];
-        if (bits == 8) ((uint16_t *)out)[i] = b;
+        if (bits == 8) ((__half *)out)[i] = __ushort2half_rn(b);
         else if (bits == 4) { ((uint8_t *)out)[2 * i] = b >> 4; ((uint8_t *)out)[2 * i + 1] = b & 15; }
         else ((uint8_t *)out)[i] = b;
     }
@@ -349,7 +354,7 @@ __global__ void kv_narrow_kernel(uint8_t *__restrict__ flat, uint64_t nbytes, in
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += stride) {
         if (bits == 8) {
-            unsigned s = ((const uint16_t *)in)[i];
+            unsigned s = __half2uint_rn(((const __half *)in)[i]);
             flat[i] = (uint8_t)(s > 255u ? 255u : s);
         } else if (bits == 4) {
             unsigned hi = ((const uint8_t *)in)[2 * i], lo = ((const uint8_t *)in)[2 * i + 1];

@@ -11,7 +11,7 @@ complete sketch.  The novel scan then runs shard-local against the replicated sk
 no further communication; ranks only exchange their (tiny) hit lists at the end.
 
 Merge strategies (`merge_sketch(..., how=)`):
-  'allreduce'  widen counters on the GPU (kv_sketch_widen: u8->u16, nibble->u8, bits->bytes),
+  'allreduce'  widen counters on the GPU (kv_sketch_widen: u8->fp16 (exact to 2048), nibble->u8),
                NCCL all-reduce (SUM; MAX-free OR for bit tables via all-gather), clamp + repack
                (kv_sketch_narrow).  Transport by NCCL over NVLink/NVSwitch, arithmetic by our kernels.
   'allgather'  NCCL all-gather of the raw tables, then ONE saturating-merge kernel
@@ -82,7 +82,7 @@ class GpuSketchAdapter(object):
     def widen(self):
         n, eb = c_uint64(), c_int()
         check(lib().kv_sketch_widen(self.sketch._h, None, byref(n), byref(eb)))
-        dtype = self.torch.int16 if eb.value == 2 else self.torch.uint8
+        dtype = self.torch.float16 if eb.value == 2 else self.torch.uint8
         buf = self.torch.empty(n.value, dtype=dtype, device=self.device)
         check(lib().kv_sketch_widen(self.sketch._h, buf.data_ptr(), byref(n), byref(eb)))
         return buf
@@ -114,8 +114,8 @@ def merge_allreduce(adapter, group=None):
     """widen -> all-reduce(SUM) -> clamp.  Bit tables (merge = OR) go through all-gather since
     NCCL has no bitwise reduction."""
     td = dist()
-    if adapter.bits == 1:
-        return merge_allgather(adapter, group)
+    if adapter.bits == 1 or (adapter.bits == 8 and td.get_world_size(group) > 8):
+        return merge_allgather(adapter, group)   # OR has no NCCL op; fp16 sums are exact up to 8 ranks
     wide = adapter.widen()
     td.all_reduce(wide, op=td.ReduceOp.SUM, group=group)
     adapter.narrow(wide)

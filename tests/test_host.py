@@ -1,0 +1,349 @@
+"""Host-side logic and the C-ABI surface -- runs without a GPU (`pytest -m "not gpu"`)."""
+import ctypes
+import io
+import os
+import re
+import socket
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import REPO, golden_data
+
+import kevlar_b200 as kv
+from kevlar_b200 import _lib, fastx, multigpu
+from kevlar_b200.sequence import KmerOfInterest, Record
+
+
+# ------------------------------------------------------------------ C ABI surface
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, 'include', 'kvsketch.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(kv_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    handle = ctypes.CDLL(_lib.LIBPATH)
+    for name in declared:
+        assert hasattr(handle, name), 'libkvsketch.so does not export ' + name
+    bound = sorted(name for name, _, _ in _lib.SYMBOLS)
+    assert bound == declared, 'ctypes binding and header disagree'
+    assert _lib.lib().kv_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every computing entry point must fail loudly."""
+    if _lib.device_count() > 0:
+        pytest.skip('a GPU is present')
+    with pytest.raises(_lib.KvError, match='no usable CUDA device'):
+        kv.khmer.Counttable(21, 1e4, 4)
+    with pytest.raises(_lib.KvError, match='no CPU fallback'):
+        kv.sketch.load(golden_data('test.counttable'))
+    with pytest.raises(_lib.KvError):
+        kv.count.load_sample_seqfile([golden_data('bogus-genome/refr.fa')], 21, 1e6)
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, 'kevlar_b200')):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, fn)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text, fn
+                assert 'kmer_oracle' not in text or fn.endswith(('.cuh', '.cu')), fn
+
+
+def test_primes_match_oracle(oracle):
+    for x, n in [(2500, 4), (250000, 4), (125, 4), (1e4, 4), (100, 4), (16000000, 4), (7, 2)]:
+        assert _lib.primes_below(x, n) == oracle.primes_below(x, n)
+    with pytest.raises(ValueError):
+        _lib.primes_below(2, 4)
+
+
+def test_memory_setting():
+    ms = kv.khmer.khmer_args.memory_setting
+    assert ms('10K') == 1e4 and ms('1M') == 1e6 and ms('8G') == 8e9 and ms('2T') == 2e12
+    assert ms('1e7') == 1e7 and ms('97') == 97.0 and ms('500k') == 5e5 and ms('1.5M') == 1.5e6
+    with pytest.raises(ValueError):
+        ms('lots')
+
+
+# ------------------------------------------------------------------ CLI
+
+def test_cli_defaults():
+    """kevlar/tests/test_novel.py:40-56, kevlar/cli/count.py, kevlar/cli/filter.py defaults."""
+    args = kv.cli.parser().parse_args(['novel', '--case', 'case1.fq', '--control', 'cntl1.fq', '--control',
+                                       'cntl2.fq', '-k', '17'])
+    assert (args.ksize, args.case_min, args.ctrl_max, args.num_bands, args.band) == (17, 6, 1, None, None)
+    assert args.case == [['case1.fq']] and args.control == [['cntl1.fq'], ['cntl2.fq']]
+    assert args.memory == 1e6 and args.max_fpr == 0.2 and args.threads == 1 and args.abund_screen is None
+    args = kv.cli.parser().parse_args(['novel', '--num-bands', '8', '--band', '1', '--case', 'c.fq', '--control', 'd.fq'])
+    assert (args.ksize, args.num_bands, args.band) == (31, 8, 1)
+    args = kv.cli.parser().parse_args(['count', 'out.ct', 'a.fq', 'b.fq'])
+    assert (args.ksize, args.counter_size, args.memory, args.max_fpr, args.mask, args.count_masked) == \
+        (31, 8, 1e6, 0.2, None, False)
+    assert args.seqfile == ['a.fq', 'b.fq'] and args.threads == 1
+    args = kv.cli.parser().parse_args(['filter', '--mask', 'm.nt', 'reads.augfastq'])
+    assert (args.memory, args.max_fpr, args.ctrl_max, args.case_min) == (1e6, 0.01, 1, 6)
+    with pytest.raises(SystemExit):
+        kv.cli.parser().parse_args(['count', '-c', '2', 'out', 'in.fq'])
+
+
+def test_band_argument_errors():
+    """kevlar/tests/test_novel.py:25-37,58-65; kevlar/tests/test_count.py:83-91."""
+    with pytest.raises(ValueError, match=r'Must specify `numbands` and `band` together'):
+        list(kv.novel.novel(None, [], [], numbands=4))
+    with pytest.raises(ValueError, match=r'Must specify `numbands` and `band` together'):
+        list(kv.novel.novel(None, [], [], band=0))
+    with pytest.raises(ValueError, match=r'`band` must be a value between 0 and 3'):
+        list(kv.novel.novel(None, [], [], numbands=4, band=-1))
+    args = kv.cli.parser().parse_args(['novel', '--case', 'c.fq', '--control', 'd.fq', '--band', '1'])
+    with pytest.raises(ValueError, match=r'Must specify --num-bands and --band together'):
+        kv.novel.main(args)
+    args = kv.cli.parser().parse_args(['count', '--band', '2', 'out', 'in.fq'])
+    with pytest.raises(ValueError, match=r'Must specify --num-bands and --band together'):
+        kv.count.main(args)
+
+
+def test_sketch_extensions():
+    """kevlar/tests/test_sketch.py:102-106."""
+    ge = kv.sketch.get_extension
+    assert ge() == ('.nt', '.nodetable')
+    assert ge(count=True) == ('.ct', '.counttable')
+    assert ge(count=True, smallcount=True) == ('.sct', '.smallcounttable')
+    assert ge(count=True, graph=True) == ('.cg', '.countgraph')
+    assert ge(graph=True) == ('.ng', '.nodegraph')
+    assert sorted(kv.sketch.sketch_loader_by_filename_extension) == sorted(
+        ['.nt', '.ng', '.ct', '.cg', '.sct', '.scg', '.nodetable', '.nodegraph', '.counttable', '.countgraph',
+         '.smallcounttable', '.smallcountgraph'])
+    with pytest.raises(kv.sketch.KevlarSketchTypeError, match='sketch type from filename'):
+        kv.sketch.load(golden_data('test.notasketchtype'))
+    assert issubclass(kv.sketch.KevlarUnsuitableFPRError, SystemExit)
+
+
+# ------------------------------------------------------------------ sequence / augmented FASTX
+
+def test_augfastx_writer_literal():
+    """kevlar/tests/test_seqio.py:135-182: exact text."""
+    out = io.StringIO()
+    kv.print_augmented_fastx(Record(
+        name='BasiliscusVulgarisRead84467/1', sequence='TTAACTCTAGATTAGGGGCGTGACTTAATAAGGTGTGGGCCTAAGCGTCT',
+        quality='B' * 50, annotations=[KmerOfInterest(19, 13, (12, 1, 1)), KmerOfInterest(19, 15, (20, 0, 1))]), out)
+    kv.print_augmented_fastx(Record(
+        name='BasiliscusVulgarisRead90577/2', sequence='CTGTAATCCCAGCACTTTGGGAGGCCGAGGCAAGCAGATGATGCGGTCAG',
+        quality='B' * 50, annotations=[KmerOfInterest(19, 2, (7, 10, 9)), KmerOfInterest(19, 1, (5, 7, 9))],
+        mates=['CAGATGTGTCTTGTGGGCAGTGCAGCGGAGAGGTGCAAATATGGGTTTGG']), out)
+    kv.print_augmented_fastx(Record(name='r3', sequence='ACGT'), out)
+    assert out.getvalue() == (
+        '@BasiliscusVulgarisRead84467/1\nTTAACTCTAGATTAGGGGCGTGACTTAATAAGGTGTGGGCCTAAGCGTCT\n+\n' + 'B' * 50 + '\n'
+        '             AGGGGCGTGACTTAATAAG          12 1 1#\n'
+        '               GGGCGTGACTTAATAAGGT          20 0 1#\n'
+        '@BasiliscusVulgarisRead90577/2\nCTGTAATCCCAGCACTTTGGGAGGCCGAGGCAAGCAGATGATGCGGTCAG\n+\n' + 'B' * 50 + '\n'
+        ' TGTAATCCCAGCACTTTGG          5 7 9#\n'
+        '  GTAATCCCAGCACTTTGGG          7 10 9#\n'
+        '#mateseq=CAGATGTGTCTTGTGGGCAGTGCAGCGGAGAGGTGCAAATATGGGTTTGG#\n'
+        '>r3\nACGT\n')
+
+
+@pytest.mark.parametrize('fn', ['example1.augfastq', 'example2.augfastq', 'collect.alpha.txt', 'trio1/novel_3_1,2.txt'])
+def test_augfastx_round_trip(fn):
+    text = open(golden_data(fn)).read()
+    out = io.StringIO()
+    recs = list(kv.parse_augmented_fastx(io.StringIO(text)))
+    for rec in recs:
+        kv.print_augmented_fastx(rec, out)
+    assert out.getvalue() == text
+    for rec in recs:
+        for ik in rec.annotations:
+            assert rec.ikmerseq(ik) in rec.ikmers and kv.revcom(rec.ikmerseq(ik)) in rec.ikmers
+
+
+def test_augfastx_reader_details():
+    recs = list(kv.parse_augmented_fastx(open(golden_data('example2.augfastq'))))
+    mated = list(kv.parse_augmented_fastx(io.StringIO('@r/1\nACGTACGT\n+\nIIIIIIII\n CGTAC          9 0#\n#mateseq=TTGACA#\n')))
+    assert mated[0].mates == ['TTGACA'] and mated[0].annotations[0] == KmerOfInterest(5, 1, (9, 0))
+    assert recs[0].id == recs[0].name.split()[0]
+    with pytest.raises(Exception):
+        list(kv.parse_augmented_fastx(io.StringIO('@r\nACGT\n+\nIIII\nnot an annotation\n')))
+    with pytest.raises(AssertionError):
+        Record('r', 'ACGTACGT').annotate('TTTT', 0, (1,))
+    assert kv.revcom('ACGTNacgtRY') == 'RYACGTNACGT'
+    assert kv.revcommin('TTTTA') == 'TAAAA' and kv.revcommin('AAAAT') == 'AAAAT'
+    assert kv.same_seq('ACCG', 'CGGT')
+    with pytest.raises(ValueError):
+        kv.open('x', 'a')
+
+
+# ------------------------------------------------------------------ FASTA/FASTQ reader
+
+@pytest.mark.parametrize('fn', ['simple-genome-case-reads.fa.gz', 'trio1/case1.fq.gz', 'bogus-genome/refr.fa',
+                                'microtrios/trio-na-proband.fq.gz', 'ambig.fasta', 'screen-case.fa'])
+def test_fastx_reader_matches_oracle_parser(oracle, fn, monkeypatch):
+    want = [(r.name, r.sequence, r.quality) for r in oracle.ReadParser(golden_data(fn))]
+    for block in (32 << 20, 4096, 333):
+        monkeypatch.setattr(fastx.FastxReader, 'BLOCK', block)
+        got = [(r.name, r.sequence, r.quality) for r in fastx.FastxReader(golden_data(fn))]
+        assert got == want
+        reader = fastx.FastxReader(golden_data(fn))
+        seen = 0
+        for batch in reader.batches(7000, keep_text=True):
+            assert batch.offsets[0] == 0 and batch.offsets[-1] == len(batch.bases)
+            for i in (0, len(batch) - 1):
+                rec = batch.record(i)
+                assert (rec.name, rec.sequence, rec.quality) == want[seen + i]
+            seen += len(batch)
+        assert seen == len(want) == reader.num_reads
+
+
+def test_fastx_reader_shared_by_threads():
+    """kevlar/count.py:40-77: several consumers drain one parser; every read exactly once."""
+    reader = fastx.FastxReader(golden_data('trio1/case1.fq.gz'))
+    got, lock = [], threading.Lock()
+
+    def work():
+        for batch in reader.batches(20000, keep_text=True):
+            with lock:
+                got.extend(batch.names)
+    threads = [threading.Thread(target=work) for _ in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert len(got) == 12000 == len(set(got)) == reader.num_reads
+    assert len(list(kv.multi_file_iter_khmer([golden_data('bogus-genome/mask-chr1.fa'),
+                                              golden_data('bogus-genome/mask-chr2.fa')]))) == 4
+
+
+# ------------------------------------------------------------------ timers / progress
+
+def test_progress_indicator_batched_equals_stepwise(capsys):
+    class Stepwise(object):   # the reference's one-record-at-a-time rule (kevlar/progress.py:31-42)
+        def __init__(self, interval, breaks):
+            self.counter, self.interval, self.nextupdate, self.breaks, self.out = 0, interval, interval, breaks, []
+
+        def update(self):
+            if self.counter in self.breaks:
+                self.interval = self.counter
+            if self.counter >= self.nextupdate:
+                self.nextupdate += self.interval
+                self.out.append(self.counter)
+            self.counter += 1
+    rng = np.random.default_rng(0)
+    for interval, breaks in [(10, [100, 1000, 10000]), (1e2, [1e3, 1e4]), (7, [50, 51, 400])]:
+        ref = Stepwise(interval, breaks)
+        ind = kv.ProgressIndicator('{counter}', interval=interval, breaks=breaks)
+        kv.logstream, saved = io.StringIO(), kv.logstream
+        try:
+            for n in rng.integers(1, 900, size=60):
+                ind.update(int(n))
+                for _ in range(int(n)):
+                    ref.update()
+            text = kv.logstream.getvalue()
+        finally:
+            kv.logstream = saved
+        assert [float(x) for x in text.split()] == [float(x) for x in ref.out]
+        assert ind.counter == ref.counter
+
+
+def test_timer():
+    timer = kv.Timer()
+    timer.start()
+    timer.start('x')
+    with pytest.raises(ValueError, match='already started'):
+        timer.start('x')
+    with pytest.raises(ValueError, match='No timer started'):
+        timer.stop('y')
+    assert timer.probe('x') >= 0 and timer.stop('x') >= 0 and timer.stop() >= 0
+
+
+# ------------------------------------------------------------------ unband
+
+def test_unband_merges_band_outputs(tmp_path):
+    """kevlar/unband.py:26-78: one record per read with the union of annotations, sorted by
+    offset; deterministic across runs."""
+    seq = 'TTAACTCTAGATTAGGGGCGTGACTTAATAAGGTGTGGGCCTAAGCGTCT'
+    band1 = [Record('readA', seq, 'I' * 50, [KmerOfInterest(19, 15, (20, 0, 1))]),
+             Record('readB', seq, 'I' * 50, [KmerOfInterest(19, 3, (9, 0, 0))])]
+    band2 = [Record('readA', seq, 'I' * 50, [KmerOfInterest(19, 13, (12, 1, 1))]),
+             Record('readC', seq, 'I' * 50, [KmerOfInterest(19, 1, (8, 1, 0))])]
+    files = []
+    for i, recs in enumerate((band1, band2)):
+        path = str(tmp_path / 'band{}.augfastq'.format(i))
+        with open(path, 'w') as fh:
+            for rec in recs:
+                kv.print_augmented_fastx(rec, fh)
+        files.append(path)
+    kv.logstream, saved = io.StringIO(), kv.logstream
+    try:
+        runs = [[(r.name, [a.offset for a in r.annotations]) for r in kv.unband.unband(kv.unband.afxstream(files), 4)]
+                for _ in range(2)]
+    finally:
+        kv.logstream = saved
+    assert runs[0] == runs[1]
+    assert sorted(runs[0]) == [('readA', [13, 15]), ('readB', [3]), ('readC', [1])]
+
+
+# ------------------------------------------------------------------ multi-GPU host logic
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 300000, 300001):
+        for world in (1, 2, 3, 4, 8):
+            cuts = [multigpu.shard_bounds(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    for nbytes in (256, 4096, 64001024):
+        for world in (2, 8):
+            cuts = [multigpu.slice_bounds(nbytes, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == nbytes - nbytes % 256
+            assert all(lo % 256 == 0 and hi % 256 == 0 for lo, hi in cuts)
+
+
+def test_shard_batch_covers_every_read(oracle):
+    seqs = [b'ACGT' * n for n in (3, 0, 10, 1, 25, 7, 7, 2, 40)]
+    bases, offs = oracle.reads_to_batch(seqs)
+    for world in (1, 2, 4, 9, 12):
+        got = []
+        for r in range(world):
+            b, o = multigpu.shard_batch(bases, offs, r, world)
+            assert o[0] == 0 and o[-1] == len(b)
+            got += [b[int(o[i]):int(o[i + 1])].tobytes() for i in range(len(o) - 1)]
+        assert got == seqs
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return str(s.getsockname()[1])
+
+
+def test_gloo_two_rank_merge_equals_single_process(oracle, tmp_path):
+    """world_size 2 over gloo: shard the reads, count per rank, merge with the all-reduce
+    choreography; result must be byte-identical to one process counting everything."""
+    port = _free_port()
+    worker = os.path.join(REPO, 'tests', '_gloo_worker.py')
+    procs = [subprocess.Popen([sys.executable, worker, str(r), '2', port, str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    res = [np.load(str(tmp_path / 'rank{}.npy'.format(r)), allow_pickle=True)[0] for r in range(2)]
+    rng = np.random.default_rng(1234)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)
+    genome = letters[rng.integers(0, 4, size=3000)]
+    seqs = []
+    for _ in range(4000):
+        s = int(rng.integers(0, 2900))
+        seqs.append(genome[s:s + int(rng.integers(25, 100))].tobytes())
+    bases, offs = oracle.reads_to_batch(seqs)
+    for name in ('Counttable', 'SmallCounttable', 'Nodetable'):
+        sk = getattr(oracle, name)(21, 900, 4)
+        sk.consume_batch(bases, offs)
+        want = [sk.table_bytes(t) for t in range(4)]
+        assert res[0][name] == want and res[1][name] == want, name
+        if name == 'Counttable':
+            assert max(max(t) for t in want) == 255      # saturation really happened
+    assert res[0]['hit_reads'] == [0, 1, 2, 2000, 2001, 2002] == res[1]['hit_reads']
