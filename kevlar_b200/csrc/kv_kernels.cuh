@@ -99,52 +99,119 @@ __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
     if (threadIdx.x == 0 && s_cnt) atomicAdd(p.n_valid, (unsigned long long)s_cnt);
 }
 
+// ------------------------------------------------------- first-touch table (used by K3 and K5)
+// See the K5 section below for what it is for.
+
+#define KV_UT_IDX_BITS 20
+#define KV_UT_BIN_BITS 38
+#define KV_UT_IDX_MASK ((1ull << KV_UT_IDX_BITS) - 1ull)
+#define KV_UT_KEY_MASK ((1ull << (KV_UT_BIN_BITS + 3)) - 1ull)
+#define KV_UT_MAX_CHUNK (1u << KV_UT_IDX_BITS)
+
+struct KvFirstTable {
+    unsigned long long *slots;
+    int log2_slots;
+    unsigned epoch;   // 1..7; 0 marks wiped slots
+};
+
+__device__ __forceinline__ unsigned long long kv_ut_key(int t, uint64_t bin)
+{
+    return ((unsigned long long)t << KV_UT_BIN_BITS) | bin;
+}
+
+__device__ __forceinline__ uint64_t kv_ut_home(unsigned long long key, int log2_slots)
+{
+    return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2_slots);
+}
+
+__device__ __forceinline__ void kv_ut_insert(const KvFirstTable &ft, unsigned long long key, unsigned pos)
+{
+    const unsigned long long entry = ((unsigned long long)ft.epoch << 61) | (key << KV_UT_IDX_BITS) | pos;
+    const uint64_t mask = (1ull << ft.log2_slots) - 1ull;
+    uint64_t slot = kv_ut_home(key, ft.log2_slots);
+    for (;;) {
+        unsigned long long cur = __ldcg(ft.slots + slot);
+        while ((cur >> 61) != ft.epoch) {   // wiped or left over from an earlier chunk: claim it
+            unsigned long long prev = atomicCAS(ft.slots + slot, cur, entry);
+            if (prev == cur) return;
+            cur = prev;
+        }
+        if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) {
+            if (pos < (unsigned)(cur & KV_UT_IDX_MASK)) atomicMin(ft.slots + slot, entry);
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+
+// is `pos` the first position of this chunk that touched (t, bin)?
+__device__ __forceinline__ bool kv_ut_owns(const KvFirstTable &ft, unsigned long long key, unsigned pos)
+{
+    const uint64_t mask = (1ull << ft.log2_slots) - 1ull;
+    uint64_t slot = kv_ut_home(key, ft.log2_slots);
+    for (;;) {
+        unsigned long long cur = __ldcg(ft.slots + slot);
+        if ((cur >> 61) != ft.epoch) return false;
+        if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) return (unsigned)(cur & KV_UT_IDX_MASK) == pos;
+        slot = (slot + 1) & mask;
+    }
+}
+
 // ----------------------------------------------------------------------- K3
 
 // One thread per base position (grid-stride).  For every valid k-mer: T bins by Barrett
 // reduction, the T counter words are fetched first (independent loads in flight), then each
-// is bumped with the CAS-saturating update.
-template <int BITS>
+// is bumped with the CAS-saturating update.  With TRACK, candidates flagged by the probe kernel
+// first settle whether they are the first toucher of one of their buckets (n_unique_kmers).
+template <int BITS, bool TRACK, bool HAS_VALID>
 __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
-                                                           const uint32_t *__restrict__ valid, uint64_t total)
+                                                           const uint32_t *__restrict__ valid, uint64_t total,
+                                                           KvFirstTable ft, const uint32_t *__restrict__ cand,
+                                                           unsigned long long *n_unique)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
+    unsigned fresh = 0;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        uint32_t vw = __ldg(valid + (g >> 5));
-        if (!((vw >> (g & 31)) & 1u)) continue;
+        if (HAS_VALID) {
+            uint32_t vw = __ldg(valid + (g >> 5));
+            if (!((vw >> (g & 31)) & 1u)) continue;
+        } else if (g >= total)
+            continue;
         const uint64_t h = __ldcs(hashes + g);
+        const bool is_cand = TRACK && ((__ldg(cand + (g >> 5)) >> (g & 31)) & 1u);
         if (v.n_tables == 4) {
+            uint64_t bin[4];
             unsigned *w[4], sh[4], old[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w[t], sh[t]);
+                bin[t] = kv_mod(h, v.size[t], v.magic[t]);
+                kv_word_addr<BITS>(v, t, bin[t], w[t], sh[t]);
                 old[t] = __ldcg(w[t]);
+            }
+            if (TRACK && is_cand) {
+                bool is_new = false;
+#pragma unroll
+                for (int t = 0; t < 4; t++) is_new = is_new || kv_ut_owns(ft, kv_ut_key(t, bin[t]), (unsigned)g);
+                fresh += is_new;
             }
 #pragma unroll
             for (int t = 0; t < 4; t++) kv_sat_inc<BITS>(w[t], sh[t], old[t]);
         } else {
+            bool is_new = false;
             for (int t = 0; t < v.n_tables; t++) {
                 unsigned *w, sh;
-                kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w, sh);
+                uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
+                if (TRACK && is_cand) is_new = is_new || kv_ut_owns(ft, kv_ut_key(t, bin), (unsigned)g);
+                kv_word_addr<BITS>(v, t, bin, w, sh);
                 kv_sat_inc<BITS>(w, sh, __ldcg(w));
             }
+            fresh += is_new;
         }
     }
-}
-
-// same update for an explicit hash list (kv_add_hashes; kevlar/filter.py:34)
-template <int BITS>
-__global__ void kv_add_hashes_kernel(KvView v, const uint64_t *__restrict__ hashes, uint64_t n)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t h = hashes[i];
-        for (int t = 0; t < v.n_tables; t++) {
-            unsigned *w, sh;
-            kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w, sh);
-            kv_sat_inc<BITS>(w, sh, __ldcg(w));
-        }
+    if (TRACK) {
+        fresh = __reduce_add_sync(0xffffffffu, fresh);
+        if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_unique, (unsigned long long)fresh);
     }
 }
 
@@ -181,66 +248,46 @@ __global__ void kv_expand_bits_kernel(const uint32_t *__restrict__ valid, uint64
 // ----------------------------------------------------------------------- K5
 //
 // khmer's n_unique_kmers counts the add() calls that found at least one of their T buckets
-// empty, in single-threaded file order.  Exact parallel equivalent, per
-// batch (batches are applied in order, so "empty at batch start" is the sequential state):
-//   probe:   every valid occurrence g whose bucket in table t is empty does
-//            first[t][bin] = min(first[t][bin], g)            (first[] is all-ones between batches)
-//   resolve: occurrence g is "new" iff first[t][bin_t] == g for some t; owners reset their slot.
-// Only occurrences that saw an empty bucket take part in resolve (cand bits).
+// empty, in single-threaded file order.  Exact parallel equivalent: reads are
+// applied in chunks of at most 2^20 base positions, chunks in stream order, so "empty at chunk
+// start" is the sequential state; inside a chunk occurrence g is "new" iff, for some table t,
+// g is the SMALLEST position of the chunk that touches its (then empty) bucket (t, bin).
+//   probe   : every valid occurrence that sees an empty bucket records
+//             first[(t, bin)] = min(first[(t, bin)], g) and is flagged as a candidate;
+//   resolve : (fused into the increment kernel) a candidate is new iff first[(t, bin)] == g
+//             for one of its buckets.
+// first[] is NOT an array over all buckets (that costs 4 B per bucket and made this the most
+// expensive part of counting): it is a small open-addressing hash table keyed by (t, bin),
+// sized for one chunk and therefore independent of the sketch size and L2-friendly.  Entries
+// are stamped with a 3-bit chunk epoch, so the table is wiped once every 7 chunks instead of
+// after each one:   [ epoch:3 | t:3 | bin:38 | position:20 ]   (u64, ordered by position for
+// equal epoch+key, so atomicMin keeps the smallest position).
 
-struct KvUniqueParams {
-    KvView v;
-    uint32_t *first;                      // one u32 per bucket, tables back to back
-    uint64_t first_base[KV_TABLES_DEV];   // start of table t inside first[]
-    const uint64_t *hashes;
-    const uint32_t *valid;
-    uint32_t *cand;                       // bit per position: saw an empty bucket
-    uint64_t total;
-    unsigned long long *n_unique;
-};
-
-__global__ void __launch_bounds__(256) kv_unique_probe_kernel(KvUniqueParams p)
+// valid == NULL means every position holds a hash (kv_add_hashes)
+__global__ void __launch_bounds__(256) kv_unique_probe_kernel(KvView v, KvFirstTable ft, const uint64_t *__restrict__ hashes,
+                                                              const uint32_t *__restrict__ valid, uint32_t *__restrict__ cand,
+                                                              uint64_t total)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t total_pad = (p.total + 31) & ~(uint64_t)31;
+    const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
         bool is_cand = false;
-        if (g < p.total && (!p.valid || ((__ldg(p.valid + (g >> 5)) >> (g & 31)) & 1u))) {
-            const uint64_t h = p.hashes[g];
-            for (int t = 0; t < p.v.n_tables; t++) {
-                uint64_t bin = kv_mod(h, p.v.size[t], p.v.magic[t]);
-                if (kv_bucket_get(p.v, t, bin) == 0) {
-                    is_cand = true;
-                    atomicMin(p.first + p.first_base[t] + bin, (uint32_t)g);
-                }
+        if (g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u))) {
+            const uint64_t h = hashes[g];
+            uint64_t bin[KV_TABLES_DEV];
+            unsigned empty = 0;
+#pragma unroll 4
+            for (int t = 0; t < v.n_tables; t++) {
+                bin[t] = kv_mod(h, v.size[t], v.magic[t]);
+                if (kv_bucket_get(v, t, bin[t]) == 0) empty |= 1u << t;
             }
+            is_cand = empty != 0;
+            for (int t = 0; t < v.n_tables; t++)
+                if ((empty >> t) & 1u) kv_ut_insert(ft, kv_ut_key(t, bin[t]), (unsigned)g);
         }
         unsigned bal = __ballot_sync(0xffffffffu, is_cand);
-        if ((threadIdx.x & 31) == 0) p.cand[g >> 5] = bal;
+        if ((threadIdx.x & 31) == 0) cand[g >> 5] = bal;
     }
-}
-
-__global__ void __launch_bounds__(256) kv_unique_resolve_kernel(KvUniqueParams p)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t total_pad = (p.total + 31) & ~(uint64_t)31;
-    unsigned mine = 0;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        if (!((__ldg(p.cand + (g >> 5)) >> (g & 31)) & 1u)) continue;
-        const uint64_t h = p.hashes[g];
-        bool is_new = false;
-        for (int t = 0; t < p.v.n_tables; t++) {
-            uint64_t bin = kv_mod(h, p.v.size[t], p.v.magic[t]);
-            uint32_t *slot = p.first + p.first_base[t] + bin;
-            if (__ldcg(slot) == (uint32_t)g) {
-                is_new = true;
-                *slot = 0xffffffffu;   // only the owner writes; every other reader just compares != its own g
-            }
-        }
-        mine += is_new;
-    }
-    mine = __reduce_add_sync(0xffffffffu, mine);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(p.n_unique, (unsigned long long)mine);
 }
 
 // khmer _occupied_bins: non-zero buckets of table 0

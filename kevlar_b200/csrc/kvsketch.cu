@@ -70,7 +70,9 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc;
+    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc, ut;
+    int ut_log2 = 0;          // first-touch table: 2^ut_log2 slots
+    unsigned ut_epoch = 0;    // 1..7, 0 = freshly wiped
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
     unsigned long long *h_counters = nullptr; // pinned mirror
     uint64_t launches = 0;
@@ -168,8 +170,6 @@ struct kv_sketch {
     uint64_t toff[KV_TABLES_DEV];     // offset of each table in the flat allocation
     uint64_t flat_bytes;
     uint8_t *flat;
-    uint32_t *first;                  // unique-tracking scratch (u32 per bucket), lazily allocated
-    uint64_t first_base[KV_TABLES_DEV];
     bool track_unique, unique_valid;
     uint64_t n_unique;                // host copy, updated at stats time
     unsigned long long *d_unique;     // device accumulator
@@ -247,14 +247,12 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     kv_sketch *s = new kv_sketch();
     memset(s, 0, sizeof *s);
     s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
-    uint64_t off = 0, nb = 0;
+    uint64_t off = 0;
     for (int t = 0; t < n_tables; t++) {
         if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete s; return kv_fail(KV_EINVAL, "bad table size"); }
         s->sizes[t] = sizes[t];
         s->nbytes[t] = kv_table_bytes(bits, sizes[t]);
         s->toff[t] = off;
-        s->first_base[t] = nb;
-        nb += sizes[t];
         off += (s->nbytes[t] + 255) & ~(uint64_t)255;
     }
     s->flat_bytes = off;
@@ -270,6 +268,8 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
     s->track_unique = true;
     s->unique_valid = true;
+    for (int t = 0; t < n_tables; t++)
+        if (sizes[t] >= (1ull << KV_UT_BIN_BITS)) s->track_unique = s->unique_valid = false;   // key field is 38 bits
     *out = s;
     return KV_OK;
 }
@@ -289,7 +289,6 @@ extern "C" int kv_sketch_destroy(kv_sketch *s)
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(ctx->compute));
     if (s->flat) cudaFree(s->flat);
-    if (s->first) cudaFree(s->first);
     if (s->d_unique) cudaFree(s->d_unique);
     delete s;
     return KV_OK;
@@ -325,6 +324,10 @@ extern "C" int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *k
 extern "C" int kv_sketch_set_unique_tracking(kv_sketch *s, int on)
 {
     if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (on)
+        for (int t = 0; t < s->n_tables; t++)
+            if (s->sizes[t] >= (1ull << KV_UT_BIN_BITS))
+                return kv_fail(KV_EINVAL, "exact n_unique tracking supports tables below 2^%d buckets", KV_UT_BIN_BITS);
     s->track_unique = on != 0;
     return KV_OK;
 }
@@ -582,49 +585,66 @@ static int kv_band_interval(int num_bands, int band, uint64_t *lo, uint64_t *hi)
     return KV_OK;
 }
 
-static int kv_ensure_first(KvCtx *ctx, kv_sketch *s)
+// First-touch table for the exact n_unique_kmers bookkeeping: sized for one chunk (every
+// position may insert up to n_tables keys; load factor <= 0.5), shared by all sketches of the
+// device, wiped every 7 chunks (3-bit epoch stamps).
+static int kv_first_table(KvCtx *ctx, uint64_t chunk_positions, int n_tables, KvFirstTable *ft)
 {
-    if (s->first) return KV_OK;
-    uint64_t n = 0;
-    for (int t = 0; t < s->n_tables; t++) n += s->sizes[t];
-    cudaError_t e = cudaMalloc((void **)&s->first, n * 4);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return kv_fail(KV_ENOMEM, "cannot allocate %llu bytes for exact n_unique_kmers tracking; "
-                       "disable it with kv_sketch_set_unique_tracking(s, 0)", (unsigned long long)(n * 4));
+    uint64_t need = std::max<uint64_t>(1024, 2 * chunk_positions * (uint64_t)n_tables);
+    int lg = 10;
+    while ((1ull << lg) < need) lg++;
+    if (lg > ctx->ut_log2) {
+        KV_TRY(kv_buf_ensure(ctx->ut, (8ull << lg)));
+        ctx->ut_log2 = lg;
+        ctx->ut_epoch = 0;
     }
-    LAUNCH(ctx, kv_fill_u32_kernel, kv_grid_for(ctx, n), 256, s->first, n, 0xffffffffu);
+    if (ctx->ut_epoch == 0 || ctx->ut_epoch == 7) {
+        CU(cudaMemsetAsync(ctx->ut.p, 0, 8ull << ctx->ut_log2, ctx->compute));
+        ctx->ut_epoch = 0;
+    }
+    ctx->ut_epoch++;
+    ft->slots = (unsigned long long *)ctx->ut.p;
+    ft->log2_slots = ctx->ut_log2;
+    ft->epoch = ctx->ut_epoch;
     return KV_OK;
 }
 
-// apply a chunk of hashes (device) to the sketch: optional exact-unique bookkeeping, then increments
+template <int BITS>
+static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n,
+                               bool track, const KvFirstTable &ft, const uint32_t *cand, unsigned long long *d_unique)
+{
+    unsigned grid = kv_grid_for(ctx, n);
+    if (track) {
+        if (d_valid) LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, true, true>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
+        else LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, true, false>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
+    } else {
+        if (d_valid) LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, false, true>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
+        else LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, false, false>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
+    }
+    return KV_OK;
+}
+
+// apply one chunk of hashes (device; n <= KV_UT_MAX_CHUNK when tracking) to the sketch:
+// optional exact-unique probe, then the (fused resolve +) saturating increments
 static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n)
 {
     if (!n) return KV_OK;
     KvView v = kv_view(s);
-    unsigned grid = kv_grid_for(ctx, n);
-    if (s->track_unique) {
-        KV_TRY(kv_ensure_first(ctx, s));
+    KvFirstTable ft;
+    memset(&ft, 0, sizeof ft);
+    uint32_t *cand = nullptr;
+    const bool track = s->track_unique;
+    if (track) {
+        if (n > KV_UT_MAX_CHUNK) return kv_fail(KV_EINVAL, "internal: tracked chunk too large");
+        KV_TRY(kv_first_table(ctx, n, s->n_tables, &ft));
         KV_TRY(kv_buf_ensure(ctx->cand, ((n + 31) / 32 + 1) * 4));
-        KvUniqueParams up;
-        memset(&up, 0, sizeof up);
-        up.v = v; up.first = s->first; up.hashes = d_hashes; up.valid = d_valid; up.cand = (uint32_t *)ctx->cand.p;
-        up.total = n; up.n_unique = s->d_unique;
-        for (int t = 0; t < s->n_tables; t++) up.first_base[t] = s->first_base[t];
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_unique_probe_kernel, grid, 256, up);
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_unique_resolve_kernel, grid, 256, up);
+        cand = (uint32_t *)ctx->cand.p;
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_unique_probe_kernel, kv_grid_for(ctx, n), 256, v, ft, d_hashes, d_valid, cand, n);
     } else
         s->unique_valid = false;
-    if (d_valid) {
-        if (s->bits == 8) LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_increment_kernel<8>, grid, 256, v, d_hashes, d_valid, n);
-        else if (s->bits == 4) LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_increment_kernel<4>, grid, 256, v, d_hashes, d_valid, n);
-        else LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_increment_kernel<1>, grid, 256, v, d_hashes, d_valid, n);
-    } else {
-        if (s->bits == 8) LAUNCH(ctx, kv_add_hashes_kernel<8>, grid, 256, v, d_hashes, n);
-        else if (s->bits == 4) LAUNCH(ctx, kv_add_hashes_kernel<4>, grid, 256, v, d_hashes, n);
-        else LAUNCH(ctx, kv_add_hashes_kernel<1>, grid, 256, v, d_hashes, n);
-    }
-    return KV_OK;
+    if (s->bits == 8) return kv_launch_increment<8>(ctx, v, d_hashes, d_valid, n, track, ft, cand, s->d_unique);
+    if (s->bits == 4) return kv_launch_increment<4>(ctx, v, d_hashes, d_valid, n, track, ft, cand, s->d_unique);
+    return kv_launch_increment<1>(ctx, v, d_hashes, d_valid, n, track, ft, cand, s->d_unique);
 }
 
 static int kv_check_mask(const kv_sketch *s, const kv_sketch *mask)
@@ -656,8 +676,10 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
     if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
 
-    const uint64_t chunk_tiles = ctx->chunk_bases / KV_TILE;
-    const uint64_t chunk_pos = std::min<uint64_t>(ctx->chunk_bases, b.n_tiles * KV_TILE);
+    // with exact n_unique tracking the chunk is what bounds the first-touch table (2^20 positions)
+    const uint64_t chunk_limit = s->track_unique ? std::min<uint64_t>(ctx->chunk_bases, KV_UT_MAX_CHUNK) : ctx->chunk_bases;
+    const uint64_t chunk_tiles = chunk_limit / KV_TILE;
+    const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
     KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
     KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
     for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
@@ -865,7 +887,9 @@ extern "C" int kv_add_hashes(kv_sketch *s, const uint64_t *hashes, uint64_t n)
     CU(cudaSetDevice(s->device));
     KV_TRY(kv_buf_ensure(ctx->misc, n * 8));
     CU(cudaMemcpyAsync(ctx->misc.p, hashes, n * 8, cudaMemcpyHostToDevice, ctx->compute));
-    KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p, nullptr, n));
+    const uint64_t step = s->track_unique ? KV_UT_MAX_CHUNK : n;
+    for (uint64_t o = 0; o < n; o += step)
+        KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p + o, nullptr, std::min(step, n - o)));
     CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }
