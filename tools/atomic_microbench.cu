@@ -54,9 +54,64 @@ __global__ void __launch_bounds__(256) bench(unsigned *table, uint64_t nbytes, u
                     if (o == a) break;
                 }
             }
-        } else {
+        } else if (MODE == 4) {
 #pragma unroll
             for (int t = 0; t < 4; t++) acc += __ldcg(w[t]);
+        } else if (MODE == 5) {   // ld + CAS, first attempt of all four issued back to back, rare retry loop after
+#pragma unroll
+            for (int t = 0; t < 4; t++) old[t] = __ldcg(w[t]);
+            unsigned res[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                res[t] = ((old[t] >> sh[t]) & 255u) != 255u ? atomicCAS(w[t], old[t], old[t] + (1u << sh[t])) : old[t];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (res[t] == old[t]) continue;
+                unsigned o = res[t];
+                while (((o >> sh[t]) & 255u) != 255u) {
+                    unsigned a = o;
+                    o = atomicCAS(w[t], a, a + (1u << sh[t]));
+                    if (o == a) break;
+                }
+            }
+        } else if (MODE == 6) {   // ld + ATOM.ADD with return (speculative add, overflow check on the old value)
+#pragma unroll
+            for (int t = 0; t < 4; t++) old[t] = __ldcg(w[t]);
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (((old[t] >> sh[t]) & 255u) != 255u) acc += (atomicAdd(w[t], 1u << sh[t]) >> sh[t]) & 255u;
+        } else if (MODE == 7) {   // ld + RED.ADD
+#pragma unroll
+            for (int t = 0; t < 4; t++) old[t] = __ldcg(w[t]);
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (((old[t] >> sh[t]) & 255u) != 255u) atomicAdd(w[t], 1u << sh[t]);
+        } else if (MODE == 8) {   // ld.ca + CAS loop
+#pragma unroll
+            for (int t = 0; t < 4; t++) old[t] = *(volatile unsigned *)w[t];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                unsigned o = old[t];
+                while (((o >> sh[t]) & 255u) != 255u) {
+                    unsigned a = o;
+                    o = atomicCAS(w[t], a, a + (1u << sh[t]));
+                    if (o == a) break;
+                }
+            }
+        } else if (MODE == 9) {   // 16-bit CAS on the containing half-word (halves the false sharing)
+#pragma unroll
+            for (int t = 0; t < 4; t++) old[t] = __ldcg(w[t]);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                unsigned short *hw = (unsigned short *)w[t] + (sh[t] >> 4);
+                unsigned hs = sh[t] & 8;
+                unsigned short o = (unsigned short)(old[t] >> (sh[t] & 16));
+                while (((o >> hs) & 255u) != 255u) {
+                    unsigned short a = o;
+                    o = atomicCAS(hw, a, (unsigned short)(a + (1u << hs)));
+                    if (o == a) break;
+                }
+            }
         }
     }
     if (acc == 0xdeadbeef) *sink = acc;
@@ -64,8 +119,8 @@ __global__ void __launch_bounds__(256) bench(unsigned *table, uint64_t nbytes, u
 
 int main()
 {
-    const char *names[5] = {"red_add", "atom_add", "cas_blind", "ld_cas", "ld_only"};
-    const uint64_t sizes[] = {16ull << 20, 64ull << 20, 192ull << 20, 1ull << 30, 4ull << 30};
+    const char *names[10] = {"red_add", "atom_add", "cas_blind", "ld_cas", "ld_only", "ld_cas_batched", "ld_atom_add", "ld_red_add", "ldca_cas", "ld_cas16"};
+    const uint64_t sizes[] = {64ull << 20, 1ull << 30};
     const uint64_t n_items = 21000000;   // one C2 sample
     unsigned *sink;
     cudaMalloc(&sink, 4);
@@ -75,7 +130,7 @@ int main()
     for (uint64_t nbytes : sizes) {
         unsigned *table;
         if (cudaMalloc(&table, nbytes) != cudaSuccess) { printf("alloc %llu failed\n", (unsigned long long)nbytes); continue; }
-        for (int mode = 0; mode < 5; mode++) {
+        for (int mode = 0; mode < 10; mode++) {
             float best = 1e30f;
             for (int rep = 0; rep < 4; rep++) {
                 cudaMemset(table, 0, nbytes);
@@ -87,7 +142,12 @@ int main()
                 case 1: bench<1><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
                 case 2: bench<2><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
                 case 3: bench<3><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
-                default: bench<4><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 4: bench<4><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 5: bench<5><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 6: bench<6><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 7: bench<7><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 8: bench<8><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                default: bench<9><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
                 }
                 cudaEventRecord(e1);
                 cudaEventSynchronize(e1);

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Condense `ncu --page raw --csv` dumps (profiles/*_ncu_raw_*.csv) into one markdown table."""
+import csv
+import glob
+import os
+import sys
+
+WANT = [
+    ('gpu__time_duration.sum', 'time'),
+    ('dram__bytes_read.sum', 'DRAM read'),
+    ('dram__bytes_write.sum', 'DRAM write'),
+    ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %'),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'LTS %'),
+    ('lts__t_sector_hit_rate.pct', 'L2 hit %'),
+    ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'SM %'),
+    ('l1tex__t_sectors_pipe_lsu_mem_global_op_atom.sum', 'atom sectors'),
+    ('l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum', 'red sectors'),
+    ('lts__t_sectors.sum', 'LTS sectors'),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occupancy %'),
+    ('launch__registers_per_thread', 'regs'),
+    ('smsp__inst_executed.sum', 'warp inst'),
+    ('launch__grid_size', 'grid'),
+]
+
+
+def main(pattern):
+    print('| kernel | ' + ' | '.join(label for _, label in WANT) + ' |')
+    print('|---|' + '---|' * len(WANT))
+    for path in sorted(glob.glob(pattern)):
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            name = vals[hdr.index('Kernel Name')].split('(')[0].replace('void ', '')
+            cells = []
+            for metric, _ in WANT:
+                if metric in hdr:
+                    i = hdr.index(metric)
+                    try:
+                        cells.append('{:.4g} {}'.format(float(vals[i].replace(',', '')), units[i]).strip())
+                    except ValueError:
+                        cells.append(vals[i])
+                else:
+                    cells.append('-')
+            print('| `{}` ({}) | '.format(name, os.path.basename(path)) + ' | '.join(cells) + ' |')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1] if len(sys.argv) > 1 else 'profiles/*_ncu_raw_*.csv')
