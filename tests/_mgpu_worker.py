@@ -1,0 +1,81 @@
+"""Worker for tests/test_multigpu.py: one rank per GPU under torchrun (NCCL).
+
+Each rank counts its shard of the same synthetic reads into a partial sketch, the partial
+sketches are merged with every strategy of kevlar_b200.multigpu, and the result must be
+byte-identical to the CPU oracle counting all reads in one process.  The novel scan then runs
+shard-local and the gathered hits must equal the oracle's."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    import torch
+    import kevlar_b200 as kv
+    from kevlar_b200 import multigpu
+    from oracle import khmer_oracle as ko
+    rank, world = multigpu.init_from_env()
+    rng = np.random.default_rng(77)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)
+    genome = letters[rng.integers(0, 4, size=20000)]
+    child = genome.copy()
+    child[7000] = letters[(np.searchsorted(letters, child[7000]) + 1) % 4]
+
+    def reads(g, n, seed):
+        r = np.random.default_rng(seed)
+        out = []
+        for _ in range(n):
+            s = int(r.integers(0, len(g) - 120))
+            out.append(g[s:s + int(r.integers(40, 120))].tobytes())
+        return out
+    samples = [reads(child, 6000, 1) + [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT'] * 700, reads(genome, 6000, 2),
+               reads(genome, 6000, 3)]
+    failures = []
+    for how in ('allreduce', 'allgather', 'p2p'):
+        for cls in ('Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'):
+            gpu, cpu = [], []
+            for seqs in samples:
+                bases, offs = ko.reads_to_batch(seqs)
+                mb, mo = multigpu.shard_batch(bases, offs, rank, world)
+                g = getattr(kv.khmer, cls)(25, 30000, 4)
+                g.consume_batch(mb, mo)
+                multigpu.merge_sketch(g, how=how)
+                c = getattr(ko, cls)(25, 30000, 4)
+                c.consume_batch(bases, offs)
+                for t in range(4):
+                    if g.table_bytes(t) != c.table_bytes(t):
+                        failures.append('{} {} table {} differs on rank {}'.format(how, cls, t, rank))
+                if g.n_occupied() != c.n_occupied():
+                    failures.append('{} {} n_occupied differs'.format(how, cls))
+                gpu.append(g)
+                cpu.append(c)
+            if cls in ('Counttable', 'Countgraph'):
+                bases, offs = ko.reads_to_batch(samples[0])
+                mb, mo = multigpu.shard_batch(bases, offs, rank, world)
+                lo, _ = multigpu.shard_bounds(len(samples[0]), rank, world)
+                hits, flags, _ = kv.khmer.novel_batch(gpu[:1], gpu[1:], mb, mo, 6, 1)
+                allhits = multigpu.gather_hits(hits, lo)
+                ohits, _ = ko.novel_batch(cpu[:1], cpu[1:], bases, offs, 6, 1)
+                order = np.lexsort((allhits['offset'], allhits['read']))
+                allhits = allhits[order]
+                same = len(allhits) == len(ohits) and (allhits['read'] == ohits['read']).all() and \
+                    (allhits['offset'] == ohits['offset']).all() and \
+                    (allhits['abund'][:, :3] == ohits['abund'][:, :3]).all()
+                if not same or len(ohits) == 0:
+                    failures.append('{} {} novel hits differ ({} vs {})'.format(how, cls, len(allhits), len(ohits)))
+            del gpu
+    torch.distributed.barrier()
+    if failures:
+        print('RANK', rank, 'FAILURES:', failures)
+        sys.exit(1)
+    if rank == 0:
+        print('multi-GPU merge OK on', world, 'ranks: allreduce/allgather/p2p x 4 sketch types, novel hits identical')
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
