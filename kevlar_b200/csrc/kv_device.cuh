@@ -17,9 +17,36 @@ struct KvView {
     uint8_t *tab[KV_TABLES_DEV];   // khmer layout: u8[p] | nibbles (even bin = high) | bits (LSB first)
     uint64_t size[KV_TABLES_DEV];  // buckets per table (the primes)
     uint64_t magic[KV_TABLES_DEV]; // floor((2^64-1)/size) for the Barrett reduction below
+    uint32_t *state[KV_TABLES_DEV]; // 2 bits per bucket beside 8/4-bit counters (see KV_ST_*); NULL for bit tables
     int n_tables;
     int bits;                      // 8, 4 or 1
 };
+
+// Per-bucket state kept in a SEPARATE array so that the update path never has to load a
+// counter line before hitting it with an atomic (a plain load followed by an atomic on the same
+// line costs ~3x the atomic alone on B200, profiles/r01_atomic_microbench_variants.csv).
+//   00 empty      counter == 0
+//   01 occupied   0 < counter, and the counter is far enough from saturation to add blindly
+//   11 hot        counter >= KV_HOT (or unknown): exact compare-and-swap path
+// Bits only ever get set (atomicOr), so a stale read is always on the safe side.
+#define KV_ST_OCC 1u
+#define KV_ST_HOT 2u
+
+template <int BITS>
+__device__ __forceinline__ unsigned kv_hot_threshold() { return BITS == 8 ? 128u : 8u; }
+
+__device__ __forceinline__ void kv_state_addr(const KvView &v, int t, uint64_t bin, uint32_t *&word, unsigned &shift)
+{
+    word = v.state[t] + (bin >> 4);
+    shift = 2u * (unsigned)(bin & 15);
+}
+
+// is the bucket empty?  (state array for counters, the table itself for bit tables)
+__device__ __forceinline__ bool kv_bucket_empty(const KvView &v, int t, uint64_t bin)
+{
+    if (v.bits == 1) return !((__ldg(v.tab[t] + (bin >> 3)) >> (bin & 7)) & 1u);
+    return !((__ldg(v.state[t] + (bin >> 4)) >> (2u * (unsigned)(bin & 15))) & KV_ST_OCC);
+}
 
 // h mod p, identical to C's `%` on uint64 (khmer: bin = hash % tablesize).
 // q = mulhi(h, floor((2^64-1)/p)) underestimates floor(h/p) by at most 2, so at most two
@@ -72,19 +99,29 @@ __device__ __forceinline__ void kv_word_addr(const KvView &v, int t, uint64_t bi
     if (BITS == 1) shift += (unsigned)(bin & 7);
 }
 
+// Exact saturating update of one bucket: atomic read of the containing word (an atomic, not a
+// load -- see above), then 32-bit compare-and-swap until the byte/nibble has been bumped or is
+// saturated.  Returns true if this call added one; *seen_old gets the counter value it replaced.
 template <int BITS>
-__device__ __forceinline__ void kv_sat_inc(unsigned *word, unsigned shift, unsigned old)
+__device__ __forceinline__ bool kv_sat_inc_exact(unsigned *word, unsigned shift, unsigned &seen_old)
 {
-    if (BITS == 1) {
-        if (!((old >> shift) & 1u)) atomicOr(word, 1u << shift);
-        return;
-    }
     const unsigned maxv = BITS == 8 ? 255u : 15u;
+    unsigned old = atomicOr(word, 0u);
     while (((old >> shift) & maxv) != maxv) {
         unsigned assumed = old;
         old = atomicCAS(word, assumed, assumed + (1u << shift));
-        if (old == assumed) break;
+        if (old == assumed) { seen_old = (old >> shift) & maxv; return true; }
     }
+    seen_old = maxv;
+    return false;
+}
+
+// after an update that replaced the value `ob`: publish the state bits it implies
+template <int BITS>
+__device__ __forceinline__ void kv_state_publish(uint32_t *sword, unsigned sshift, unsigned st, unsigned ob)
+{
+    unsigned want = KV_ST_OCC | (ob + 1 >= kv_hot_threshold<BITS>() ? KV_ST_HOT : 0u);
+    if (want & ~st) atomicOr(sword, want << sshift);
 }
 
 // ------------------------------------------------------------------ MurmurHash3

@@ -158,60 +158,157 @@ __device__ __forceinline__ bool kv_ut_owns(const KvFirstTable &ft, unsigned long
 }
 
 // ----------------------------------------------------------------------- K3
-
-// One thread per base position (grid-stride).  For every valid k-mer: T bins by Barrett
-// reduction, the T counter words are fetched first (independent loads in flight), then each
-// is bumped with the CAS-saturating update.  With TRACK, candidates flagged by the probe kernel
-// first settle whether they are the first toucher of one of their buckets (n_unique_kmers).
-template <int BITS, bool TRACK, bool HAS_VALID>
+//
+// Saturating counter update, one thread per base position (grid-stride).  For every valid k-mer
+// and each of its T tables:
+//   cold bucket (state != hot): ONE speculative 32-bit ATOM.ADD on the containing word.  Its return
+//       value tells what was replaced: 0 -> publish "occupied"; near the hot threshold -> publish
+//       "hot"; the maximum -> the add carried into the neighbouring counter: raise the chunk's
+//       dirty flag (only possible if >= 128 adds to one bucket were in flight together).
+//   hot bucket: exact path (atomic read + compare-and-swap loop, stops at the maximum).
+//   bit tables: fire-and-forget RED.OR.
+// Every add that actually changed memory is recorded (one bit per position and table), so a
+// dirty chunk can be undone arithmetically -- 32-bit adds commute, whatever transient carries
+// happened -- and redone with the exact path by the two follow-up kernels below, which exit
+// immediately when the flag is clear.  With TRACK, candidates flagged by the probe kernel first
+// settle whether they are the first toucher of one of their buckets (n_unique_kmers).
+template <int BITS, bool TRACK, bool HAS_VALID, bool EXACT>
 __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
                                                            const uint32_t *__restrict__ valid, uint64_t total,
                                                            KvFirstTable ft, const uint32_t *__restrict__ cand,
-                                                           unsigned long long *n_unique)
+                                                           unsigned long long *n_unique, uint32_t *__restrict__ added,
+                                                           uint64_t added_stride, unsigned *dirty)
 {
+    if (EXACT && *dirty == 0) return;   // redo pass of a clean chunk
+    const unsigned maxv = BITS == 8 ? 255u : 15u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
     unsigned fresh = 0;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        if (HAS_VALID) {
-            uint32_t vw = __ldg(valid + (g >> 5));
-            if (!((vw >> (g & 31)) & 1u)) continue;
-        } else if (g >= total)
-            continue;
-        const uint64_t h = __ldcs(hashes + g);
-        const bool is_cand = TRACK && ((__ldg(cand + (g >> 5)) >> (g & 31)) & 1u);
-        if (v.n_tables == 4) {
-            uint64_t bin[4];
-            unsigned *w[4], sh[4], old[4];
+        bool live = g < total;
+        if (HAS_VALID && live) live = (__ldg(valid + (g >> 5)) >> (g & 31)) & 1u;
+        uint64_t h = 0;
+        if (live) h = __ldcs(hashes + g);
+        const bool is_cand = TRACK && live && ((__ldg(cand + (g >> 5)) >> (g & 31)) & 1u);
+        bool is_new = false;
+        if (BITS != 1 && !EXACT && v.n_tables == 4) {
+            // common shape (kevlar always builds 4 tables): addresses and states for all four
+            // tables first, then the four speculative adds back to back (independent L2 round
+            // trips), only then look at what they returned
+            unsigned *w[4], sh[4], ssh[4], st[4], ob[4];
+            uint32_t *sw[4];
+            bool did[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                bin[t] = kv_mod(h, v.size[t], v.magic[t]);
-                kv_word_addr<BITS>(v, t, bin[t], w[t], sh[t]);
-                old[t] = __ldcg(w[t]);
+                did[t] = false;
+                ob[t] = 0;
+                st[t] = KV_ST_HOT;
+                if (live) {
+                    const uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
+                    if (TRACK && is_cand && !is_new) is_new = kv_ut_owns(ft, kv_ut_key(t, bin), (unsigned)g);
+                    kv_word_addr<BITS>(v, t, bin, w[t], sh[t]);
+                    kv_state_addr(v, t, bin, sw[t], ssh[t]);
+                    st[t] = (*(volatile uint32_t *)sw[t] >> ssh[t]) & 3u;
+                }
             }
-            if (TRACK && is_cand) {
-                bool is_new = false;
 #pragma unroll
-                for (int t = 0; t < 4; t++) is_new = is_new || kv_ut_owns(ft, kv_ut_key(t, bin[t]), (unsigned)g);
-                fresh += is_new;
-            }
+            for (int t = 0; t < 4; t++)
+                if (live && !(st[t] & KV_ST_HOT)) {
+                    ob[t] = (atomicAdd(w[t], 1u << sh[t]) >> sh[t]) & maxv;
+                    did[t] = true;
+                }
 #pragma unroll
-            for (int t = 0; t < 4; t++) kv_sat_inc<BITS>(w[t], sh[t], old[t]);
-        } else {
-            bool is_new = false;
-            for (int t = 0; t < v.n_tables; t++) {
-                unsigned *w, sh;
-                uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
-                if (TRACK && is_cand) is_new = is_new || kv_ut_owns(ft, kv_ut_key(t, bin), (unsigned)g);
-                kv_word_addr<BITS>(v, t, bin, w, sh);
-                kv_sat_inc<BITS>(w, sh, __ldcg(w));
+            for (int t = 0; t < 4; t++) {
+                if (live) {
+                    if (st[t] & KV_ST_HOT) {
+                        did[t] = kv_sat_inc_exact<BITS>(w[t], sh[t], ob[t]);
+                        if (did[t]) kv_state_publish<BITS>(sw[t], ssh[t], st[t], ob[t]);
+                    } else if (ob[t] == maxv)
+                        atomicOr(dirty, 1u);
+                    else
+                        kv_state_publish<BITS>(sw[t], ssh[t], st[t], ob[t]);
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, did[t]);
+                if ((threadIdx.x & 31) == 0) added[t * added_stride + (g >> 5)] = bal;
             }
             fresh += is_new;
+            continue;
         }
+#pragma unroll 4
+        for (int t = 0; t < v.n_tables; t++) {
+            bool did = false;
+            if (live) {
+                const uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
+                if (TRACK && is_cand && !is_new) is_new = kv_ut_owns(ft, kv_ut_key(t, bin), (unsigned)g);
+                unsigned *w, sh;
+                kv_word_addr<BITS>(v, t, bin, w, sh);
+                if (BITS == 1) {
+                    atomicOr(w, 1u << sh);
+                } else {
+                    uint32_t *sw;
+                    unsigned ssh;
+                    kv_state_addr(v, t, bin, sw, ssh);
+                    const unsigned st = (*(volatile uint32_t *)sw >> ssh) & 3u;
+                    unsigned ob;
+                    if (EXACT || (st & KV_ST_HOT)) {
+                        did = kv_sat_inc_exact<BITS>(w, sh, ob);
+                        if (did) kv_state_publish<BITS>(sw, ssh, st, ob);
+                    } else {
+                        ob = (atomicAdd(w, 1u << sh) >> sh) & maxv;
+                        did = true;
+                        if (ob == maxv) atomicOr(dirty, 1u);
+                        else kv_state_publish<BITS>(sw, ssh, st, ob);
+                    }
+                }
+            }
+            if (BITS != 1 && !EXACT) {
+                unsigned bal = __ballot_sync(0xffffffffu, did);
+                if ((threadIdx.x & 31) == 0) added[t * added_stride + (g >> 5)] = bal;
+            }
+        }
+        fresh += is_new;
     }
     if (TRACK) {
         fresh = __reduce_add_sync(0xffffffffu, fresh);
         if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_unique, (unsigned long long)fresh);
+    }
+}
+
+// Undo a dirty chunk: subtract exactly what the speculative pass added.
+template <int BITS>
+__global__ void __launch_bounds__(256) kv_rollback_kernel(KvView v, const uint64_t *__restrict__ hashes, uint64_t total,
+                                                          const uint32_t *__restrict__ added, uint64_t added_stride,
+                                                          const unsigned *dirty)
+{
+    if (*dirty == 0) return;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const uint64_t h = hashes[g];
+        for (int t = 0; t < v.n_tables; t++) {
+            if (!((added[t * added_stride + (g >> 5)] >> (g & 31)) & 1u)) continue;
+            unsigned *w, sh;
+            kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w, sh);
+            atomicAdd(w, 0u - (1u << sh));
+        }
+    }
+}
+
+// Recompute the 2-bit state array from the counters (after load / merge / raw writes).
+template <int BITS>
+__global__ void kv_state_rebuild_kernel(KvView v, int t)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_words = (v.size[t] + 15) / 16;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        uint32_t word = 0;
+        for (int j = 0; j < 16; j++) {
+            uint64_t bin = i * 16 + j;
+            if (bin >= v.size[t]) break;
+            unsigned c = BITS == 8 ? v.tab[t][bin] : ((v.tab[t][bin >> 1] >> ((bin & 1) ? 0 : 4)) & 15u);
+            unsigned st = c == 0 ? 0u : (c >= kv_hot_threshold<BITS>() ? (KV_ST_OCC | KV_ST_HOT) : KV_ST_OCC);
+            word |= st << (2 * j);
+        }
+        v.state[t][i] = word;
     }
 }
 
@@ -279,7 +376,7 @@ __global__ void __launch_bounds__(256) kv_unique_probe_kernel(KvView v, KvFirstT
 #pragma unroll 4
             for (int t = 0; t < v.n_tables; t++) {
                 bin[t] = kv_mod(h, v.size[t], v.magic[t]);
-                if (kv_bucket_get(v, t, bin[t]) == 0) empty |= 1u << t;
+                if (kv_bucket_empty(v, t, bin[t])) empty |= 1u << t;
             }
             is_cand = empty != 0;
             for (int t = 0; t < v.n_tables; t++)

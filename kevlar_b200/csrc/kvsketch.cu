@@ -70,7 +70,9 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc, ut;
+    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc, ut, added;
+    unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
+    unsigned dirty_next = 0;
     int ut_log2 = 0;          // first-touch table: 2^ut_log2 slots
     unsigned ut_epoch = 0;    // 1..7, 0 = freshly wiped
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
@@ -112,6 +114,8 @@ static int kv_ctx_get(int device, KvCtx **out)
         CU(cudaMalloc(&c.counters, 8 * sizeof(unsigned long long)));
         CU(cudaMemset(c.counters, 0, 8 * sizeof(unsigned long long)));
         CU(cudaMallocHost(&c.h_counters, 8 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c.dirty, 64 * sizeof(unsigned)));
+        CU(cudaMemset(c.dirty, 0, 64 * sizeof(unsigned)));
         CU(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
         if (const char *env = getenv("KV_CHUNK_BASES")) {
             uint64_t v = strtoull(env, nullptr, 10);
@@ -170,6 +174,9 @@ struct kv_sketch {
     uint64_t toff[KV_TABLES_DEV];     // offset of each table in the flat allocation
     uint64_t flat_bytes;
     uint8_t *flat;
+    uint32_t *state;                  // 2-bit bucket states (KV_ST_*), 8/4-bit sketches only
+    uint64_t soff[KV_TABLES_DEV];     // word offset of each table's states
+    uint64_t state_words;
     bool track_unique, unique_valid;
     uint64_t n_unique;                // host copy, updated at stats time
     unsigned long long *d_unique;     // device accumulator
@@ -181,6 +188,8 @@ static uint64_t kv_table_bytes(int bits, uint64_t size)
     return bits == 8 ? size : (bits == 4 ? size / 2 + 1 : size / 8 + 1);
 }
 
+static int kv_state_rebuild_locked(KvCtx *ctx, kv_sketch *s);
+
 static KvView kv_view(const kv_sketch *s)
 {
     KvView v;
@@ -191,6 +200,7 @@ static KvView kv_view(const kv_sketch *s)
         v.tab[t] = s->flat + s->toff[t];
         v.size[t] = s->sizes[t];
         v.magic[t] = UINT64_MAX / s->sizes[t];
+        v.state[t] = s->state ? s->state + s->soff[t] : nullptr;
     }
     return v;
 }
@@ -247,14 +257,17 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     kv_sketch *s = new kv_sketch();
     memset(s, 0, sizeof *s);
     s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
-    uint64_t off = 0;
+    uint64_t off = 0, soff = 0;
     for (int t = 0; t < n_tables; t++) {
         if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete s; return kv_fail(KV_EINVAL, "bad table size"); }
         s->sizes[t] = sizes[t];
         s->nbytes[t] = kv_table_bytes(bits, sizes[t]);
         s->toff[t] = off;
         off += (s->nbytes[t] + 255) & ~(uint64_t)255;
+        s->soff[t] = soff;
+        soff += ((sizes[t] + 15) / 16 + 63) & ~(uint64_t)63;
     }
+    s->state_words = bits == 1 ? 0 : soff;
     s->flat_bytes = off;
     cudaError_t e = cudaMalloc((void **)&s->flat, off);
     if (e != cudaSuccess) {
@@ -264,6 +277,16 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
                        cudaGetErrorString(e));
     }
     if (zero) CU(cudaMemsetAsync(s->flat, 0, off, ctx->compute));
+    if (s->state_words) {
+        e = cudaMalloc((void **)&s->state, s->state_words * 4);
+        if (e != cudaSuccess) {
+            cudaFree(s->flat);
+            delete s;
+            cudaGetLastError();
+            return kv_fail(KV_ENOMEM, "cannot allocate the bucket-state array: %s", cudaGetErrorString(e));
+        }
+        CU(cudaMemsetAsync(s->state, 0, s->state_words * 4, ctx->compute));
+    }
     CU(cudaMalloc((void **)&s->d_unique, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
     s->track_unique = true;
@@ -289,6 +312,7 @@ extern "C" int kv_sketch_destroy(kv_sketch *s)
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(ctx->compute));
     if (s->flat) cudaFree(s->flat);
+    if (s->state) cudaFree(s->state);
     if (s->d_unique) cudaFree(s->d_unique);
     delete s;
     return KV_OK;
@@ -302,6 +326,7 @@ extern "C" int kv_sketch_clear(kv_sketch *s)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     CU(cudaMemsetAsync(s->flat, 0, s->flat_bytes, ctx->compute));
+    if (s->state) CU(cudaMemsetAsync(s->state, 0, s->state_words * 4, ctx->compute));
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
     s->unique_valid = true;   // first[] is all-ones between batches by construction
     s->n_unique = 0;
@@ -370,8 +395,22 @@ extern "C" int kv_sketch_write_table(kv_sketch *s, int t, const uint8_t *host_in
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(s->flat + s->toff[t], host_in, nbytes, cudaMemcpyHostToDevice, ctx->compute));
+    KV_TRY(kv_state_rebuild_locked(ctx, s));
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
+    return KV_OK;
+}
+
+// bucket states from the counters (after anything that wrote the tables behind the kernels' back)
+static int kv_state_rebuild_locked(KvCtx *ctx, kv_sketch *s)
+{
+    if (!s->state) return KV_OK;
+    KvView v = kv_view(s);
+    for (int t = 0; t < s->n_tables; t++) {
+        uint64_t n_words = (s->sizes[t] + 15) / 16;
+        if (s->bits == 8) LAUNCH(ctx, kv_state_rebuild_kernel<8>, kv_grid_for(ctx, n_words), 256, v, t);
+        else LAUNCH(ctx, kv_state_rebuild_kernel<4>, kv_grid_for(ctx, n_words), 256, v, t);
+    }
     return KV_OK;
 }
 
@@ -491,7 +530,8 @@ extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int
     }
     cudaFreeHost(stage);
     fclose(f);
-    if (rc != KV_OK) { cudaFree(s->flat); cudaFree(s->d_unique); delete s; return rc; }
+    if (rc != KV_OK) { cudaFree(s->flat); cudaFree(s->state); cudaFree(s->d_unique); delete s; return rc; }
+    KV_TRY(kv_state_rebuild_locked(ctx, s));
     s->file_occupied = occ;
     *out = s;
     return KV_OK;
@@ -614,13 +654,29 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_ha
                                bool track, const KvFirstTable &ft, const uint32_t *cand, unsigned long long *d_unique)
 {
     unsigned grid = kv_grid_for(ctx, n);
-    if (track) {
-        if (d_valid) LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, true, true>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
-        else LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, true, false>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
-    } else {
-        if (d_valid) LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, false, true>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
-        else LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, false, false>), grid, 256, v, d_hashes, d_valid, n, ft, cand, d_unique);
+    const uint64_t stride = (n + 31) / 32 + 1;
+    uint32_t *added = nullptr;
+    unsigned *dirty = nullptr;
+    if (BITS != 1) {
+        KV_TRY(kv_buf_ensure(ctx->added, stride * 4 * KV_TABLES_DEV));
+        added = (uint32_t *)ctx->added.p;
+        if (ctx->dirty_next == 64) {
+            CU(cudaMemsetAsync(ctx->dirty, 0, 64 * sizeof(unsigned), ctx->compute));
+            ctx->dirty_next = 0;
+        }
+        dirty = ctx->dirty + ctx->dirty_next++;
     }
+#define KV_INC(TRACK_, VALID_, EXACT_)                                                                               \
+    LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, TRACK_, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, \
+             ft, cand, d_unique, added, stride, dirty)
+    if (track) { if (d_valid) KV_INC(true, true, false); else KV_INC(true, false, false); }
+    else { if (d_valid) KV_INC(false, true, false); else KV_INC(false, false, false); }
+    if (BITS != 1) {
+        // fix-up pair: both exit at once unless the speculative pass saw a counter overflow
+        LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_rollback_kernel<BITS>, grid, 256, v, d_hashes, n, added, stride, dirty);
+        if (d_valid) KV_INC(false, true, true); else KV_INC(false, false, true);
+    }
+#undef KV_INC
     return KV_OK;
 }
 
@@ -956,6 +1012,7 @@ extern "C" int kv_sketch_narrow(kv_sketch *s, const void *dev_in)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     LAUNCH_C(KV_PROF_MERGE, ctx, kv_narrow_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_in);
+    KV_TRY(kv_state_rebuild_locked(ctx, s));
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -986,6 +1043,7 @@ extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat,
     for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)((const uint8_t *)peer_flat[i] + byte_lo);
     uint64_t n_vec = (byte_hi - byte_lo) / 16;
     LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
+    if (byte_lo == 0 && byte_hi == s->flat_bytes) KV_TRY(kv_state_rebuild_locked(ctx, s));   // sliced merges: rebuilt after the gather phase
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -1002,6 +1060,7 @@ extern "C" int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uin
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(s->flat + byte_lo, (const uint8_t *)peer_flat + byte_lo, byte_hi - byte_lo,
                        cudaMemcpyDeviceToDevice, ctx->compute));
+    KV_TRY(kv_state_rebuild_locked(ctx, s));
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;

@@ -98,6 +98,33 @@ __global__ void __launch_bounds__(256) bench(unsigned *table, uint64_t nbytes, u
                     if (o == a) break;
                 }
             }
+        } else if (MODE >= 10 && MODE <= 13) {   // how the expected value is fetched: cv / relaxed.gpu / atom.or 0 / acquire
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (MODE == 10) old[t] = __ldcv(w[t]);
+                else if (MODE == 11) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(old[t]) : "l"(w[t]) : "memory");
+                else if (MODE == 12) old[t] = atomicOr(w[t], 0u);
+                else asm volatile("ld.global.lu.u32 %0, [%1];" : "=r"(old[t]) : "l"(w[t]) : "memory");
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                unsigned o = old[t];
+                while (((o >> sh[t]) & 255u) != 255u) {
+                    unsigned a = o;
+                    o = atomicCAS(w[t], a, a + (1u << sh[t]));
+                    if (o == a) break;
+                }
+            }
+        } else if (MODE == 14) {   // side bitmap (1 bit per counter, separate array) + speculative ATOM.ADD
+            const unsigned *bitmap = table + (nbytes >> 2);   // caller allocates nbytes + nbytes/8
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                uint64_t byte = (uint64_t)((const char *)w[t] - (const char *)table) + (sh[t] >> 3);
+                old[t] = __ldg(bitmap + (byte >> 5)) >> (byte & 31);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (!(old[t] & 1u)) acc += (atomicAdd(w[t], 1u << sh[t]) >> sh[t]) & 255u;
         } else if (MODE == 9) {   // 16-bit CAS on the containing half-word (halves the false sharing)
 #pragma unroll
             for (int t = 0; t < 4; t++) old[t] = __ldcg(w[t]);
@@ -119,7 +146,7 @@ __global__ void __launch_bounds__(256) bench(unsigned *table, uint64_t nbytes, u
 
 int main()
 {
-    const char *names[10] = {"red_add", "atom_add", "cas_blind", "ld_cas", "ld_only", "ld_cas_batched", "ld_atom_add", "ld_red_add", "ldca_cas", "ld_cas16"};
+    const char *names[15] = {"red_add", "atom_add", "cas_blind", "ld_cas", "ld_only", "ld_cas_batched", "ld_atom_add", "ld_red_add", "ldca_cas", "ld_cas16", "ldcv_cas", "ldrelaxed_cas", "atomor0_cas", "ldlu_cas", "bitmap_atom_add"};
     const uint64_t sizes[] = {64ull << 20, 1ull << 30};
     const uint64_t n_items = 21000000;   // one C2 sample
     unsigned *sink;
@@ -129,11 +156,11 @@ int main()
     printf("mode,table_MB,ms,G_updates_per_s,G_items_per_s\n");
     for (uint64_t nbytes : sizes) {
         unsigned *table;
-        if (cudaMalloc(&table, nbytes) != cudaSuccess) { printf("alloc %llu failed\n", (unsigned long long)nbytes); continue; }
-        for (int mode = 0; mode < 10; mode++) {
+        if (cudaMalloc(&table, nbytes + nbytes / 8 + 256) != cudaSuccess) { printf("alloc %llu failed\n", (unsigned long long)nbytes); continue; }
+        for (int mode = 0; mode < 15; mode++) {
             float best = 1e30f;
             for (int rep = 0; rep < 4; rep++) {
-                cudaMemset(table, 0, nbytes);
+                cudaMemset(table, 0, nbytes + nbytes / 8 + 256);
                 cudaEvent_t e0, e1;
                 cudaEventCreate(&e0); cudaEventCreate(&e1);
                 cudaEventRecord(e0);
@@ -147,7 +174,12 @@ int main()
                 case 6: bench<6><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
                 case 7: bench<7><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
                 case 8: bench<8><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
-                default: bench<9><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 9: bench<9><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 10: bench<10><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 11: bench<11><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 12: bench<12><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                case 13: bench<13><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
+                default: bench<14><<<sm * 8, 256>>>(table, nbytes, n_items, sink); break;
                 }
                 cudaEventRecord(e1);
                 cudaEventSynchronize(e1);
