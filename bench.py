@@ -317,9 +317,9 @@ def run_ours(args):
     kmers_count = (nk_rank - int(np.maximum(np.diff(trio[0][1].astype(np.int64)) - K + 1, 0).sum())) // 3
     kmers_scan = nk_rank - 3 * kmers_count
     lfrac = READ_LEN / float(READ_LEN - K + 1)
-    alg_bytes = {   # algorithmic bytes per LAUNCH (SURVEY.md 8d per-k-mer figure x k-mers per launch)
-        'increment': 64.0 * N_TABLES * kmers_count,
-        'hash': lfrac * kmers_count,
+    alg_bytes = {   # algorithmic bytes per STEP and kernel class (SURVEY.md 8d per-k-mer figure x k-mers per step)
+        'increment': 64.0 * N_TABLES * kmers_count * 3,
+        'hash': lfrac * kmers_count * 3,
         'novel': (32.0 * 3 * N_TABLES + lfrac) * kmers_scan,
     }
     peak, peak_src = load_peaks()
@@ -330,17 +330,20 @@ def run_ours(args):
             continue
         entry = {'launches_per_step': count / args.steps, 'ms_per_launch': ms / count,
                  'share_of_kernel_time': ms / total_kernel_ms}
+        entry['ms_per_step'] = ms / args.steps
         if name in alg_bytes:
-            entry['algorithmic_GBps'] = alg_bytes[name] / (ms / count / 1e3) / 1e9
+            entry['algorithmic_GBps'] = alg_bytes[name] / (ms / args.steps / 1e3) / 1e9
         kernels[name] = entry
     dominant = max((k for k in kernels if k in alg_bytes), key=lambda k_: kernels[k_]['share_of_kernel_time'])
     kname = {'increment': 'kv_increment_kernel<8>', 'hash': 'kv_hash_kernel', 'novel': 'kv_novel_kernel'}[dominant]
     achieved = kernels[dominant]['algorithmic_GBps']
     roofline = {'kernel': kname, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': load_traffic(kname), 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': alg_bytes[dominant]}
+                'algorithmic_bytes_per_launch': alg_bytes[dominant] / kernels[dominant]['launches_per_step'],
+                'launches_per_step': kernels[dominant]['launches_per_step'],
+                'avg_launch_ms': kernels[dominant]['ms_per_launch']}
     # the count path (hash + unique + increment per sample) and the novel path against 8d's figures
-    count_ms = sum(prof[c][0] for c in ('hash', 'unique', 'increment')) / (3.0 * args.steps)
+    count_ms = sum(prof[c][0] for c in ('hash', 'unique', 'increment', 'fixup')) / (3.0 * args.steps)
     novel_ms = prof['novel'][0] / args.steps
     paths = {
         'count': {'ms_per_sample': count_ms, 'kmers_per_s': kmers_count / (count_ms / 1e3),
@@ -407,6 +410,8 @@ def run_ours(args):
             del r2
         line['variants'] = variants
     print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def main():

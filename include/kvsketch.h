@@ -190,8 +190,9 @@ int kv_sync(int device);
 /* Per-kernel-class device timing, measured with CUDA events on the launching stream.
  * enable: 1 = start (and reset), 0 = stop (and reset), 2 = read only.  ms_out / n_out receive
  * KV_PROF_CLASSES totals accumulated since the last reset: milliseconds and launch counts for
- * [0] other, [1] hash, [2] increment, [3] unique-tracking, [4] novel, [5] merge kernels. */
-#define KV_PROF_CLASSES 6
+ * [0] other, [1] hash, [2] increment, [3] unique-tracking probe, [4] novel, [5] merge,
+ * [6] overflow fix-up (rollback + exact redo; normally two empty launches per chunk). */
+#define KV_PROF_CLASSES 7
 int kv_profile(int device, int enable, double *ms_out, uint64_t *n_out);
 
 /* Number of kernels this library has launched on `device` since load (bench accounting). */

@@ -50,7 +50,7 @@ extern "C" int kv_abi_version(void) { return KV_ABI_VERSION; }
 // ------------------------------------------------------------------ context
 
 enum { KV_PROF_OTHER = 0, KV_PROF_HASH = 1, KV_PROF_INCREMENT = 2, KV_PROF_UNIQUE = 3, KV_PROF_NOVEL = 4,
-       KV_PROF_MERGE = 5 };   // KV_PROF_CLASSES (= 6) comes from kvsketch.h
+       KV_PROF_MERGE = 5, KV_PROF_FIXUP = 6 };   // KV_PROF_CLASSES (= 7) comes from kvsketch.h
 
 struct KvBuf {
     void *p = nullptr;
@@ -666,6 +666,9 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_ha
         }
         dirty = ctx->dirty + ctx->dirty_next++;
     }
+#define KV_INC_X(TRACK_, VALID_, EXACT_)                                                                             \
+    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_increment_kernel<BITS, TRACK_, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, \
+             ft, cand, d_unique, added, stride, dirty)
 #define KV_INC(TRACK_, VALID_, EXACT_)                                                                               \
     LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, TRACK_, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, \
              ft, cand, d_unique, added, stride, dirty)
@@ -673,10 +676,11 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_ha
     else { if (d_valid) KV_INC(false, true, false); else KV_INC(false, false, false); }
     if (BITS != 1) {
         // fix-up pair: both exit at once unless the speculative pass saw a counter overflow
-        LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_rollback_kernel<BITS>, grid, 256, v, d_hashes, n, added, stride, dirty);
-        if (d_valid) KV_INC(false, true, true); else KV_INC(false, false, true);
+        LAUNCH_C(KV_PROF_FIXUP, ctx, kv_rollback_kernel<BITS>, grid, 256, v, d_hashes, n, added, stride, dirty);
+        if (d_valid) KV_INC_X(false, true, true); else KV_INC_X(false, false, true);
     }
 #undef KV_INC
+#undef KV_INC_X
     return KV_OK;
 }
 
