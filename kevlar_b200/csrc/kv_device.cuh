@@ -17,35 +17,46 @@ struct KvView {
     uint8_t *tab[KV_TABLES_DEV];   // khmer layout: u8[p] | nibbles (even bin = high) | bits (LSB first)
     uint64_t size[KV_TABLES_DEV];  // buckets per table (the primes)
     uint64_t magic[KV_TABLES_DEV]; // floor((2^64-1)/size) for the Barrett reduction below
-    uint32_t *state[KV_TABLES_DEV]; // 2 bits per bucket beside 8/4-bit counters (see KV_ST_*); NULL for bit tables
+    uint32_t *occ[KV_TABLES_DEV];  // 1 bit per bucket: counter != 0 (8/4-bit sketches; NULL for bit tables)
+    uint32_t *hotf;                // "maybe hot" filter shared by all tables: 2^hot_log2 bits
+    int hot_log2;
     int n_tables;
     int bits;                      // 8, 4 or 1
 };
 
-// Per-bucket state kept in a SEPARATE array so that the update path never has to load a
+// Side information kept in SEPARATE small arrays so that the update path never has to load a
 // counter line before hitting it with an atomic (a plain load followed by an atomic on the same
-// line costs ~3x the atomic alone on B200, profiles/r01_atomic_microbench_variants.csv).
-//   00 empty      counter == 0
-//   01 occupied   0 < counter, and the counter is far enough from saturation to add blindly
-//   11 hot        counter >= KV_HOT (or unknown): exact compare-and-swap path
+// line costs ~3x the atomic alone on B200, profiles/r01_atomic_microbench_variants.csv):
+//   occ[t]  exact occupancy bitmap, read by the n_unique probe ("was this bucket empty?");
+//   hotf    a small hashed bit filter; a set bit means the bucket MAY hold a counter at or above
+//           KV_HOT (128 / 8) and must take the exact compare-and-swap path.  It is 1/8 bit per
+//           bucket, so it stays cache-resident; false positives only cost speed.
 // Bits only ever get set (atomicOr), so a stale read is always on the safe side.
-#define KV_ST_OCC 1u
-#define KV_ST_HOT 2u
-
 template <int BITS>
 __device__ __forceinline__ unsigned kv_hot_threshold() { return BITS == 8 ? 128u : 8u; }
 
-__device__ __forceinline__ void kv_state_addr(const KvView &v, int t, uint64_t bin, uint32_t *&word, unsigned &shift)
+__device__ __forceinline__ uint64_t kv_hot_index(const KvView &v, int t, uint64_t bin)
 {
-    word = v.state[t] + (bin >> 4);
-    shift = 2u * (unsigned)(bin & 15);
+    return ((bin * 8 + (uint64_t)t) * 0x9E3779B97F4A7C15ull) >> (64 - v.hot_log2);
 }
 
-// is the bucket empty?  (state array for counters, the table itself for bit tables)
+__device__ __forceinline__ bool kv_maybe_hot(const KvView &v, int t, uint64_t bin)
+{
+    uint64_t i = kv_hot_index(v, t, bin);
+    return (*(volatile uint32_t *)(v.hotf + (i >> 5)) >> (i & 31)) & 1u;
+}
+
+__device__ __forceinline__ void kv_mark_hot(const KvView &v, int t, uint64_t bin)
+{
+    uint64_t i = kv_hot_index(v, t, bin);
+    atomicOr(v.hotf + (i >> 5), 1u << (i & 31));
+}
+
+// is the bucket empty?  (occupancy bitmap for counters, the table itself for bit tables)
 __device__ __forceinline__ bool kv_bucket_empty(const KvView &v, int t, uint64_t bin)
 {
     if (v.bits == 1) return !((__ldg(v.tab[t] + (bin >> 3)) >> (bin & 7)) & 1u);
-    return !((__ldg(v.state[t] + (bin >> 4)) >> (2u * (unsigned)(bin & 15))) & KV_ST_OCC);
+    return !((__ldg(v.occ[t] + (bin >> 5)) >> (bin & 31)) & 1u);
 }
 
 // h mod p, identical to C's `%` on uint64 (khmer: bin = hash % tablesize).
@@ -116,12 +127,12 @@ __device__ __forceinline__ bool kv_sat_inc_exact(unsigned *word, unsigned shift,
     return false;
 }
 
-// after an update that replaced the value `ob`: publish the state bits it implies
+// after an update that replaced the value `ob`: publish what it implies
 template <int BITS>
-__device__ __forceinline__ void kv_state_publish(uint32_t *sword, unsigned sshift, unsigned st, unsigned ob)
+__device__ __forceinline__ void kv_state_publish(const KvView &v, int t, uint64_t bin, unsigned ob)
 {
-    unsigned want = KV_ST_OCC | (ob + 1 >= kv_hot_threshold<BITS>() ? KV_ST_HOT : 0u);
-    if (want & ~st) atomicOr(sword, want << sshift);
+    if (ob == 0) atomicOr(v.occ[t] + (bin >> 5), 1u << (bin & 31));
+    if (ob + 1 >= kv_hot_threshold<BITS>()) kv_mark_hot(v, t, bin);
 }
 
 // ------------------------------------------------------------------ MurmurHash3

@@ -109,10 +109,12 @@ __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
 #define KV_UT_MAX_CHUNK (1u << KV_UT_IDX_BITS)
 
 struct KvFirstTable {
-    unsigned long long *slots;
-    int log2_slots;
-    unsigned epoch;   // 1..7; 0 marks wiped slots
+    unsigned long long *small;   // primary table: 2^log2_small slots, at most KV_UT_SMALL_PROBES probes
+    unsigned long long *big;     // overflow table sized for the worst case of one chunk
+    int log2_small, log2_big;
+    unsigned epoch;              // 1..7; 0 marks wiped slots
 };
+#define KV_UT_SMALL_PROBES 16
 
 __device__ __forceinline__ unsigned long long kv_ut_key(int t, uint64_t bin)
 {
@@ -124,33 +126,53 @@ __device__ __forceinline__ uint64_t kv_ut_home(unsigned long long key, int log2_
     return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2_slots);
 }
 
+// try to record `entry` in the slot; 1 = done, 0 = slot belongs to another key
+__device__ __forceinline__ int kv_ut_try(unsigned long long *slotp, unsigned long long entry, unsigned long long key,
+                                         unsigned pos, unsigned epoch)
+{
+    unsigned long long cur = __ldcg(slotp);
+    while ((cur >> 61) != epoch) {   // wiped or left over from an earlier chunk: claim it
+        unsigned long long prev = atomicCAS(slotp, cur, entry);
+        if (prev == cur) return 1;
+        cur = prev;
+    }
+    if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) != key) return 0;
+    if (pos < (unsigned)(cur & KV_UT_IDX_MASK)) atomicMin(slotp, entry);
+    return 1;
+}
+
+// Most chunks have few candidates, so they live in the small (L2-resident) primary table;
+// only when KV_UT_SMALL_PROBES consecutive slots are taken does a key go to the big table.
+// Slots are never released within an epoch, which keeps insert and lookup consistent.
 __device__ __forceinline__ void kv_ut_insert(const KvFirstTable &ft, unsigned long long key, unsigned pos)
 {
     const unsigned long long entry = ((unsigned long long)ft.epoch << 61) | (key << KV_UT_IDX_BITS) | pos;
-    const uint64_t mask = (1ull << ft.log2_slots) - 1ull;
-    uint64_t slot = kv_ut_home(key, ft.log2_slots);
-    for (;;) {
-        unsigned long long cur = __ldcg(ft.slots + slot);
-        while ((cur >> 61) != ft.epoch) {   // wiped or left over from an earlier chunk: claim it
-            unsigned long long prev = atomicCAS(ft.slots + slot, cur, entry);
-            if (prev == cur) return;
-            cur = prev;
-        }
-        if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) {
-            if (pos < (unsigned)(cur & KV_UT_IDX_MASK)) atomicMin(ft.slots + slot, entry);
-            return;
-        }
+    uint64_t mask = (1ull << ft.log2_small) - 1ull;
+    uint64_t slot = kv_ut_home(key, ft.log2_small);
+    for (int i = 0; i < KV_UT_SMALL_PROBES; i++) {
+        if (kv_ut_try(ft.small + slot, entry, key, pos, ft.epoch)) return;
         slot = (slot + 1) & mask;
     }
+    mask = (1ull << ft.log2_big) - 1ull;
+    slot = kv_ut_home(key, ft.log2_big);
+    while (!kv_ut_try(ft.big + slot, entry, key, pos, ft.epoch)) slot = (slot + 1) & mask;
 }
 
 // is `pos` the first position of this chunk that touched (t, bin)?
 __device__ __forceinline__ bool kv_ut_owns(const KvFirstTable &ft, unsigned long long key, unsigned pos)
 {
-    const uint64_t mask = (1ull << ft.log2_slots) - 1ull;
-    uint64_t slot = kv_ut_home(key, ft.log2_slots);
+    uint64_t mask = (1ull << ft.log2_small) - 1ull;
+    uint64_t slot = kv_ut_home(key, ft.log2_small);
+    for (int i = 0; i < KV_UT_SMALL_PROBES; i++) {
+        unsigned long long cur = __ldcg(ft.small + slot);
+        if ((cur >> 61) != ft.epoch) return false;
+        if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) return (unsigned)(cur & KV_UT_IDX_MASK) == pos;
+        slot = (slot + 1) & mask;
+    }
+    mask = (1ull << ft.log2_big) - 1ull;
+    slot = kv_ut_home(key, ft.log2_big);
     for (;;) {
-        unsigned long long cur = __ldcg(ft.slots + slot);
+        unsigned long long cur = __ldcg(ft.big + slot);
         if ((cur >> 61) != ft.epoch) return false;
         if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) return (unsigned)(cur & KV_UT_IDX_MASK) == pos;
         slot = (slot + 1) & mask;
@@ -195,38 +217,37 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
             // common shape (kevlar always builds 4 tables): addresses and states for all four
             // tables first, then the four speculative adds back to back (independent L2 round
             // trips), only then look at what they returned
-            unsigned *w[4], sh[4], ssh[4], st[4], ob[4];
-            uint32_t *sw[4];
-            bool did[4];
+            unsigned *w[4], sh[4], ob[4];
+            uint64_t bin[4];
+            bool did[4], hot[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 did[t] = false;
                 ob[t] = 0;
-                st[t] = KV_ST_HOT;
+                hot[t] = true;
                 if (live) {
-                    const uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
-                    if (TRACK && is_cand && !is_new) is_new = kv_ut_owns(ft, kv_ut_key(t, bin), (unsigned)g);
-                    kv_word_addr<BITS>(v, t, bin, w[t], sh[t]);
-                    kv_state_addr(v, t, bin, sw[t], ssh[t]);
-                    st[t] = (*(volatile uint32_t *)sw[t] >> ssh[t]) & 3u;
+                    bin[t] = kv_mod(h, v.size[t], v.magic[t]);
+                    if (TRACK && is_cand && !is_new) is_new = kv_ut_owns(ft, kv_ut_key(t, bin[t]), (unsigned)g);
+                    kv_word_addr<BITS>(v, t, bin[t], w[t], sh[t]);
+                    hot[t] = kv_maybe_hot(v, t, bin[t]);
                 }
             }
 #pragma unroll
             for (int t = 0; t < 4; t++)
-                if (live && !(st[t] & KV_ST_HOT)) {
+                if (live && !hot[t]) {
                     ob[t] = (atomicAdd(w[t], 1u << sh[t]) >> sh[t]) & maxv;
                     did[t] = true;
                 }
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 if (live) {
-                    if (st[t] & KV_ST_HOT) {
+                    if (hot[t]) {
                         did[t] = kv_sat_inc_exact<BITS>(w[t], sh[t], ob[t]);
-                        if (did[t]) kv_state_publish<BITS>(sw[t], ssh[t], st[t], ob[t]);
+                        if (did[t]) kv_state_publish<BITS>(v, t, bin[t], ob[t]);
                     } else if (ob[t] == maxv)
                         atomicOr(dirty, 1u);
                     else
-                        kv_state_publish<BITS>(sw[t], ssh[t], st[t], ob[t]);
+                        kv_state_publish<BITS>(v, t, bin[t], ob[t]);
                 }
                 unsigned bal = __ballot_sync(0xffffffffu, did[t]);
                 if ((threadIdx.x & 31) == 0) added[t * added_stride + (g >> 5)] = bal;
@@ -245,19 +266,15 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
                 if (BITS == 1) {
                     atomicOr(w, 1u << sh);
                 } else {
-                    uint32_t *sw;
-                    unsigned ssh;
-                    kv_state_addr(v, t, bin, sw, ssh);
-                    const unsigned st = (*(volatile uint32_t *)sw >> ssh) & 3u;
                     unsigned ob;
-                    if (EXACT || (st & KV_ST_HOT)) {
+                    if (EXACT || kv_maybe_hot(v, t, bin)) {
                         did = kv_sat_inc_exact<BITS>(w, sh, ob);
-                        if (did) kv_state_publish<BITS>(sw, ssh, st, ob);
+                        if (did) kv_state_publish<BITS>(v, t, bin, ob);
                     } else {
                         ob = (atomicAdd(w, 1u << sh) >> sh) & maxv;
                         did = true;
                         if (ob == maxv) atomicOr(dirty, 1u);
-                        else kv_state_publish<BITS>(sw, ssh, st, ob);
+                        else kv_state_publish<BITS>(v, t, bin, ob);
                     }
                 }
             }
@@ -293,22 +310,23 @@ __global__ void __launch_bounds__(256) kv_rollback_kernel(KvView v, const uint64
     }
 }
 
-// Recompute the 2-bit state array from the counters (after load / merge / raw writes).
+// Recompute the occupancy bitmap and the hot filter from the counters (after load / merge /
+// raw writes).  One thread per 32 buckets.
 template <int BITS>
 __global__ void kv_state_rebuild_kernel(KvView v, int t)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_words = (v.size[t] + 15) / 16;
+    const uint64_t n_words = (v.size[t] + 31) / 32;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
         uint32_t word = 0;
-        for (int j = 0; j < 16; j++) {
-            uint64_t bin = i * 16 + j;
+        for (int j = 0; j < 32; j++) {
+            uint64_t bin = i * 32 + j;
             if (bin >= v.size[t]) break;
             unsigned c = BITS == 8 ? v.tab[t][bin] : ((v.tab[t][bin >> 1] >> ((bin & 1) ? 0 : 4)) & 15u);
-            unsigned st = c == 0 ? 0u : (c >= kv_hot_threshold<BITS>() ? (KV_ST_OCC | KV_ST_HOT) : KV_ST_OCC);
-            word |= st << (2 * j);
+            if (c) word |= 1u << j;
+            if (c >= kv_hot_threshold<BITS>()) kv_mark_hot(v, t, bin);
         }
-        v.state[t][i] = word;
+        v.occ[t][i] = word;
     }
 }
 

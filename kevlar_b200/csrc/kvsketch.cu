@@ -70,7 +70,8 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc, ut, added;
+    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc, ut, ut_small, added;
+    int ut_small_log2 = 0;
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
     int ut_log2 = 0;          // first-touch table: 2^ut_log2 slots
@@ -174,8 +175,10 @@ struct kv_sketch {
     uint64_t toff[KV_TABLES_DEV];     // offset of each table in the flat allocation
     uint64_t flat_bytes;
     uint8_t *flat;
-    uint32_t *state;                  // 2-bit bucket states (KV_ST_*), 8/4-bit sketches only
-    uint64_t soff[KV_TABLES_DEV];     // word offset of each table's states
+    uint32_t *state;                  // [occ bitmap of table 0 | ... | hot filter], 8/4-bit sketches only
+    uint64_t soff[KV_TABLES_DEV];     // word offset of each table's occupancy bitmap
+    uint64_t hot_off;                 // word offset of the hot filter
+    int hot_log2;                     // hot filter holds 2^hot_log2 bits
     uint64_t state_words;
     bool track_unique, unique_valid;
     uint64_t n_unique;                // host copy, updated at stats time
@@ -196,11 +199,13 @@ static KvView kv_view(const kv_sketch *s)
     memset(&v, 0, sizeof v);
     v.n_tables = s->n_tables;
     v.bits = s->bits;
+    v.hotf = s->state ? s->state + s->hot_off : nullptr;
+    v.hot_log2 = s->hot_log2;
     for (int t = 0; t < s->n_tables; t++) {
         v.tab[t] = s->flat + s->toff[t];
         v.size[t] = s->sizes[t];
         v.magic[t] = UINT64_MAX / s->sizes[t];
-        v.state[t] = s->state ? s->state + s->soff[t] : nullptr;
+        v.occ[t] = s->state ? s->state + s->soff[t] : nullptr;
     }
     return v;
 }
@@ -257,7 +262,7 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     kv_sketch *s = new kv_sketch();
     memset(s, 0, sizeof *s);
     s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
-    uint64_t off = 0, soff = 0;
+    uint64_t off = 0, soff = 0, buckets = 0;
     for (int t = 0; t < n_tables; t++) {
         if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete s; return kv_fail(KV_EINVAL, "bad table size"); }
         s->sizes[t] = sizes[t];
@@ -265,9 +270,13 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
         s->toff[t] = off;
         off += (s->nbytes[t] + 255) & ~(uint64_t)255;
         s->soff[t] = soff;
-        soff += ((sizes[t] + 15) / 16 + 63) & ~(uint64_t)63;
+        soff += ((sizes[t] + 31) / 32 + 63) & ~(uint64_t)63;
+        buckets += sizes[t];
     }
-    s->state_words = bits == 1 ? 0 : soff;
+    s->hot_log2 = 15;
+    while ((1ull << s->hot_log2) < buckets / 8) s->hot_log2++;
+    s->hot_off = soff;
+    s->state_words = bits == 1 ? 0 : soff + ((1ull << s->hot_log2) / 32);
     s->flat_bytes = off;
     cudaError_t e = cudaMalloc((void **)&s->flat, off);
     if (e != cudaSuccess) {
@@ -406,8 +415,9 @@ static int kv_state_rebuild_locked(KvCtx *ctx, kv_sketch *s)
 {
     if (!s->state) return KV_OK;
     KvView v = kv_view(s);
+    CU(cudaMemsetAsync(s->state, 0, s->state_words * 4, ctx->compute));
     for (int t = 0; t < s->n_tables; t++) {
-        uint64_t n_words = (s->sizes[t] + 15) / 16;
+        uint64_t n_words = (s->sizes[t] + 31) / 32;
         if (s->bits == 8) LAUNCH(ctx, kv_state_rebuild_kernel<8>, kv_grid_for(ctx, n_words), 256, v, t);
         else LAUNCH(ctx, kv_state_rebuild_kernel<4>, kv_grid_for(ctx, n_words), 256, v, t);
     }
@@ -633,18 +643,24 @@ static int kv_first_table(KvCtx *ctx, uint64_t chunk_positions, int n_tables, Kv
     uint64_t need = std::max<uint64_t>(1024, 2 * chunk_positions * (uint64_t)n_tables);
     int lg = 10;
     while ((1ull << lg) < need) lg++;
-    if (lg > ctx->ut_log2) {
+    const int lg_small = std::min(lg, 21);   // 2^21 slots = 16 MB: holds a steady-state chunk at load < 0.5
+    if (lg > ctx->ut_log2 || lg_small > ctx->ut_small_log2) {
         KV_TRY(kv_buf_ensure(ctx->ut, (8ull << lg)));
-        ctx->ut_log2 = lg;
+        KV_TRY(kv_buf_ensure(ctx->ut_small, (8ull << lg_small)));
+        ctx->ut_log2 = std::max(lg, ctx->ut_log2);
+        ctx->ut_small_log2 = std::max(lg_small, ctx->ut_small_log2);
         ctx->ut_epoch = 0;
     }
     if (ctx->ut_epoch == 0 || ctx->ut_epoch == 7) {
         CU(cudaMemsetAsync(ctx->ut.p, 0, 8ull << ctx->ut_log2, ctx->compute));
+        CU(cudaMemsetAsync(ctx->ut_small.p, 0, 8ull << ctx->ut_small_log2, ctx->compute));
         ctx->ut_epoch = 0;
     }
     ctx->ut_epoch++;
-    ft->slots = (unsigned long long *)ctx->ut.p;
-    ft->log2_slots = ctx->ut_log2;
+    ft->small = (unsigned long long *)ctx->ut_small.p;
+    ft->big = (unsigned long long *)ctx->ut.p;
+    ft->log2_small = ctx->ut_small_log2;
+    ft->log2_big = ctx->ut_log2;
     ft->epoch = ctx->ut_epoch;
     return KV_OK;
 }
