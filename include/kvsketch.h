@@ -100,9 +100,9 @@ int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *ksize, int *
  * for every consume since creation; otherwise *n_unique_valid is 0. */
 int kv_sketch_stats(kv_sketch *s, uint64_t *n_occupied, uint64_t *n_unique, int *n_unique_valid);
 
-/* Turn the exact n_unique_kmers bookkeeping on/off (default on; costs one extra probe kernel
- * per 2^20-position chunk and a chunk-sized first-touch hash table shared per device --
- * independent of the sketch size). */
+/* Turn the exact n_unique_kmers bookkeeping on/off (default on; costs two extra passes per
+ * table over each batch and a scratch array of 4 bytes per bucket of the LARGEST table, shared
+ * per device). */
 int kv_sketch_set_unique_tracking(kv_sketch *s, int on);
 
 /* Raw table storage, for collectives that the host runs over it (torch.distributed/NCCL)

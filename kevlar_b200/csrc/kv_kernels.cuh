@@ -99,86 +99,6 @@ __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
     if (threadIdx.x == 0 && s_cnt) atomicAdd(p.n_valid, (unsigned long long)s_cnt);
 }
 
-// ------------------------------------------------------- first-touch table (used by K3 and K5)
-// See the K5 section below for what it is for.
-
-#define KV_UT_IDX_BITS 20
-#define KV_UT_BIN_BITS 38
-#define KV_UT_IDX_MASK ((1ull << KV_UT_IDX_BITS) - 1ull)
-#define KV_UT_KEY_MASK ((1ull << (KV_UT_BIN_BITS + 3)) - 1ull)
-#define KV_UT_MAX_CHUNK (1u << KV_UT_IDX_BITS)
-
-struct KvFirstTable {
-    unsigned long long *small;   // primary table: 2^log2_small slots, at most KV_UT_SMALL_PROBES probes
-    unsigned long long *big;     // overflow table sized for the worst case of one chunk
-    int log2_small, log2_big;
-    unsigned epoch;              // 1..7; 0 marks wiped slots
-};
-#define KV_UT_SMALL_PROBES 16
-
-__device__ __forceinline__ unsigned long long kv_ut_key(int t, uint64_t bin)
-{
-    return ((unsigned long long)t << KV_UT_BIN_BITS) | bin;
-}
-
-__device__ __forceinline__ uint64_t kv_ut_home(unsigned long long key, int log2_slots)
-{
-    return (key * 0x9E3779B97F4A7C15ull) >> (64 - log2_slots);
-}
-
-// try to record `entry` in the slot; 1 = done, 0 = slot belongs to another key
-__device__ __forceinline__ int kv_ut_try(unsigned long long *slotp, unsigned long long entry, unsigned long long key,
-                                         unsigned pos, unsigned epoch)
-{
-    unsigned long long cur = __ldcg(slotp);
-    while ((cur >> 61) != epoch) {   // wiped or left over from an earlier chunk: claim it
-        unsigned long long prev = atomicCAS(slotp, cur, entry);
-        if (prev == cur) return 1;
-        cur = prev;
-    }
-    if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) != key) return 0;
-    if (pos < (unsigned)(cur & KV_UT_IDX_MASK)) atomicMin(slotp, entry);
-    return 1;
-}
-
-// Most chunks have few candidates, so they live in the small (L2-resident) primary table;
-// only when KV_UT_SMALL_PROBES consecutive slots are taken does a key go to the big table.
-// Slots are never released within an epoch, which keeps insert and lookup consistent.
-__device__ __forceinline__ void kv_ut_insert(const KvFirstTable &ft, unsigned long long key, unsigned pos)
-{
-    const unsigned long long entry = ((unsigned long long)ft.epoch << 61) | (key << KV_UT_IDX_BITS) | pos;
-    uint64_t mask = (1ull << ft.log2_small) - 1ull;
-    uint64_t slot = kv_ut_home(key, ft.log2_small);
-    for (int i = 0; i < KV_UT_SMALL_PROBES; i++) {
-        if (kv_ut_try(ft.small + slot, entry, key, pos, ft.epoch)) return;
-        slot = (slot + 1) & mask;
-    }
-    mask = (1ull << ft.log2_big) - 1ull;
-    slot = kv_ut_home(key, ft.log2_big);
-    while (!kv_ut_try(ft.big + slot, entry, key, pos, ft.epoch)) slot = (slot + 1) & mask;
-}
-
-// is `pos` the first position of this chunk that touched (t, bin)?
-__device__ __forceinline__ bool kv_ut_owns(const KvFirstTable &ft, unsigned long long key, unsigned pos)
-{
-    uint64_t mask = (1ull << ft.log2_small) - 1ull;
-    uint64_t slot = kv_ut_home(key, ft.log2_small);
-    for (int i = 0; i < KV_UT_SMALL_PROBES; i++) {
-        unsigned long long cur = __ldcg(ft.small + slot);
-        if ((cur >> 61) != ft.epoch) return false;
-        if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) return (unsigned)(cur & KV_UT_IDX_MASK) == pos;
-        slot = (slot + 1) & mask;
-    }
-    mask = (1ull << ft.log2_big) - 1ull;
-    slot = kv_ut_home(key, ft.log2_big);
-    for (;;) {
-        unsigned long long cur = __ldcg(ft.big + slot);
-        if ((cur >> 61) != ft.epoch) return false;
-        if (((cur >> KV_UT_IDX_BITS) & KV_UT_KEY_MASK) == key) return (unsigned)(cur & KV_UT_IDX_MASK) == pos;
-        slot = (slot + 1) & mask;
-    }
-}
-
 // ----------------------------------------------------------------------- K3
 //
 // Saturating counter update, one thread per base position (grid-stride).  For every valid k-mer
@@ -192,27 +112,22 @@ __device__ __forceinline__ bool kv_ut_owns(const KvFirstTable &ft, unsigned long
 // Every add that actually changed memory is recorded (one bit per position and table), so a
 // dirty chunk can be undone arithmetically -- 32-bit adds commute, whatever transient carries
 // happened -- and redone with the exact path by the two follow-up kernels below, which exit
-// immediately when the flag is clear.  With TRACK, candidates flagged by the probe kernel first
-// settle whether they are the first toucher of one of their buckets (n_unique_kmers).
-template <int BITS, bool TRACK, bool HAS_VALID, bool EXACT>
+// immediately when the flag is clear.
+template <int BITS, bool HAS_VALID, bool EXACT>
 __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
                                                            const uint32_t *__restrict__ valid, uint64_t total,
-                                                           KvFirstTable ft, const uint32_t *__restrict__ cand,
-                                                           unsigned long long *n_unique, uint32_t *__restrict__ added,
-                                                           uint64_t added_stride, unsigned *dirty)
+                                                           uint32_t *__restrict__ added, uint64_t added_stride,
+                                                           unsigned *dirty)
 {
     if (EXACT && *dirty == 0) return;   // redo pass of a clean chunk
     const unsigned maxv = BITS == 8 ? 255u : 15u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
-    unsigned fresh = 0;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
         bool live = g < total;
         if (HAS_VALID && live) live = (__ldg(valid + (g >> 5)) >> (g & 31)) & 1u;
         uint64_t h = 0;
         if (live) h = __ldcs(hashes + g);
-        const bool is_cand = TRACK && live && ((__ldg(cand + (g >> 5)) >> (g & 31)) & 1u);
-        bool is_new = false;
         if (BITS != 1 && !EXACT && v.n_tables == 4) {
             // common shape (kevlar always builds 4 tables): addresses and states for all four
             // tables first, then the four speculative adds back to back (independent L2 round
@@ -227,7 +142,6 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
                 hot[t] = true;
                 if (live) {
                     bin[t] = kv_mod(h, v.size[t], v.magic[t]);
-                    if (TRACK && is_cand && !is_new) is_new = kv_ut_owns(ft, kv_ut_key(t, bin[t]), (unsigned)g);
                     kv_word_addr<BITS>(v, t, bin[t], w[t], sh[t]);
                     hot[t] = kv_maybe_hot(v, t, bin[t]);
                 }
@@ -252,7 +166,6 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
                 unsigned bal = __ballot_sync(0xffffffffu, did[t]);
                 if ((threadIdx.x & 31) == 0) added[t * added_stride + (g >> 5)] = bal;
             }
-            fresh += is_new;
             continue;
         }
 #pragma unroll 4
@@ -260,7 +173,6 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
             bool did = false;
             if (live) {
                 const uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
-                if (TRACK && is_cand && !is_new) is_new = kv_ut_owns(ft, kv_ut_key(t, bin), (unsigned)g);
                 unsigned *w, sh;
                 kv_word_addr<BITS>(v, t, bin, w, sh);
                 if (BITS == 1) {
@@ -283,11 +195,6 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
                 if ((threadIdx.x & 31) == 0) added[t * added_stride + (g >> 5)] = bal;
             }
         }
-        fresh += is_new;
-    }
-    if (TRACK) {
-        fresh = __reduce_add_sync(0xffffffffu, fresh);
-        if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(n_unique, (unsigned long long)fresh);
     }
 }
 
@@ -363,46 +270,55 @@ __global__ void kv_expand_bits_kernel(const uint32_t *__restrict__ valid, uint64
 // ----------------------------------------------------------------------- K5
 //
 // khmer's n_unique_kmers counts the add() calls that found at least one of their T buckets
-// empty, in single-threaded file order.  Exact parallel equivalent: reads are
-// applied in chunks of at most 2^20 base positions, chunks in stream order, so "empty at chunk
-// start" is the sequential state; inside a chunk occurrence g is "new" iff, for some table t,
-// g is the SMALLEST position of the chunk that touches its (then empty) bucket (t, bin).
-//   probe   : every valid occurrence that sees an empty bucket records
-//             first[(t, bin)] = min(first[(t, bin)], g) and is flagged as a candidate;
-//   resolve : (fused into the increment kernel) a candidate is new iff first[(t, bin)] == g
-//             for one of its buckets.
-// first[] is NOT an array over all buckets (that costs 4 B per bucket and made this the most
-// expensive part of counting): it is a small open-addressing hash table keyed by (t, bin),
-// sized for one chunk and therefore independent of the sketch size and L2-friendly.  Entries
-// are stamped with a 3-bit chunk epoch, so the table is wiped once every 7 chunks instead of
-// after each one:   [ epoch:3 | t:3 | bin:38 | position:20 ]   (u64, ordered by position for
-// equal epoch+key, so atomicMin keeps the smallest position).
+// empty, in single-threaded file order.  That number depends only on the
+// stream of hashes and on which buckets were empty when the batch started -- not on the
+// counter values -- so it is computed per batch, BEFORE the batch's increments, table by table:
+//   occurrence g is new  <=>  for some table t its bucket was empty at batch start (occ bit
+//                             clear) and g is the smallest position of the batch touching it.
+// pass A (per table): first[bin] = min(first[bin], g) for every valid g whose bucket is empty;
+// pass B (per table): g is flagged if first[bin_t(g)] == g;   finally popcount of the flags.
+// first[] is ONE u32 array as long as the largest table, reused for each table in turn, so the
+// random atomics of a pass stay inside a (for the benchmark config L2-resident) 4-bytes-per-
+// bucket region instead of spreading over all tables at once.
+__global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint32_t *__restrict__ first,
+                                                           const uint64_t *__restrict__ hashes,
+                                                           const uint32_t *__restrict__ valid, uint64_t total)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t size = v.size[t], magic = v.magic[t];
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
+        const uint64_t bin = kv_mod(__ldcs(hashes + g), size, magic);
+        if (kv_bucket_empty(v, t, bin)) atomicMin(first + bin, (uint32_t)g);
+    }
+}
 
-// valid == NULL means every position holds a hash (kv_add_hashes)
-__global__ void __launch_bounds__(256) kv_unique_probe_kernel(KvView v, KvFirstTable ft, const uint64_t *__restrict__ hashes,
-                                                              const uint32_t *__restrict__ valid, uint32_t *__restrict__ cand,
-                                                              uint64_t total)
+__global__ void __launch_bounds__(256) kv_first_resolve_kernel(KvView v, int t, const uint32_t *__restrict__ first,
+                                                               const uint64_t *__restrict__ hashes,
+                                                               const uint32_t *__restrict__ valid, uint64_t total,
+                                                               uint32_t *__restrict__ fresh)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
+    const uint64_t size = v.size[t], magic = v.magic[t];
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        bool is_cand = false;
+        bool mine = false;
         if (g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u))) {
-            const uint64_t h = hashes[g];
-            uint64_t bin[KV_TABLES_DEV];
-            unsigned empty = 0;
-#pragma unroll 4
-            for (int t = 0; t < v.n_tables; t++) {
-                bin[t] = kv_mod(h, v.size[t], v.magic[t]);
-                if (kv_bucket_empty(v, t, bin[t])) empty |= 1u << t;
-            }
-            is_cand = empty != 0;
-            for (int t = 0; t < v.n_tables; t++)
-                if ((empty >> t) & 1u) kv_ut_insert(ft, kv_ut_key(t, bin[t]), (unsigned)g);
+            const uint64_t bin = kv_mod(__ldcs(hashes + g), size, magic);
+            mine = kv_bucket_empty(v, t, bin) && __ldcg(first + bin) == (uint32_t)g;
         }
-        unsigned bal = __ballot_sync(0xffffffffu, is_cand);
-        if ((threadIdx.x & 31) == 0) cand[g >> 5] = bal;
+        unsigned bal = __ballot_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && bal) fresh[g >> 5] |= bal;   // passes run one after another: no race
     }
+}
+
+__global__ void kv_popcount_kernel(const uint32_t *__restrict__ words, uint64_t n_words, unsigned long long *out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) mine += __popc(words[i]);
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
 }
 
 // khmer _occupied_bins: non-zero buckets of table 0

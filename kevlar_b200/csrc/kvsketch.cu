@@ -70,12 +70,9 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, cand, scratch8, hits, flags, discard, misc, ut, ut_small, added;
-    int ut_small_log2 = 0;
+    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added;
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
-    int ut_log2 = 0;          // first-touch table: 2^ut_log2 slots
-    unsigned ut_epoch = 0;    // 1..7, 0 = freshly wiped
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
     unsigned long long *h_counters = nullptr; // pinned mirror
     uint64_t launches = 0;
@@ -300,8 +297,6 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
     s->track_unique = true;
     s->unique_valid = true;
-    for (int t = 0; t < n_tables; t++)
-        if (sizes[t] >= (1ull << KV_UT_BIN_BITS)) s->track_unique = s->unique_valid = false;   // key field is 38 bits
     *out = s;
     return KV_OK;
 }
@@ -358,10 +353,6 @@ extern "C" int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *k
 extern "C" int kv_sketch_set_unique_tracking(kv_sketch *s, int on)
 {
     if (!s) return kv_fail(KV_EINVAL, "null sketch");
-    if (on)
-        for (int t = 0; t < s->n_tables; t++)
-            if (s->sizes[t] >= (1ull << KV_UT_BIN_BITS))
-                return kv_fail(KV_EINVAL, "exact n_unique tracking supports tables below 2^%d buckets", KV_UT_BIN_BITS);
     s->track_unique = on != 0;
     return KV_OK;
 }
@@ -635,39 +626,8 @@ static int kv_band_interval(int num_bands, int band, uint64_t *lo, uint64_t *hi)
     return KV_OK;
 }
 
-// First-touch table for the exact n_unique_kmers bookkeeping: sized for one chunk (every
-// position may insert up to n_tables keys; load factor <= 0.5), shared by all sketches of the
-// device, wiped every 7 chunks (3-bit epoch stamps).
-static int kv_first_table(KvCtx *ctx, uint64_t chunk_positions, int n_tables, KvFirstTable *ft)
-{
-    uint64_t need = std::max<uint64_t>(1024, 2 * chunk_positions * (uint64_t)n_tables);
-    int lg = 10;
-    while ((1ull << lg) < need) lg++;
-    const int lg_small = std::min(lg, 21);   // 2^21 slots = 16 MB: holds a steady-state chunk at load < 0.5
-    if (lg > ctx->ut_log2 || lg_small > ctx->ut_small_log2) {
-        KV_TRY(kv_buf_ensure(ctx->ut, (8ull << lg)));
-        KV_TRY(kv_buf_ensure(ctx->ut_small, (8ull << lg_small)));
-        ctx->ut_log2 = std::max(lg, ctx->ut_log2);
-        ctx->ut_small_log2 = std::max(lg_small, ctx->ut_small_log2);
-        ctx->ut_epoch = 0;
-    }
-    if (ctx->ut_epoch == 0 || ctx->ut_epoch == 7) {
-        CU(cudaMemsetAsync(ctx->ut.p, 0, 8ull << ctx->ut_log2, ctx->compute));
-        CU(cudaMemsetAsync(ctx->ut_small.p, 0, 8ull << ctx->ut_small_log2, ctx->compute));
-        ctx->ut_epoch = 0;
-    }
-    ctx->ut_epoch++;
-    ft->small = (unsigned long long *)ctx->ut_small.p;
-    ft->big = (unsigned long long *)ctx->ut.p;
-    ft->log2_small = ctx->ut_small_log2;
-    ft->log2_big = ctx->ut_log2;
-    ft->epoch = ctx->ut_epoch;
-    return KV_OK;
-}
-
 template <int BITS>
-static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n,
-                               bool track, const KvFirstTable &ft, const uint32_t *cand, unsigned long long *d_unique)
+static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n)
 {
     unsigned grid = kv_grid_for(ctx, n);
     const uint64_t stride = (n + 31) / 32 + 1;
@@ -682,45 +642,51 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, const uint64_t *d_ha
         }
         dirty = ctx->dirty + ctx->dirty_next++;
     }
-#define KV_INC_X(TRACK_, VALID_, EXACT_)                                                                             \
-    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_increment_kernel<BITS, TRACK_, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, \
-             ft, cand, d_unique, added, stride, dirty)
-#define KV_INC(TRACK_, VALID_, EXACT_)                                                                               \
-    LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_increment_kernel<BITS, TRACK_, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, \
-             ft, cand, d_unique, added, stride, dirty)
-    if (track) { if (d_valid) KV_INC(true, true, false); else KV_INC(true, false, false); }
-    else { if (d_valid) KV_INC(false, true, false); else KV_INC(false, false, false); }
+#define KV_INC(CLS_, VALID_, EXACT_)                                                                              \
+    LAUNCH_C(CLS_, ctx, (kv_increment_kernel<BITS, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, added, stride, dirty)
+    if (d_valid) KV_INC(KV_PROF_INCREMENT, true, false); else KV_INC(KV_PROF_INCREMENT, false, false);
     if (BITS != 1) {
         // fix-up pair: both exit at once unless the speculative pass saw a counter overflow
         LAUNCH_C(KV_PROF_FIXUP, ctx, kv_rollback_kernel<BITS>, grid, 256, v, d_hashes, n, added, stride, dirty);
-        if (d_valid) KV_INC_X(false, true, true); else KV_INC_X(false, false, true);
+        if (d_valid) KV_INC(KV_PROF_FIXUP, true, true); else KV_INC(KV_PROF_FIXUP, false, true);
     }
 #undef KV_INC
-#undef KV_INC_X
     return KV_OK;
 }
 
-// apply one chunk of hashes (device; n <= KV_UT_MAX_CHUNK when tracking) to the sketch:
-// optional exact-unique probe, then the (fused resolve +) saturating increments
+// exact n_unique_kmers contribution of one chunk (must run before the chunk's increments)
+static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid,
+                          uint64_t n)
+{
+    uint64_t maxsize = 0;
+    for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
+    KV_TRY(kv_buf_ensure(ctx->first, maxsize * 4));
+    const uint64_t n_words = (n + 31) / 32;
+    KV_TRY(kv_buf_ensure(ctx->fresh, n_words * 4));
+    CU(cudaMemsetAsync(ctx->fresh.p, 0, n_words * 4, ctx->compute));
+    unsigned grid = kv_grid_for(ctx, n);
+    for (int t = 0; t < s->n_tables; t++) {
+        CU(cudaMemsetAsync(ctx->first.p, 0xff, s->sizes[t] * 4, ctx->compute));
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n);
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, grid, 256, v, t, (const uint32_t *)ctx->first.p, d_hashes,
+                 d_valid, n, (uint32_t *)ctx->fresh.p);
+    }
+    LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_popcount_kernel, kv_grid_for(ctx, n_words), 256, (const uint32_t *)ctx->fresh.p, n_words,
+             s->d_unique);
+    return KV_OK;
+}
+
+// apply one chunk of hashes (device, n < 2^32) to the sketch: exact-unique bookkeeping first
+// (it must see the buckets as they were before this chunk), then the saturating increments
 static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n)
 {
     if (!n) return KV_OK;
     KvView v = kv_view(s);
-    KvFirstTable ft;
-    memset(&ft, 0, sizeof ft);
-    uint32_t *cand = nullptr;
-    const bool track = s->track_unique;
-    if (track) {
-        if (n > KV_UT_MAX_CHUNK) return kv_fail(KV_EINVAL, "internal: tracked chunk too large");
-        KV_TRY(kv_first_table(ctx, n, s->n_tables, &ft));
-        KV_TRY(kv_buf_ensure(ctx->cand, ((n + 31) / 32 + 1) * 4));
-        cand = (uint32_t *)ctx->cand.p;
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_unique_probe_kernel, kv_grid_for(ctx, n), 256, v, ft, d_hashes, d_valid, cand, n);
-    } else
-        s->unique_valid = false;
-    if (s->bits == 8) return kv_launch_increment<8>(ctx, v, d_hashes, d_valid, n, track, ft, cand, s->d_unique);
-    if (s->bits == 4) return kv_launch_increment<4>(ctx, v, d_hashes, d_valid, n, track, ft, cand, s->d_unique);
-    return kv_launch_increment<1>(ctx, v, d_hashes, d_valid, n, track, ft, cand, s->d_unique);
+    if (s->track_unique) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n));
+    else s->unique_valid = false;
+    if (s->bits == 8) return kv_launch_increment<8>(ctx, v, d_hashes, d_valid, n);
+    if (s->bits == 4) return kv_launch_increment<4>(ctx, v, d_hashes, d_valid, n);
+    return kv_launch_increment<1>(ctx, v, d_hashes, d_valid, n);
 }
 
 static int kv_check_mask(const kv_sketch *s, const kv_sketch *mask)
@@ -752,10 +718,8 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
     if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
 
-    // with exact n_unique tracking the chunk is what bounds the first-touch table (2^20 positions)
-    const uint64_t chunk_limit = s->track_unique ? std::min<uint64_t>(ctx->chunk_bases, KV_UT_MAX_CHUNK) : ctx->chunk_bases;
-    const uint64_t chunk_tiles = chunk_limit / KV_TILE;
-    const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
+    const uint64_t chunk_tiles = ctx->chunk_bases / KV_TILE;
+    const uint64_t chunk_pos = std::min<uint64_t>(ctx->chunk_bases, b.n_tiles * KV_TILE);
     KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
     KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
     for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
@@ -963,9 +927,7 @@ extern "C" int kv_add_hashes(kv_sketch *s, const uint64_t *hashes, uint64_t n)
     CU(cudaSetDevice(s->device));
     KV_TRY(kv_buf_ensure(ctx->misc, n * 8));
     CU(cudaMemcpyAsync(ctx->misc.p, hashes, n * 8, cudaMemcpyHostToDevice, ctx->compute));
-    const uint64_t step = s->track_unique ? KV_UT_MAX_CHUNK : n;
-    for (uint64_t o = 0; o < n; o += step)
-        KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p + o, nullptr, std::min(step, n - o)));
+    KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p, nullptr, n));
     CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }
