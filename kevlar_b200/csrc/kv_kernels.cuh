@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) kv_first_resolve_kernel(KvView v, int t, 
         bool mine = false;
         if (g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u))) {
             const uint64_t bin = kv_mod(__ldcs(hashes + g), size, magic);
-            mine = kv_bucket_empty(v, t, bin) && __ldcg(first + bin) == (uint32_t)g;
+            mine = __ldcg(first + bin) == (uint32_t)g;   // buckets that were occupied never got an entry
         }
         unsigned bal = __ballot_sync(0xffffffffu, mine);
         if ((threadIdx.x & 31) == 0 && bal) fresh[g >> 5] |= bal;   // passes run one after another: no race
