@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--hasher', default='murmur', choices=['murmur', 'twobit'],
                     help='murmur = Counttable (what `kevlar count` builds); twobit = Countgraph')
-    ap.add_argument('--merge', default='allreduce', choices=['allreduce', 'allgather', 'p2p'])
+    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p'])
     ap.add_argument('--reads-per-sample', type=int, default=READS_PER_SAMPLE)
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -211,8 +211,7 @@ class GpuTrio(object):
                 sk.consume_batch(b.numpy(), o.numpy().view(np.uint64), wait=False)
         if self.world > 1:
             self.lib.sync(self.device)
-            for sk in self.sketches:
-                self.multigpu.merge_sketch(sk, how=self.args.merge)
+            self.multigpu.merge_sketches(self.sketches, how=self.args.merge)
         if resident:
             b, o = self.dev[0]
             hits, flags, _ = khmer.novel_batch(self.sketches[:1], self.sketches[1:], b.data_ptr(),

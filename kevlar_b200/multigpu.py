@@ -137,57 +137,87 @@ def slice_bounds(nbytes, rank, world, align=256):
     return lo * align, hi * align
 
 
-def merge_p2p(sketch, group=None):
-    """Peer-to-peer merge with no NCCL on the data path.  Ranks exchange CUDA IPC handles of
-    their table storage; then
-      phase 1 (reduce-scatter): rank r folds bytes slice(r) of every peer's table into its own
-               table with one kernel of NVLink loads (kv_sketch_merge_peers) -- peers only ever
-               write their OWN slice, so nobody reads bytes that are being written;
-      phase 2 (all-gather): rank r pulls the finished slice(p) from every peer p.
-    Barriers separate the phases."""
+_P2P_PEERS = {}   # sketch handle -> {rank: mapped device pointer of that rank's table storage}
+
+
+def _p2p_peers(sketch, group=None):
+    """Map the peers' table storage once per sketch (CUDA IPC open is slow: ~ms) and reuse it."""
+    key = sketch._h.value
+    if key in _P2P_PEERS:
+        return _P2P_PEERS[key]
     td = dist()
     world, rank = td.get_world_size(group), td.get_rank(group)
     handle = (ctypes.c_uint8 * 64)()
     check(lib().kv_sketch_ipc_export(sketch._h, handle))
     handles = [None] * world
     td.all_gather_object(handles, bytes(handle), group=group)
-    _, nbytes = sketch.flat_device_buffer()
     peers = {}
     for r, h in enumerate(handles):
         if r != rank:
             ptr = c_void_p()
             check(lib().kv_ipc_open(sketch.device, (ctypes.c_uint8 * 64)(*h), byref(ptr)))
             peers[r] = ptr
-    _lib.sync(sketch.device)
-    td.barrier(group=group)                           # every partial table is complete and mapped
-    lo, hi = slice_bounds(nbytes, rank, world)
-    order = [peers[r] for r in sorted(peers)]
-    for i in range(0, len(order), 8):
-        grp = order[i:i + 8]
-        ptrs = (c_void_p * len(grp))(*[p.value for p in grp])
-        check(lib().kv_sketch_merge_peers(sketch._h, ptrs, len(grp), lo, hi))
+    _P2P_PEERS[key] = peers
+    return peers
+
+
+def release_p2p(sketch):
+    """Unmap the peers' storage of a sketch (call on every rank before the sketches are freed)."""
+    peers = _P2P_PEERS.pop(sketch._h.value, None)
+    if peers:
+        for ptr in peers.values():
+            check(lib().kv_ipc_close(sketch.device, ptr))
+
+
+def merge_p2p(sketches, group=None):
+    """Peer-to-peer merge with no NCCL on the data path.  Ranks exchange CUDA IPC handles of
+    their table storage once; then, for all sketches together,
+      phase 1 (reduce-scatter): rank r folds bytes slice(r) of every peer's table into its own
+               table with one kernel of NVLink loads (kv_sketch_merge_peers) -- peers only ever
+               write their OWN slice, so nobody reads bytes that are being written;
+      phase 2 (all-gather): rank r pulls the finished slice(p) from every peer p.
+    Barriers separate the phases."""
+    td = dist()
+    if not isinstance(sketches, (list, tuple)):
+        sketches = [sketches]
+    world, rank = td.get_world_size(group), td.get_rank(group)
+    peers = [_p2p_peers(sk, group) for sk in sketches]
+    _lib.sync(sketches[0].device)
+    td.barrier(group=group)                           # every partial table is complete
+    for sk, pr in zip(sketches, peers):
+        _, nbytes = sk.flat_device_buffer()
+        lo, hi = slice_bounds(nbytes, rank, world)
+        order = [pr[r] for r in sorted(pr)]
+        for i in range(0, len(order), 8):
+            grp = order[i:i + 8]
+            ptrs = (c_void_p * len(grp))(*[p.value for p in grp])
+            check(lib().kv_sketch_merge_peers(sk._h, ptrs, len(grp), lo, hi))
     td.barrier(group=group)                           # every slice is reduced
-    for r in sorted(peers):
-        plo, phi = slice_bounds(nbytes, r, world)
-        check(lib().kv_sketch_copy_from_peer(sketch._h, peers[r], plo, phi))
+    for sk, pr in zip(sketches, peers):
+        _, nbytes = sk.flat_device_buffer()
+        for r in sorted(pr):
+            plo, phi = slice_bounds(nbytes, r, world)
+            check(lib().kv_sketch_copy_from_peer(sk._h, pr[r], plo, phi))
     td.barrier(group=group)                           # nobody still reads my table
-    for ptr in peers.values():
-        check(lib().kv_ipc_close(sketch.device, ptr))
 
 
-def merge_sketch(sketch, how='allreduce', group=None):
-    """Combine per-rank partial sketches in place; afterwards every rank holds the full sketch."""
+def merge_sketches(sketches, how='p2p', group=None):
+    """Combine per-rank partial sketches in place; afterwards every rank holds the full sketches."""
     td = dist()
     if not td.is_initialized() or td.get_world_size(group) == 1:
-        return sketch
+        return sketches
     if how == 'p2p':
-        merge_p2p(sketch, group)
-    elif how == 'allgather':
-        merge_allgather(GpuSketchAdapter(sketch), group)
-    elif how == 'allreduce':
-        merge_allreduce(GpuSketchAdapter(sketch), group)
+        merge_p2p(sketches, group)
+    elif how in ('allgather', 'allreduce'):
+        for sketch in sketches:
+            (merge_allgather if how == 'allgather' else merge_allreduce)(GpuSketchAdapter(sketch), group)
     else:
         raise ValueError('unknown merge strategy ' + how)
+    return sketches
+
+
+def merge_sketch(sketch, how='p2p', group=None):
+    merge_sketches([sketch], how=how, group=group)
     return sketch
 
 

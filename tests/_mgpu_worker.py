@@ -67,6 +67,8 @@ def main():
                     (allhits['abund'][:, :3] == ohits['abund'][:, :3]).all()
                 if not same or len(ohits) == 0:
                     failures.append('{} {} novel hits differ ({} vs {})'.format(how, cls, len(allhits), len(ohits)))
+            for g in gpu:
+                multigpu.release_p2p(g)
             del gpu
     torch.distributed.barrier()
     if failures:
