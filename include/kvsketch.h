@@ -191,8 +191,9 @@ int kv_sync(int device);
  * enable: 1 = start (and reset), 0 = stop (and reset), 2 = read only.  ms_out / n_out receive
  * KV_PROF_CLASSES totals accumulated since the last reset: milliseconds and launch counts for
  * [0] other, [1] hash, [2] increment, [3] unique-tracking probe, [4] novel, [5] merge,
- * [6] overflow fix-up (rollback + exact redo; normally two empty launches per chunk). */
-#define KV_PROF_CLASSES 7
+ * [6] overflow fix-up (rollback + exact redo; normally two empty launches per chunk),
+ * [7] region partitioning of the updates (large sketches: hist + scan + scatter). */
+#define KV_PROF_CLASSES 8
 int kv_profile(int device, int enable, double *ms_out, uint64_t *n_out);
 
 /* Number of kernels this library has launched on `device` since load (bench accounting). */

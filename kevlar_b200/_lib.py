@@ -151,7 +151,7 @@ def launch_count(device=None):
     return n.value
 
 
-PROF_CLASSES = ('other', 'hash', 'increment', 'unique', 'novel', 'merge', 'fixup')
+PROF_CLASSES = ('other', 'hash', 'increment', 'unique', 'novel', 'merge', 'fixup', 'partition')
 
 
 def profile(enable, device=None):

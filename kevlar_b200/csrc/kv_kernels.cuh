@@ -267,6 +267,152 @@ __global__ void kv_expand_bits_kernel(const uint32_t *__restrict__ valid, uint64
         out[i] = (valid[i >> 5] >> (i & 31)) & 1u;
 }
 
+// ------------------------------------------------------------- K3b: region-partitioned updates
+//
+// For sketches larger than L2 every counter update is a random DRAM sector read-modify-write
+// that also misses the TLB (2 MB pages, 256 MB reach): 13-20 G updates/s however the update is
+// written (profiles/r01_notes.md).  The partitioned path turns a chunk's updates into streams:
+//   hist     count the chunk's (table, region) pairs            region = 2^rb buckets of one table
+//   scan     exclusive prefix -> where each (table, region) run starts in the item array
+//   scatter  write every update as a 32-bit bucket index into its run.  A CTA first counts its
+//            tile in shared memory, then reserves room in each run with ONE global atomic per
+//            (CTA, run), so its items land next to each other and L2 merges them into full sectors
+//   apply    walk the item array front to back: at any moment all CTAs work inside the same
+//            16 MB region, which therefore stays L2- and TLB-resident while it is hit; same
+//            speculative / exact update logic, rollback and redo as the direct kernel.
+
+#define KV_PART_TILE 512        // positions per CTA tile in hist/scatter (2 per thread)
+#define KV_PART_MAX 4096        // (table, region) runs
+
+struct KvPartInfo {
+    int rb;                        // log2(buckets per region)
+    uint32_t pbase[KV_TABLES_DEV + 1];   // first run of table t; pbase[n_tables] = number of runs
+};
+
+// meta[0] = number of items, meta[1 + t] = index of the first item of table t (t <= n_tables)
+__global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
+                                                           const uint32_t *__restrict__ valid, uint64_t total,
+                                                           uint32_t *__restrict__ hist)
+{
+    extern __shared__ uint32_t sm_hist[];
+    const int P = (int)pi.pbase[v.n_tables];
+    for (int q = threadIdx.x; q < P; q += blockDim.x) sm_hist[q] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
+        const uint64_t h = __ldcs(hashes + g);
+        for (int t = 0; t < v.n_tables; t++)
+            atomicAdd(&sm_hist[pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb)], 1u);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < P; q += blockDim.x)
+        if (sm_hist[q]) atomicAdd(hist + q, sm_hist[q]);
+}
+
+__global__ void kv_part_scan_kernel(KvPartInfo pi, int n_tables, const uint32_t *__restrict__ hist,
+                                    uint32_t *__restrict__ cursor, uint32_t *__restrict__ meta)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const int P = (int)pi.pbase[n_tables];
+    uint32_t run = 0;
+    int t = 0;
+    for (int q = 0; q < P; q++) {
+        while (t <= n_tables && (uint32_t)q == pi.pbase[t]) meta[1 + t++] = run;
+        cursor[q] = run;
+        run += hist[q];
+    }
+    while (t <= n_tables) meta[1 + t++] = run;
+    meta[0] = run;
+}
+
+__global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
+                                                              const uint32_t *__restrict__ valid, uint64_t total,
+                                                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ items)
+{
+    extern __shared__ uint32_t sm_part[];
+    const int P = (int)pi.pbase[v.n_tables];
+    uint32_t *cnt = sm_part, *base = sm_part + P;
+    const uint64_t n_tiles = (total + KV_PART_TILE - 1) / KV_PART_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int q = threadIdx.x; q < P; q += blockDim.x) cnt[q] = 0;
+        __syncthreads();
+        uint32_t bin[2][4], run[2][4], rank[2][4];
+        bool live[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint64_t g = tile * KV_PART_TILE + j * 256 + threadIdx.x;
+            live[j] = g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
+            if (live[j]) {
+                const uint64_t h = __ldcs(hashes + g);
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (t < v.n_tables) {
+                        bin[j][t] = (uint32_t)kv_mod(h, v.size[t], v.magic[t]);
+                        run[j][t] = pi.pbase[t] + (bin[j][t] >> pi.rb);
+                        rank[j][t] = atomicAdd(&cnt[run[j][t]], 1u);
+                    }
+            }
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < P; q += blockDim.x) {
+            uint32_t c = cnt[q];
+            base[q] = c ? atomicAdd(cursor + q, c) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+            if (live[j]) {
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (t < v.n_tables) items[base[run[j][t]] + rank[j][t]] = bin[j][t];
+            }
+        __syncthreads();
+    }
+}
+
+// Apply / undo / redo over the item array.  MODE 0: speculative update, records `added`;
+// MODE 1: rollback of a dirty chunk; MODE 2: exact redo of a dirty chunk.
+template <int BITS, int MODE>
+__global__ void __launch_bounds__(256) kv_part_apply_kernel(KvView v, const uint32_t *__restrict__ items,
+                                                            const uint32_t *__restrict__ meta, uint32_t *__restrict__ added,
+                                                            unsigned *dirty)
+{
+    if (MODE != 0 && *dirty == 0) return;
+    const unsigned maxv = BITS == 8 ? 255u : 15u;
+    const uint64_t n = meta[0];
+    const uint64_t n_pad = (n + 31) & ~(uint64_t)31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool did = false;
+        if (i < n) {
+            int t = 0;
+            while (t + 1 < v.n_tables && i >= meta[2 + t]) t++;
+            const uint64_t bin = __ldcs(items + i);
+            unsigned *w, sh;
+            kv_word_addr<BITS>(v, t, bin, w, sh);
+            if (MODE == 1) {
+                if ((added[i >> 5] >> (i & 31)) & 1u) atomicAdd(w, 0u - (1u << sh));
+            } else {
+                unsigned ob;
+                if (MODE == 2 || kv_maybe_hot(v, t, bin)) {
+                    did = kv_sat_inc_exact<BITS>(w, sh, ob);
+                    if (did) kv_state_publish<BITS>(v, t, bin, ob);
+                } else {
+                    ob = (atomicAdd(w, 1u << sh) >> sh) & maxv;
+                    did = true;
+                    if (ob == maxv) atomicOr(dirty, 1u);
+                    else kv_state_publish<BITS>(v, t, bin, ob);
+                }
+            }
+        }
+        if (MODE == 0) {
+            unsigned bal = __ballot_sync(0xffffffffu, did);
+            if ((threadIdx.x & 31) == 0) added[i >> 5] = bal;
+        }
+    }
+}
+
 // ----------------------------------------------------------------------- K5
 //
 // khmer's n_unique_kmers counts the add() calls that found at least one of their T buckets

@@ -50,7 +50,7 @@ extern "C" int kv_abi_version(void) { return KV_ABI_VERSION; }
 // ------------------------------------------------------------------ context
 
 enum { KV_PROF_OTHER = 0, KV_PROF_HASH = 1, KV_PROF_INCREMENT = 2, KV_PROF_UNIQUE = 3, KV_PROF_NOVEL = 4,
-       KV_PROF_MERGE = 5, KV_PROF_FIXUP = 6 };   // KV_PROF_CLASSES (= 7) comes from kvsketch.h
+       KV_PROF_MERGE = 5, KV_PROF_FIXUP = 6, KV_PROF_PARTITION = 7 };   // KV_PROF_CLASSES (= 8) comes from kvsketch.h
 
 struct KvBuf {
     void *p = nullptr;
@@ -70,7 +70,9 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added;
+    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small;
+    uint64_t part_min_bytes = 128ull << 20;   // sketches at least this large take the region-partitioned update path
+    int part_region_log2 = 24;                // buckets per region (8-bit: 16 MB)
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
@@ -136,6 +138,8 @@ static int kv_ctx_get(int device, KvCtx **out)
             if (v >= KV_TILE) c.chunk_bases = v;
         }
         c.chunk_bases = (c.chunk_bases + KV_TILE - 1) / KV_TILE * KV_TILE;
+        if (const char *env = getenv("KV_PART_MIN_BYTES")) c.part_min_bytes = strtoull(env, nullptr, 10);
+        if (const char *env = getenv("KV_PART_REGION_LOG2")) c.part_region_log2 = std::max(4, std::min(30, atoi(env)));
         c.ready = true;
     }
     *out = &c;
@@ -695,6 +699,54 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, uint64_t flat_bytes,
     return KV_OK;
 }
 
+// Region-partitioned update of one chunk (K3b): hist -> scan -> scatter -> apply (+ fix-up pair).
+template <int BITS>
+static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &pi, const uint64_t *d_hashes,
+                                 const uint32_t *d_valid, uint64_t n)
+{
+    const int P = (int)pi.pbase[v.n_tables];
+    const uint64_t max_items = n * (uint64_t)v.n_tables;
+    if (max_items >= 0xffffffffull) return kv_fail(KV_EINVAL, "internal: partitioned chunk too large");
+    KV_TRY(kv_buf_ensure(ctx->part_items, max_items * 4));
+    KV_TRY(kv_buf_ensure(ctx->part_small, (2 * (size_t)P + 16) * 4));
+    KV_TRY(kv_buf_ensure(ctx->added, (max_items / 32 + 2) * 4));
+    uint32_t *hist = (uint32_t *)ctx->part_small.p, *cursor = hist + P, *meta = cursor + P;
+    uint32_t *items = (uint32_t *)ctx->part_items.p, *added = (uint32_t *)ctx->added.p;
+    if (ctx->dirty_next == 64) {
+        CU(cudaMemsetAsync(ctx->dirty, 0, 64 * sizeof(unsigned), ctx->compute));
+        ctx->dirty_next = 0;
+    }
+    unsigned *dirty = ctx->dirty + ctx->dirty_next++;
+    CU(cudaMemsetAsync(hist, 0, (size_t)P * 4, ctx->compute));
+    const unsigned grid = kv_grid_for(ctx, n);
+    {
+        auto kfn = kv_part_hist_kernel;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->compute); }
+        kfn<<<grid, 256, (size_t)P * 4, ctx->compute>>>(v, pi, d_hashes, d_valid, n, hist);
+        if (ctx->profiling) { cudaEventRecord(e1, ctx->compute); ctx->prof_events.push_back({KV_PROF_PARTITION, {e0, e1}}); }
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_scan_kernel, 1, 32, pi, v.n_tables, hist, cursor, meta);
+    {
+        auto kfn = kv_part_scatter_kernel;
+        const uint64_t n_tiles = (n + KV_PART_TILE - 1) / KV_PART_TILE;
+        const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 8));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->compute); }
+        kfn<<<sgrid, 256, (size_t)P * 8, ctx->compute>>>(v, pi, d_hashes, d_valid, n, cursor, items);
+        if (ctx->profiling) { cudaEventRecord(e1, ctx->compute); ctx->prof_events.push_back({KV_PROF_PARTITION, {e0, e1}}); }
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    const unsigned agrid = kv_grid_for(ctx, max_items);
+    LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_part_apply_kernel<BITS, 0>), agrid, 256, v, items, meta, added, dirty);
+    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 1>), agrid, 256, v, items, meta, added, dirty);
+    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 2>), agrid, 256, v, items, meta, added, dirty);
+    return KV_OK;
+}
+
 // exact n_unique_kmers contribution of one chunk (must run before the chunk's increments)
 static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid,
                           uint64_t n)
@@ -727,6 +779,25 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
     KvView v = kv_view(s);
     if (s->track_unique) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n));
     else s->unique_valid = false;
+    // large counter sketches: region-partitioned updates (tables must index with 32 bits, <= 4 tables)
+    bool partitioned = s->bits != 1 && s->flat_bytes >= ctx->part_min_bytes && s->n_tables <= 4;
+    KvPartInfo pi;
+    memset(&pi, 0, sizeof pi);
+    if (partitioned) {
+        pi.rb = ctx->part_region_log2 + (s->bits == 4 ? 1 : 0);
+        uint64_t runs = 0;
+        for (int t = 0; t < s->n_tables && partitioned; t++) {
+            if (s->sizes[t] >= 0xffffffffull) partitioned = false;
+            pi.pbase[t] = (uint32_t)runs;
+            runs += ((s->sizes[t] - 1) >> pi.rb) + 1;
+        }
+        pi.pbase[s->n_tables] = (uint32_t)runs;
+        if (runs > KV_PART_MAX) partitioned = false;
+    }
+    if (partitioned) {
+        if (s->bits == 8) return kv_launch_partitioned<8>(ctx, v, pi, d_hashes, d_valid, n);
+        return kv_launch_partitioned<4>(ctx, v, pi, d_hashes, d_valid, n);
+    }
     if (s->bits == 8) return kv_launch_increment<8>(ctx, v, s->flat_bytes, d_hashes, d_valid, n);
     if (s->bits == 4) return kv_launch_increment<4>(ctx, v, s->flat_bytes, d_hashes, d_valid, n);
     return kv_launch_increment<1>(ctx, v, s->flat_bytes, d_hashes, d_valid, n);
