@@ -18,8 +18,8 @@ struct KvView {
     uint64_t size[KV_TABLES_DEV];  // buckets per table (the primes)
     uint64_t magic[KV_TABLES_DEV]; // floor((2^64-1)/size) for the Barrett reduction below
     uint32_t *occ[KV_TABLES_DEV];  // 1 bit per bucket: counter != 0 (8/4-bit sketches; NULL for bit tables)
-    uint32_t *hotf;                // "maybe hot" filter shared by all tables: 2^hot_log2 bits
-    int hot_log2;
+    uint32_t *hotf;                // "maybe hot" bitmap: one bit per 8 ADJACENT buckets of a table
+    uint64_t hot_base[KV_TABLES_DEV];   // first bit of table t in hotf
     int n_tables;
     int bits;                      // 8, 4 or 1
 };
@@ -28,16 +28,18 @@ struct KvView {
 // counter line before hitting it with an atomic (a plain load followed by an atomic on the same
 // line costs ~3x the atomic alone on B200, profiles/r01_atomic_microbench_variants.csv):
 //   occ[t]  exact occupancy bitmap, read by the n_unique probe ("was this bucket empty?");
-//   hotf    a small hashed bit filter; a set bit means the bucket MAY hold a counter at or above
-//           KV_HOT (128 / 8) and must take the exact compare-and-swap path.  It is 1/8 bit per
-//           bucket, so it stays cache-resident; false positives only cost speed.
+//   hotf    one bit per group of 8 adjacent buckets; a set bit means some bucket of the group MAY
+//           hold a counter at or above KV_HOT (128 / 8), and the whole group takes the exact
+//           compare-and-swap path.  1/8 bit per bucket keeps it cache-resident, false positives
+//           only cost speed, and -- unlike a hashed filter -- it is as local as the buckets are,
+//           which the region-partitioned update path relies on.
 // Bits only ever get set (atomicOr), so a stale read is always on the safe side.
 template <int BITS>
 __device__ __forceinline__ unsigned kv_hot_threshold() { return BITS == 8 ? 128u : 8u; }
 
 __device__ __forceinline__ uint64_t kv_hot_index(const KvView &v, int t, uint64_t bin)
 {
-    return ((bin * 8 + (uint64_t)t) * 0x9E3779B97F4A7C15ull) >> (64 - v.hot_log2);
+    return v.hot_base[t] + (bin >> 3);
 }
 
 __device__ __forceinline__ bool kv_maybe_hot(const KvView &v, int t, uint64_t bin)

@@ -281,7 +281,6 @@ __global__ void kv_expand_bits_kernel(const uint32_t *__restrict__ valid, uint64
 //            16 MB region, which therefore stays L2- and TLB-resident while it is hit; same
 //            speculative / exact update logic, rollback and redo as the direct kernel.
 
-#define KV_PART_TILE 512        // positions per CTA tile in hist/scatter (2 per thread)
 #define KV_PART_MAX 4096        // (table, region) runs
 
 struct KvPartInfo {
@@ -289,29 +288,64 @@ struct KvPartInfo {
     uint32_t pbase[KV_TABLES_DEV + 1];   // first run of table t; pbase[n_tables] = number of runs
 };
 
-// meta[0] = number of items, meta[1 + t] = index of the first item of table t (t <= n_tables)
+// CTA b owns positions [b*slice, (b+1)*slice) in BOTH hist and scatter.  rows[run * G + b] first
+// holds how many items of `run` CTA b produces, after kv_part_rowscan_kernel the number produced
+// by CTAs before b (exclusive prefix inside the run).
 __global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
-                                                           const uint32_t *__restrict__ valid, uint64_t total,
-                                                           uint32_t *__restrict__ hist)
+                                                           const uint32_t *__restrict__ valid, uint64_t total, uint64_t slice,
+                                                           uint32_t *__restrict__ rows)
 {
-    extern __shared__ uint32_t sm_hist[];
+    extern __shared__ uint32_t sm_cnt[];
     const int P = (int)pi.pbase[v.n_tables];
-    for (int q = threadIdx.x; q < P; q += blockDim.x) sm_hist[q] = 0;
+    for (int q = threadIdx.x; q < P; q += blockDim.x) sm_cnt[q] = 0;
     __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+    const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
+    for (uint64_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
         if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
         const uint64_t h = __ldcs(hashes + g);
         for (int t = 0; t < v.n_tables; t++)
-            atomicAdd(&sm_hist[pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb)], 1u);
+            atomicAdd(&sm_cnt[pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb)], 1u);
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < P; q += blockDim.x)
-        if (sm_hist[q]) atomicAdd(hist + q, sm_hist[q]);
+    for (int q = threadIdx.x; q < P; q += blockDim.x) rows[(size_t)q * gridDim.x + blockIdx.x] = sm_cnt[q];
 }
 
-__global__ void kv_part_scan_kernel(KvPartInfo pi, int n_tables, const uint32_t *__restrict__ hist,
-                                    uint32_t *__restrict__ cursor, uint32_t *__restrict__ meta)
+// one CTA per run: exclusive scan of its G per-CTA counts, run total to runsum[run]  (G <= 2048)
+__global__ void __launch_bounds__(256) kv_part_rowscan_kernel(uint32_t *__restrict__ rows, int G, uint32_t *__restrict__ runsum)
+{
+    __shared__ uint32_t warp_tot[8];
+    uint32_t *row = rows + (size_t)blockIdx.x * G;
+    uint32_t val[8], mine = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int i = threadIdx.x * 8 + j;
+        val[j] = i < G ? row[i] : 0u;
+        mine += val[j];
+    }
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < wid; w++) before += warp_tot[w];
+    uint32_t run = before + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int i = threadIdx.x * 8 + j;
+        if (i < G) row[i] = run;
+        run += val[j];
+    }
+    if (threadIdx.x == 255) runsum[blockIdx.x] = before + incl;
+}
+
+// meta[0] = number of items, meta[1 + t] = index of the first item of table t (t <= n_tables)
+__global__ void kv_part_scan_kernel(KvPartInfo pi, int n_tables, const uint32_t *__restrict__ runsum,
+                                    uint32_t *__restrict__ runbase, uint32_t *__restrict__ meta)
 {
     if (threadIdx.x || blockIdx.x) return;
     const int P = (int)pi.pbase[n_tables];
@@ -319,55 +353,34 @@ __global__ void kv_part_scan_kernel(KvPartInfo pi, int n_tables, const uint32_t 
     int t = 0;
     for (int q = 0; q < P; q++) {
         while (t <= n_tables && (uint32_t)q == pi.pbase[t]) meta[1 + t++] = run;
-        cursor[q] = run;
-        run += hist[q];
+        runbase[q] = run;
+        run += runsum[q];
     }
     while (t <= n_tables) meta[1 + t++] = run;
     meta[0] = run;
 }
 
+// Each CTA re-walks its slice; a shared-memory cursor per run hands out absolute item slots, so
+// the CTA's items of one run are written next to each other (L2 merges them into full sectors)
+// and no global atomic is needed.
 __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
                                                               const uint32_t *__restrict__ valid, uint64_t total,
-                                                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ items)
+                                                              uint64_t slice, const uint32_t *__restrict__ rows,
+                                                              const uint32_t *__restrict__ runbase,
+                                                              uint32_t *__restrict__ items)
 {
-    extern __shared__ uint32_t sm_part[];
+    extern __shared__ uint32_t sm_cur[];
     const int P = (int)pi.pbase[v.n_tables];
-    uint32_t *cnt = sm_part, *base = sm_part + P;
-    const uint64_t n_tiles = (total + KV_PART_TILE - 1) / KV_PART_TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int q = threadIdx.x; q < P; q += blockDim.x) cnt[q] = 0;
-        __syncthreads();
-        uint32_t bin[2][4], run[2][4], rank[2][4];
-        bool live[2];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const uint64_t g = tile * KV_PART_TILE + j * 256 + threadIdx.x;
-            live[j] = g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
-            if (live[j]) {
-                const uint64_t h = __ldcs(hashes + g);
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (t < v.n_tables) {
-                        bin[j][t] = (uint32_t)kv_mod(h, v.size[t], v.magic[t]);
-                        run[j][t] = pi.pbase[t] + (bin[j][t] >> pi.rb);
-                        rank[j][t] = atomicAdd(&cnt[run[j][t]], 1u);
-                    }
-            }
+    for (int q = threadIdx.x; q < P; q += blockDim.x) sm_cur[q] = runbase[q] + rows[(size_t)q * gridDim.x + blockIdx.x];
+    __syncthreads();
+    const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
+    for (uint64_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+        if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
+        const uint64_t h = __ldcs(hashes + g);
+        for (int t = 0; t < v.n_tables; t++) {
+            const uint32_t bin = (uint32_t)kv_mod(h, v.size[t], v.magic[t]);
+            items[atomicAdd(&sm_cur[pi.pbase[t] + (bin >> pi.rb)], 1u)] = bin;
         }
-        __syncthreads();
-        for (int q = threadIdx.x; q < P; q += blockDim.x) {
-            uint32_t c = cnt[q];
-            base[q] = c ? atomicAdd(cursor + q, c) : 0u;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-            if (live[j]) {
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (t < v.n_tables) items[base[run[j][t]] + rank[j][t]] = bin[j][t];
-            }
-        __syncthreads();
     }
 }
 

@@ -216,8 +216,8 @@ struct kv_sketch {
     uint8_t *flat;
     uint32_t *state;                  // [occ bitmap of table 0 | ... | hot filter], 8/4-bit sketches only
     uint64_t soff[KV_TABLES_DEV];     // word offset of each table's occupancy bitmap
-    uint64_t hot_off;                 // word offset of the hot filter
-    int hot_log2;                     // hot filter holds 2^hot_log2 bits
+    uint64_t hot_off;                 // word offset of the hot bitmap
+    uint64_t hot_base[KV_TABLES_DEV]; // first bit of each table inside the hot bitmap
     uint64_t state_words;
     bool track_unique, unique_valid;
     uint64_t n_unique;                // host copy, updated at stats time
@@ -239,7 +239,7 @@ static KvView kv_view(const kv_sketch *s)
     v.n_tables = s->n_tables;
     v.bits = s->bits;
     v.hotf = s->state ? s->state + s->hot_off : nullptr;
-    v.hot_log2 = s->hot_log2;
+    for (int t = 0; t < s->n_tables; t++) v.hot_base[t] = s->hot_base[t];
     for (int t = 0; t < s->n_tables; t++) {
         v.tab[t] = s->flat + s->toff[t];
         v.size[t] = s->sizes[t];
@@ -301,7 +301,7 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     kv_sketch *s = new kv_sketch();
     memset(s, 0, sizeof *s);
     s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
-    uint64_t off = 0, soff = 0, buckets = 0;
+    uint64_t off = 0, soff = 0, hotbits = 0;
     for (int t = 0; t < n_tables; t++) {
         if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete s; return kv_fail(KV_EINVAL, "bad table size"); }
         s->sizes[t] = sizes[t];
@@ -310,12 +310,11 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
         off += (s->nbytes[t] + 255) & ~(uint64_t)255;
         s->soff[t] = soff;
         soff += ((sizes[t] + 31) / 32 + 63) & ~(uint64_t)63;
-        buckets += sizes[t];
+        s->hot_base[t] = hotbits;
+        hotbits += ((sizes[t] >> 3) + 1 + 2047) & ~(uint64_t)2047;
     }
-    s->hot_log2 = 15;
-    while ((1ull << s->hot_log2) < buckets / 8) s->hot_log2++;
     s->hot_off = soff;
-    s->state_words = bits == 1 ? 0 : soff + ((1ull << s->hot_log2) / 32);
+    s->state_words = bits == 1 ? 0 : soff + hotbits / 32;
     s->flat_bytes = off;
     cudaError_t e = cudaMalloc((void **)&s->flat, off);
     if (e != cudaSuccess) {
@@ -699,7 +698,21 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, uint64_t flat_bytes,
     return KV_OK;
 }
 
-// Region-partitioned update of one chunk (K3b): hist -> scan -> scatter -> apply (+ fix-up pair).
+// Region-partitioned update of one chunk (K3b): per-CTA histogram rows -> scan -> scatter -> apply
+// (+ fix-up pair).  hist and scatter MUST use the same grid: CTA b owns the same slice of
+// positions in both.
+template <typename K, typename... Args>
+static int kv_launch_smem(KvCtx *ctx, int cls, K kern, unsigned grid, unsigned block, size_t smem, Args... args)
+{
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->compute); }
+    kern<<<grid, block, smem, ctx->compute>>>(args...);
+    if (ctx->profiling) { cudaEventRecord(e1, ctx->compute); ctx->prof_events.push_back({cls, {e0, e1}}); }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return KV_OK;
+}
+
 template <int BITS>
 static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &pi, const uint64_t *d_hashes,
                                  const uint32_t *d_valid, uint64_t n)
@@ -707,39 +720,25 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
     const int P = (int)pi.pbase[v.n_tables];
     const uint64_t max_items = n * (uint64_t)v.n_tables;
     if (max_items >= 0xffffffffull) return kv_fail(KV_EINVAL, "internal: partitioned chunk too large");
+    const unsigned grid = kv_grid_for(ctx, n);                       // <= 8 CTAs per SM
+    const uint64_t slice = (((n + grid - 1) / grid) + 31) & ~(uint64_t)31;   // positions per CTA
     KV_TRY(kv_buf_ensure(ctx->part_items, max_items * 4));
-    KV_TRY(kv_buf_ensure(ctx->part_small, (2 * (size_t)P + 16) * 4));
+    KV_TRY(kv_buf_ensure(ctx->part_small, ((size_t)P * grid + 2 * (size_t)P + 16) * 4));
     KV_TRY(kv_buf_ensure(ctx->added, (max_items / 32 + 2) * 4));
-    uint32_t *hist = (uint32_t *)ctx->part_small.p, *cursor = hist + P, *meta = cursor + P;
+    uint32_t *rows = (uint32_t *)ctx->part_small.p, *runsum = rows + (size_t)P * grid, *runbase = runsum + P,
+             *meta = runbase + P;
     uint32_t *items = (uint32_t *)ctx->part_items.p, *added = (uint32_t *)ctx->added.p;
     if (ctx->dirty_next == 64) {
         CU(cudaMemsetAsync(ctx->dirty, 0, 64 * sizeof(unsigned), ctx->compute));
         ctx->dirty_next = 0;
     }
     unsigned *dirty = ctx->dirty + ctx->dirty_next++;
-    CU(cudaMemsetAsync(hist, 0, (size_t)P * 4, ctx->compute));
-    const unsigned grid = kv_grid_for(ctx, n);
-    {
-        auto kfn = kv_part_hist_kernel;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (ctx->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->compute); }
-        kfn<<<grid, 256, (size_t)P * 4, ctx->compute>>>(v, pi, d_hashes, d_valid, n, hist);
-        if (ctx->profiling) { cudaEventRecord(e1, ctx->compute); ctx->prof_events.push_back({KV_PROF_PARTITION, {e0, e1}}); }
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
-    LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_scan_kernel, 1, 32, pi, v.n_tables, hist, cursor, meta);
-    {
-        auto kfn = kv_part_scatter_kernel;
-        const uint64_t n_tiles = (n + KV_PART_TILE - 1) / KV_PART_TILE;
-        const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 8));
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (ctx->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->compute); }
-        kfn<<<sgrid, 256, (size_t)P * 8, ctx->compute>>>(v, pi, d_hashes, d_valid, n, cursor, items);
-        if (ctx->profiling) { cudaEventRecord(e1, ctx->compute); ctx->prof_events.push_back({KV_PROF_PARTITION, {e0, e1}}); }
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
+    KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_hist_kernel, grid, 256, (size_t)P * 4, v, pi, d_hashes, d_valid, n,
+                          slice, rows));
+    LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_rowscan_kernel, (unsigned)P, 256, rows, (int)grid, runsum);
+    LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_scan_kernel, 1, 32, pi, v.n_tables, runsum, runbase, meta);
+    KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_scatter_kernel, grid, 256, (size_t)P * 4, v, pi, d_hashes, d_valid,
+                          n, slice, rows, runbase, items));
     const unsigned agrid = kv_grid_for(ctx, max_items);
     LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_part_apply_kernel<BITS, 0>), agrid, 256, v, items, meta, added, dirty);
     LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 1>), agrid, 256, v, items, meta, added, dirty);
@@ -832,8 +831,10 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
     if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
 
-    const uint64_t chunk_tiles = ctx->chunk_bases / KV_TILE;
-    const uint64_t chunk_pos = std::min<uint64_t>(ctx->chunk_bases, b.n_tiles * KV_TILE);
+    // positions are 32-bit inside a chunk, and the partitioned path indexes n_tables items per position
+    const uint64_t chunk_limit = std::min<uint64_t>(ctx->chunk_bases, (0xfffffff0ull / (uint64_t)s->n_tables) / KV_TILE * KV_TILE);
+    const uint64_t chunk_tiles = chunk_limit / KV_TILE;
+    const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
     KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
     KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
     for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
