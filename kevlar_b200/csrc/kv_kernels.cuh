@@ -300,11 +300,17 @@ __global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo 
     for (int q = threadIdx.x; q < P; q += blockDim.x) sm_cnt[q] = 0;
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
-    for (uint64_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
-        if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
-        const uint64_t h = __ldcs(hashes + g);
-        for (int t = 0; t < v.n_tables; t++)
-            atomicAdd(&sm_cnt[pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb)], 1u);
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t g0 = lo; g0 < hi; g0 += blockDim.x) {     // slice is a multiple of 32: whole warps stay together
+        const uint64_t g = g0 + threadIdx.x;
+        const bool live = g < hi && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
+        const uint64_t h = live ? __ldcs(hashes + g) : 0;
+        for (int t = 0; t < v.n_tables; t++) {
+            // lanes of a warp that feed the same run are counted with one shared-memory atomic
+            const uint32_t run = live ? pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, run);
+            if (live && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sm_cnt[run], (uint32_t)__popc(peers));
+        }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < P; q += blockDim.x) rows[(size_t)q * gridDim.x + blockIdx.x] = sm_cnt[q];
@@ -374,12 +380,20 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
     for (int q = threadIdx.x; q < P; q += blockDim.x) sm_cur[q] = runbase[q] + rows[(size_t)q * gridDim.x + blockIdx.x];
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
-    for (uint64_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
-        if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
-        const uint64_t h = __ldcs(hashes + g);
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t g0 = lo; g0 < hi; g0 += blockDim.x) {
+        const uint64_t g = g0 + threadIdx.x;
+        const bool live = g < hi && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
+        const uint64_t h = live ? __ldcs(hashes + g) : 0;
         for (int t = 0; t < v.n_tables; t++) {
-            const uint32_t bin = (uint32_t)kv_mod(h, v.size[t], v.magic[t]);
-            items[atomicAdd(&sm_cur[pi.pbase[t] + (bin >> pi.rb)], 1u)] = bin;
+            const uint32_t bin = live ? (uint32_t)kv_mod(h, v.size[t], v.magic[t]) : 0u;
+            const uint32_t run = live ? pi.pbase[t] + (bin >> pi.rb) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, run);
+            const int leader = __ffs(peers) - 1;
+            uint32_t slot = 0;
+            if (live && (int)lane == leader) slot = atomicAdd(&sm_cur[run], (uint32_t)__popc(peers));
+            slot = __shfl_sync(0xffffffffu, slot, leader);
+            if (live) items[slot + __popc(peers & ((1u << lane) - 1u))] = bin;
         }
     }
 }
@@ -394,34 +408,58 @@ __global__ void __launch_bounds__(256) kv_part_apply_kernel(KvView v, const uint
     if (MODE != 0 && *dirty == 0) return;
     const unsigned maxv = BITS == 8 ? 255u : 15u;
     const uint64_t n = meta[0];
-    const uint64_t n_pad = (n + 31) & ~(uint64_t)31;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        bool did = false;
-        if (i < n) {
-            int t = 0;
-            while (t + 1 < v.n_tables && i >= meta[2 + t]) t++;
-            const uint64_t bin = __ldcs(items + i);
-            unsigned *w, sh;
-            kv_word_addr<BITS>(v, t, bin, w, sh);
-            if (MODE == 1) {
-                if ((added[i >> 5] >> (i & 31)) & 1u) atomicAdd(w, 0u - (1u << sh));
-            } else {
-                unsigned ob;
-                if (MODE == 2 || kv_maybe_hot(v, t, bin)) {
-                    did = kv_sat_inc_exact<BITS>(w, sh, ob);
-                    if (did) kv_state_publish<BITS>(v, t, bin, ob);
-                } else {
-                    ob = (atomicAdd(w, 1u << sh) >> sh) & maxv;
-                    did = true;
-                    if (ob == maxv) atomicOr(dirty, 1u);
-                    else kv_state_publish<BITS>(v, t, bin, ob);
-                }
+    // each CTA iteration covers 4 consecutive groups of 256 items; a thread owns one item in each
+    // group, so four independent atomics are in flight per thread
+    const uint64_t span = 4ull * blockDim.x;
+    const uint64_t n_pad = (n + span - 1) / span * span;
+    const uint64_t stride = (uint64_t)gridDim.x * span;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * span + threadIdx.x; i0 < n_pad; i0 += stride) {
+        unsigned *w[4], sh[4], ob[4];
+        uint64_t bin[4];
+        int tt[4];
+        bool live[4], hot[4], did[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t i = i0 + (uint64_t)j * blockDim.x;
+            live[j] = i < n;
+            did[j] = false;
+            hot[j] = true;
+            ob[j] = 0;
+            if (live[j]) {
+                int t = 0;
+                while (t + 1 < v.n_tables && i >= meta[2 + t]) t++;
+                tt[j] = t;
+                bin[j] = __ldcs(items + i);
+                kv_word_addr<BITS>(v, t, bin[j], w[j], sh[j]);
+                if (MODE == 0) hot[j] = kv_maybe_hot(v, t, bin[j]);
             }
         }
         if (MODE == 0) {
-            unsigned bal = __ballot_sync(0xffffffffu, did);
-            if ((threadIdx.x & 31) == 0) added[i >> 5] = bal;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (live[j] && !hot[j]) {
+                    ob[j] = (atomicAdd(w[j], 1u << sh[j]) >> sh[j]) & maxv;
+                    did[j] = true;
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t i = i0 + (uint64_t)j * blockDim.x;
+            if (live[j]) {
+                if (MODE == 1) {
+                    if ((added[i >> 5] >> (i & 31)) & 1u) atomicAdd(w[j], 0u - (1u << sh[j]));
+                } else if (hot[j]) {
+                    did[j] = kv_sat_inc_exact<BITS>(w[j], sh[j], ob[j]);
+                    if (did[j]) kv_state_publish<BITS>(v, tt[j], bin[j], ob[j]);
+                } else if (ob[j] == maxv)
+                    atomicOr(dirty, 1u);
+                else
+                    kv_state_publish<BITS>(v, tt[j], bin[j], ob[j]);
+            }
+            if (MODE == 0) {
+                unsigned bal = __ballot_sync(0xffffffffu, did[j]);
+                if ((threadIdx.x & 31) == 0 && i < n_pad) added[i >> 5] = bal;
+            }
         }
     }
 }

@@ -72,7 +72,7 @@ struct KvCtx {
     int next_slot = 0;
     KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small;
     uint64_t part_min_bytes = 128ull << 20;   // sketches at least this large take the region-partitioned update path
-    int part_region_log2 = 24;                // buckets per region (8-bit: 16 MB)
+    int part_region_log2 = 26;                // buckets per region (8-bit: 64 MB, what stays L2-resident in config 2)
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
@@ -724,7 +724,7 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
     const uint64_t slice = (((n + grid - 1) / grid) + 31) & ~(uint64_t)31;   // positions per CTA
     KV_TRY(kv_buf_ensure(ctx->part_items, max_items * 4));
     KV_TRY(kv_buf_ensure(ctx->part_small, ((size_t)P * grid + 2 * (size_t)P + 16) * 4));
-    KV_TRY(kv_buf_ensure(ctx->added, (max_items / 32 + 2) * 4));
+    KV_TRY(kv_buf_ensure(ctx->added, (max_items / 32 + 64) * 4));
     uint32_t *rows = (uint32_t *)ctx->part_small.p, *runsum = rows + (size_t)P * grid, *runbase = runsum + P,
              *meta = runbase + P;
     uint32_t *items = (uint32_t *)ctx->part_items.p, *added = (uint32_t *)ctx->added.p;
