@@ -71,8 +71,10 @@ struct KvCtx {
     KvSlot slot[2];
     int next_slot = 0;
     KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small;
-    uint64_t part_min_bytes = 128ull << 20;   // sketches at least this large take the region-partitioned update path
-    int part_region_log2 = 26;                // buckets per region (8-bit: 64 MB, what stays L2-resident in config 2)
+    // sketches between these sizes take the region-partitioned update path (measured: 1.2-1.7x over
+    // direct random atomics from 256 MB to 4 GB, break-even at 16 GB; profiles/r01_notes.md)
+    uint64_t part_min_bytes = 128ull << 20, part_max_bytes = 8ull << 30;
+    int part_region_log2 = 24;                // buckets per region (8-bit: 16 MB)
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
@@ -139,6 +141,7 @@ static int kv_ctx_get(int device, KvCtx **out)
         }
         c.chunk_bases = (c.chunk_bases + KV_TILE - 1) / KV_TILE * KV_TILE;
         if (const char *env = getenv("KV_PART_MIN_BYTES")) c.part_min_bytes = strtoull(env, nullptr, 10);
+        if (const char *env = getenv("KV_PART_MAX_BYTES")) c.part_max_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_REGION_LOG2")) c.part_region_log2 = std::max(4, std::min(30, atoi(env)));
         c.ready = true;
     }
@@ -779,7 +782,8 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
     if (s->track_unique) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n));
     else s->unique_valid = false;
     // large counter sketches: region-partitioned updates (tables must index with 32 bits, <= 4 tables)
-    bool partitioned = s->bits != 1 && s->flat_bytes >= ctx->part_min_bytes && s->n_tables <= 4;
+    bool partitioned = s->bits != 1 && s->flat_bytes >= ctx->part_min_bytes && s->flat_bytes <= ctx->part_max_bytes &&
+                       s->n_tables <= 4;
     KvPartInfo pi;
     memset(&pi, 0, sizeof pi);
     if (partitioned) {

@@ -700,3 +700,20 @@ def test_full_size_properties(kv, oracle):
     # every k-mer of a read just counted is present at least once
     counts = g.get_kmer_counts(bases[:100].tobytes().decode())
     assert min(counts) >= 1
+
+
+def test_partitioned_update_path_is_exact():
+    """Sketches larger than L2 use the region-partitioned update kernels (hist / scan / scatter /
+    apply).  The path is chosen per process from the sketch size, so a child process with the
+    threshold forced to zero and tiny regions re-runs the count parity tests through it."""
+    import subprocess
+    import sys
+    env = dict(os.environ, KV_PART_MIN_BYTES='0', KV_PART_REGION_LOG2='10')
+    if env.get('KV_PART_CHILD'):
+        pytest.skip('already inside the forced-partition child')
+    env['KV_PART_CHILD'] = '1'
+    res = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-x', '-q', '-k',
+                          'consume or saturation or add_get or count_simple or full_size'],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert ' passed' in res.stdout
