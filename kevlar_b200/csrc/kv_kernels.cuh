@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) kv_part_apply_kernel(KvView v, const uint
 //   occurrence g is new  <=>  for some table t its bucket was empty at batch start (occ bit
 //                             clear) and g is the smallest position of the batch touching it.
 // pass A (per table): first[bin] = min(first[bin], g) for every valid g whose bucket is empty;
-// pass B (per table): g is flagged if first[bin_t(g)] == g;   finally popcount of the flags.
+// pass B (per table): every position recorded in first[] is flagged;   finally popcount of the flags.
 // first[] is ONE u32 array as long as the largest table, reused for each table in turn, so the
 // random atomics of a pass stay inside a (for the benchmark config L2-resident) 4-bytes-per-
 // bucket region instead of spreading over all tables at once.
@@ -490,22 +490,29 @@ __global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint
     }
 }
 
-__global__ void __launch_bounds__(256) kv_first_resolve_kernel(KvView v, int t, const uint32_t *__restrict__ first,
-                                                               const uint64_t *__restrict__ hashes,
-                                                               const uint32_t *__restrict__ valid, uint64_t total,
+// pass B, bucket-major: stream first[] once; every recorded owner position gets its bit in
+// fresh[] (RED.OR into a bitmap of a few MB) and the entry is reset for the next table / batch.
+__global__ void __launch_bounds__(256) kv_first_resolve_kernel(uint32_t *__restrict__ first, uint64_t n_buckets,
                                                                uint32_t *__restrict__ fresh)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
-    const uint64_t size = v.size[t], magic = v.magic[t];
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        bool mine = false;
-        if (g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u))) {
-            const uint64_t bin = kv_mod(__ldcs(hashes + g), size, magic);
-            mine = __ldcg(first + bin) == (uint32_t)g;   // buckets that were occupied never got an entry
+    const uint64_t n_vec = n_buckets / 4;
+    uint4 *fv = (uint4 *)first;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        uint4 e = fv[i];
+        if ((e.x & e.y & e.z & e.w) == 0xffffffffu) continue;
+        if (e.x != 0xffffffffu) atomicOr(fresh + (e.x >> 5), 1u << (e.x & 31));
+        if (e.y != 0xffffffffu) atomicOr(fresh + (e.y >> 5), 1u << (e.y & 31));
+        if (e.z != 0xffffffffu) atomicOr(fresh + (e.z >> 5), 1u << (e.z & 31));
+        if (e.w != 0xffffffffu) atomicOr(fresh + (e.w >> 5), 1u << (e.w & 31));
+        fv[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
+    for (uint64_t b = n_vec * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += stride) {
+        uint32_t e = first[b];
+        if (e != 0xffffffffu) {
+            atomicOr(fresh + (e >> 5), 1u << (e & 31));
+            first[b] = 0xffffffffu;
         }
-        unsigned bal = __ballot_sync(0xffffffffu, mine);
-        if ((threadIdx.x & 31) == 0 && bal) fresh[g >> 5] |= bal;   // passes run one after another: no race
     }
 }
 

@@ -755,17 +755,19 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
 {
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
-    KV_TRY(kv_buf_ensure(ctx->first, maxsize * 4));
+    if (maxsize * 4 > ctx->first.cap) {   // (re)allocated: establish the all-ones invariant the passes maintain
+        KV_TRY(kv_buf_ensure(ctx->first, maxsize * 4));
+        CU(cudaMemsetAsync(ctx->first.p, 0xff, ctx->first.cap, ctx->compute));
+    }
     const uint64_t n_words = (n + 31) / 32;
     KV_TRY(kv_buf_ensure(ctx->fresh, n_words * 4));
     CU(cudaMemsetAsync(ctx->fresh.p, 0, n_words * 4, ctx->compute));
     unsigned grid = kv_grid_for(ctx, n);
     kv_l2_window(ctx, ctx->first.p, maxsize * 4);
     for (int t = 0; t < s->n_tables; t++) {
-        CU(cudaMemsetAsync(ctx->first.p, 0xff, s->sizes[t] * 4, ctx->compute));
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n);
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, grid, 256, v, t, (const uint32_t *)ctx->first.p, d_hashes,
-                 d_valid, n, (uint32_t *)ctx->fresh.p);
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, kv_grid_for(ctx, s->sizes[t] / 4 + 1), 256,
+                 (uint32_t *)ctx->first.p, s->sizes[t], (uint32_t *)ctx->fresh.p);
     }
     kv_l2_window(ctx, nullptr, 0);
     LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_popcount_kernel, kv_grid_for(ctx, n_words), 256, (const uint32_t *)ctx->fresh.p, n_words,
