@@ -27,7 +27,8 @@ struct KvView {
 // Side information kept in SEPARATE small arrays so that the update path never has to load a
 // counter line before hitting it with an atomic (a plain load followed by an atomic on the same
 // line costs ~3x the atomic alone on B200, profiles/r01_atomic_microbench_variants.csv):
-//   occ[t]  exact occupancy bitmap, read by the n_unique probe ("was this bucket empty?");
+//   occ[t]  occupancy bitmap, rebuilt from the counters by one streaming pass at the start of each
+//           batch's n_unique bookkeeping ("was this bucket empty when the batch started?");
 //   hotf    one bit per group of 8 adjacent buckets; a set bit means some bucket of the group MAY
 //           hold a counter at or above KV_HOT (128 / 8), and the whole group takes the exact
 //           compare-and-swap path.  1/8 bit per bucket keeps it cache-resident, false positives
@@ -129,11 +130,11 @@ __device__ __forceinline__ bool kv_sat_inc_exact(unsigned *word, unsigned shift,
     return false;
 }
 
-// after an update that replaced the value `ob`: publish what it implies
+// after an update that replaced the value `ob`: a counter that reaches the hot threshold routes
+// its group of buckets to the exact path from now on
 template <int BITS>
 __device__ __forceinline__ void kv_state_publish(const KvView &v, int t, uint64_t bin, unsigned ob)
 {
-    if (ob == 0) atomicOr(v.occ[t] + (bin >> 5), 1u << (bin & 31));
     if (ob + 1 >= kv_hot_threshold<BITS>()) kv_mark_hot(v, t, bin);
 }
 

@@ -217,21 +217,49 @@ __global__ void __launch_bounds__(256) kv_rollback_kernel(KvView v, const uint64
     }
 }
 
-// Recompute the occupancy bitmap and the hot filter from the counters (after load / merge /
-// raw writes).  One thread per 32 buckets.
+// Recompute the hot bitmap from the counters (after load / merge / raw writes).
 template <int BITS>
 __global__ void kv_state_rebuild_kernel(KvView v, int t)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t bin = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; bin < v.size[t]; bin += stride) {
+        unsigned c = BITS == 8 ? v.tab[t][bin] : ((v.tab[t][bin >> 1] >> ((bin & 1) ? 0 : 4)) & 15u);
+        if (c >= kv_hot_threshold<BITS>()) kv_mark_hot(v, t, bin);
+    }
+}
+
+// Occupancy bitmap of table t from its counters: one thread per 32 buckets, 16-byte loads.
+template <int BITS>
+__global__ void __launch_bounds__(256) kv_occ_rebuild_kernel(KvView v, int t)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n_words = (v.size[t] + 31) / 32;
+    const uint64_t nbytes = BITS == 8 ? v.size[t] : v.size[t] / 2 + 1;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
         uint32_t word = 0;
-        for (int j = 0; j < 32; j++) {
-            uint64_t bin = i * 32 + j;
-            if (bin >= v.size[t]) break;
-            unsigned c = BITS == 8 ? v.tab[t][bin] : ((v.tab[t][bin >> 1] >> ((bin & 1) ? 0 : 4)) & 15u);
-            if (c) word |= 1u << j;
-            if (c >= kv_hot_threshold<BITS>()) kv_mark_hot(v, t, bin);
+        if (BITS == 8) {
+            const uint64_t b0 = i * 32;
+            if (b0 + 32 <= nbytes) {
+                const uint4 *p = (const uint4 *)(v.tab[t] + b0);
+                uint4 a = __ldcs(p), c = __ldcs(p + 1);
+                const uint32_t q[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t nz = __vcmpne4(q[j], 0u);   // 0xff per non-zero byte
+                    word |= ((nz & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * j);
+                }
+            } else {
+                for (int j = 0; j < 32 && b0 + j < v.size[t]; j++)
+                    if (v.tab[t][b0 + j]) word |= 1u << j;
+            }
+        } else {
+            // 32 buckets = 16 bytes; even bucket = high nibble
+            const uint64_t y0 = i * 16;
+            for (int j = 0; j < 16 && y0 + j < nbytes; j++) {
+                unsigned byte = v.tab[t][y0 + j];
+                if (byte >> 4) word |= 1u << (2 * j);
+                if ((byte & 15u) && i * 32 + 2 * j + 1 < v.size[t]) word |= 1u << (2 * j + 1);
+            }
         }
         v.occ[t][i] = word;
     }

@@ -452,9 +452,8 @@ static int kv_state_rebuild_locked(KvCtx *ctx, kv_sketch *s)
     KvView v = kv_view(s);
     CU(cudaMemsetAsync(s->state, 0, s->state_words * 4, ctx->compute));
     for (int t = 0; t < s->n_tables; t++) {
-        uint64_t n_words = (s->sizes[t] + 31) / 32;
-        if (s->bits == 8) LAUNCH(ctx, kv_state_rebuild_kernel<8>, kv_grid_for(ctx, n_words), 256, v, t);
-        else LAUNCH(ctx, kv_state_rebuild_kernel<4>, kv_grid_for(ctx, n_words), 256, v, t);
+        if (s->bits == 8) LAUNCH(ctx, kv_state_rebuild_kernel<8>, kv_grid_for(ctx, s->sizes[t], 16), 256, v, t);
+        else LAUNCH(ctx, kv_state_rebuild_kernel<4>, kv_grid_for(ctx, s->sizes[t], 16), 256, v, t);
     }
     return KV_OK;
 }
@@ -763,6 +762,12 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
     KV_TRY(kv_buf_ensure(ctx->fresh, n_words * 4));
     CU(cudaMemsetAsync(ctx->fresh.p, 0, n_words * 4, ctx->compute));
     unsigned grid = kv_grid_for(ctx, n);
+    if (s->bits != 1)   // which buckets are empty right now (= at batch start): one streaming pass per table
+        for (int t = 0; t < s->n_tables; t++) {
+            uint64_t n_words = (s->sizes[t] + 31) / 32;
+            if (s->bits == 8) LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<8>, kv_grid_for(ctx, n_words, 16), 256, v, t);
+            else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<4>, kv_grid_for(ctx, n_words, 16), 256, v, t);
+        }
     kv_l2_window(ctx, ctx->first.p, maxsize * 4);
     for (int t = 0; t < s->n_tables; t++) {
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n);
