@@ -182,6 +182,21 @@ int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);
 int kv_ipc_open(int device, const uint8_t handle[64], void **dev_ptr);
 int kv_ipc_close(int device, void *dev_ptr);
 
+/* khmer.ReadParser(filename) (kevlar/count.py:40, kevlar/__init__.py:125-128): FASTA/FASTQ, plain or
+ * gzip.  kv_reader_next parses at least one and at most ~max_bases bases' worth of records, in
+ * file order, straight into the batch layout above; n_reads = 0 means end of file.  All output
+ * pointers refer to reader-owned host memory that stays valid until the next call on the same
+ * reader: names / quals are the header lines (without '@' / '>') and quality strings of the
+ * batch back to back, with n_reads+1 offsets each; is_fastq[i] tells whether record i has a
+ * quality string.  Any of the text outputs may be NULL.  Not thread-safe per reader. */
+typedef struct kv_reader kv_reader;
+int kv_reader_open(const char *path, kv_reader **out);
+int kv_reader_next(kv_reader *r, uint64_t max_bases, const uint8_t **bases, const uint64_t **offsets,
+                   uint64_t *n_reads, const char **names, const uint64_t **name_offsets, const char **quals,
+                   const uint64_t **qual_offsets, const uint8_t **is_fastq);
+int kv_reader_num_reads(const kv_reader *r, uint64_t *n);
+int kv_reader_close(kv_reader *r);
+
 /* Stream plumbing: the cudaStream_t all work for `device` is enqueued on, so a host
  * framework can record events on it; kv_sync waits for it. */
 int kv_stream(int device, void **cuda_stream);

@@ -68,6 +68,11 @@ SYMBOLS = [
     ('kv_sketch_ipc_export', c_int, [_P, _P]),
     ('kv_ipc_open', c_int, [c_int, _P, POINTER(_P)]),
     ('kv_ipc_close', c_int, [c_int, _P]),
+    ('kv_reader_open', c_int, [c_char_p, POINTER(_P)]),
+    ('kv_reader_next', c_int, [_P, c_uint64, POINTER(_P), POINTER(_P), POINTER(c_uint64), POINTER(_P), POINTER(_P),
+                               POINTER(_P), POINTER(_P), POINTER(_P)]),
+    ('kv_reader_num_reads', c_int, [_P, POINTER(c_uint64)]),
+    ('kv_reader_close', c_int, [_P]),
     ('kv_stream', c_int, [c_int, POINTER(_P)]),
     ('kv_sync', c_int, [c_int]),
     ('kv_launch_count', c_int, [c_int, POINTER(c_uint64)]),

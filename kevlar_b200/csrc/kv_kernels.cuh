@@ -1,13 +1,19 @@
 // kv_kernels.cuh -- the sm_100a kernels behind libkvsketch.so.
 //
-//   K0  kv_tile_index_kernel   which read does each 1024-base tile start in
-//   K1/K2 kv_hash_kernel       clean + (2-bit pack) + canonical hash per base position,
-//                              band and mask predicates fused; writes hashes + valid bits
-//   K3  kv_increment_kernel    saturating 8/4/1-bit Count-Min / Bloom update (khmer Storage::add)
-//   K4  kv_novel_kernel        fused hash + case/control lookups + thresholds (kevlar/novel.py:21-53,123-169)
-//   K5  kv_unique_probe/resolve_kernel, kv_occupied_kernel   n_unique_kmers / n_occupied bookkeeping
-//   K6  kv_widen/narrow/merge_peers kernels   multi-GPU saturating merge
-//   +   kv_get_kernel          min-over-tables lookups for explicit hashes
+//   K0  kv_tile_index_kernel    which read does each 1024-base tile start in
+//   K1/K2 kv_hash_kernel        clean + (2-bit pack) + canonical hash per base position,
+//                               band and mask predicates fused; writes hashes + valid bits
+//   K3  kv_increment_kernel     saturating 8/4/1-bit Count-Min / Bloom update (khmer Storage::add):
+//                               speculative ATOM.ADD for cold buckets, exact CAS for hot ones;
+//       kv_rollback_kernel      undo of a chunk whose speculative pass overflowed a counter
+//   K3b kv_part_*_kernel        the same update for sketches larger than L2: updates partitioned
+//                               by (table, 16 MB region), then applied region by region
+//   K4  kv_novel_kernel         fused hash + case/control lookups + thresholds
+//                               (kevlar/novel.py:21-53,123-169)
+//   K5  kv_occ_rebuild / kv_first_min / kv_first_resolve / kv_popcount   exact n_unique_kmers;
+//       kv_occupied_kernel      n_occupied
+//   K6  kv_widen / kv_narrow / kv_merge_peers kernels   multi-GPU saturating merge
+//   +   kv_get_kernel, kv_gather_kernel, kv_expand_bits_kernel, kv_state_rebuild_kernel   helpers
 #pragma once
 #include <cuda_fp16.h>
 
@@ -707,8 +713,3 @@ __global__ void kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec,
     }
 }
 
-__global__ void kv_fill_u32_kernel(uint32_t *p, uint64_t n, uint32_t val)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = val;
-}

@@ -30,6 +30,18 @@ static int kv_fail(int code, const char *fmt, ...)
     return code;
 }
 
+// error reporting for the other translation units of the library (kv_fastx.cpp)
+int kv_fail_public(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
 #define CU(expr)                                                                                     \
     do {                                                                                             \
         cudaError_t e_ = (expr);                                                                     \
@@ -79,6 +91,7 @@ struct KvCtx {
     unsigned dirty_next = 0;
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
     unsigned long long *h_counters = nullptr; // pinned mirror
+    uint8_t *h_stage = nullptr;               // pinned staging for sketch file I/O (lazily allocated)
     uint64_t launches = 0;
     // optional per-kernel-class timing (kv_profile): event pairs around launches
     bool profiling = false;
@@ -146,6 +159,19 @@ static int kv_ctx_get(int device, KvCtx **out)
         c.ready = true;
     }
     *out = &c;
+    return KV_OK;
+}
+
+static const size_t KV_IO_STAGE = 64u << 20;
+
+static int kv_io_stage(KvCtx *ctx, uint8_t **out)
+{
+    if (!ctx->h_stage && cudaMallocHost((void **)&ctx->h_stage, KV_IO_STAGE) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->h_stage = nullptr;
+        return kv_fail(KV_ENOMEM, "cannot allocate pinned staging memory for sketch I/O");
+    }
+    *out = ctx->h_stage;
     return KV_OK;
 }
 
@@ -225,7 +251,6 @@ struct kv_sketch {
     bool track_unique, unique_valid;
     uint64_t n_unique;                // host copy, updated at stats time
     unsigned long long *d_unique;     // device accumulator
-    uint64_t file_occupied;           // n_occupied as stored in the file it was loaded from
 };
 
 static uint64_t kv_table_bytes(int bits, uint64_t size)
@@ -509,10 +534,10 @@ extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
     fwrite(&k, 4, 1, f);
     fwrite(&nt, 1, 1, f);
     fwrite(&occ, 8, 1, f);
-    const size_t CH = 64u << 20;
+    const size_t CH = KV_IO_STAGE;
     uint8_t *stage = nullptr;
-    if (cudaMallocHost((void **)&stage, CH) != cudaSuccess) { fclose(f); cudaGetLastError(); return kv_fail(KV_ENOMEM, "pinned staging"); }
-    int rc = KV_OK;
+    int rc = kv_io_stage(ctx, &stage);
+    if (rc != KV_OK) { fclose(f); return rc; }
     for (int t = 0; t < s->n_tables && rc == KV_OK; t++) {
         fwrite(&s->sizes[t], 8, 1, f);
         for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
@@ -522,7 +547,6 @@ extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
             if (fwrite(stage, 1, n, f) != n) { rc = kv_fail(KV_EIO, "short write to %s", path); break; }
         }
     }
-    cudaFreeHost(stage);
     if (rc == KV_OK && s->bits == 8) { uint64_t nbig = 0; fwrite(&nbig, 8, 1, f); }
     if (rc == KV_OK && ferror(f)) rc = kv_fail(KV_EIO, "write error on %s", path);
     fclose(f);
@@ -560,9 +584,9 @@ extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int
     KvCtx *ctx;
     kv_ctx_get(device, &ctx);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t CH = 64u << 20;
+    const size_t CH = KV_IO_STAGE;
     uint8_t *stage = nullptr;
-    if (cudaMallocHost((void **)&stage, CH) != cudaSuccess) { fclose(f); cudaGetLastError(); return kv_fail(KV_ENOMEM, "pinned staging"); }
+    rc = kv_io_stage(ctx, &stage);
     for (int t = 0; t < nt && rc == KV_OK; t++) {
         fseek(f, data_pos[t], SEEK_SET);
         for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
@@ -572,11 +596,10 @@ extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int
                 cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "H2D copy failed"); break; }
         }
     }
-    cudaFreeHost(stage);
     fclose(f);
     if (rc != KV_OK) { cudaFree(s->flat); cudaFree(s->state); cudaFree(s->d_unique); delete s; return rc; }
     KV_TRY(kv_state_rebuild_locked(ctx, s));
-    s->file_occupied = occ;
+    (void)occ;   // recomputed from table 0 whenever it is asked for
     *out = s;
     return KV_OK;
 }

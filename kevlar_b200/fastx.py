@@ -5,6 +5,7 @@ record-at-a-time iteration the reference uses, it can hand out whole *batches* -
 concatenated sequence bytes plus read offsets that ``kv_consume_batch`` / ``kv_novel_batch``
 take (include/kvsketch.h) -- so the hot loops never touch Python strings.
 """
+import ctypes
 import gzip
 import threading
 
@@ -25,22 +26,71 @@ class Read(object):
 
 
 class SeqBatch(object):
-    """A batch in the C-ABI layout plus what is needed to rebuild records for a few reads."""
-    __slots__ = ('bases', 'offsets', 'names', 'quals')
+    """A batch in the C-ABI layout plus what is needed to rebuild records for a few reads.
+    Header and quality text is kept either as Python lists or as the packed blobs the native
+    reader returns (blob + n+1 offsets), and only unpacked for the reads somebody asks for."""
+    __slots__ = ('bases', 'offsets', '_names', '_quals', '_name_blob', '_name_offs', '_qual_blob', '_qual_offs',
+                 '_is_fastq')
 
-    def __init__(self, bases, offsets, names, quals):
+    def __init__(self, bases, offsets, names=None, quals=None, packed=None):
         self.bases = bases        # np.uint8[total]
         self.offsets = offsets    # np.uint64[n+1]
-        self.names = names        # list[bytes]
-        self.quals = quals        # list[bytes] or None
+        self._names = names       # list[bytes] or None
+        self._quals = quals       # list[bytes or None] or None
+        self._name_blob = self._name_offs = self._qual_blob = self._qual_offs = self._is_fastq = None
+        if packed is not None:
+            self._name_blob, self._name_offs, self._qual_blob, self._qual_offs, self._is_fastq = packed
 
     def __len__(self):
         return len(self.offsets) - 1
 
+    def name(self, i):
+        if self._names is not None:
+            return self._names[i]
+        if self._name_blob is None:
+            return b''
+        return self._name_blob[int(self._name_offs[i]):int(self._name_offs[i + 1])]
+
+    def qual(self, i):
+        if self._quals is not None:
+            return self._quals[i]
+        if self._qual_blob is None or not self._is_fastq[i]:
+            return None
+        return self._qual_blob[int(self._qual_offs[i]):int(self._qual_offs[i + 1])]
+
+    @property
+    def names(self):
+        if self._names is None:
+            self._names = [self.name(i) for i in range(len(self))]
+        return self._names
+
+    def find_name(self, key):
+        """Index of the first read called `key` (bytes), or -1."""
+        if self._names is None and self._name_blob is not None:
+            at = self._name_blob.find(key)
+            while at >= 0:   # a hit must span exactly one name
+                i = int(np.searchsorted(self._name_offs, at, side='right')) - 1
+                if int(self._name_offs[i]) == at and int(self._name_offs[i + 1]) == at + len(key):
+                    return i
+                at = self._name_blob.find(key, at + 1)
+            return -1
+        try:
+            return self.names.index(key)
+        except ValueError:
+            return -1
+
+    def tail(self, start):
+        """The batch without its first `start` reads."""
+        offsets = np.ascontiguousarray(self.offsets[start:] - self.offsets[start])
+        bases = self.bases[int(self.offsets[start]):]
+        n = len(self)
+        return SeqBatch(bases, offsets, [self.name(i) for i in range(start, n)], [self.qual(i) for i in range(start, n)])
+
     def record(self, i):
         lo, hi = int(self.offsets[i]), int(self.offsets[i + 1])
-        qual = self.quals[i].decode('ascii') if self.quals is not None and self.quals[i] is not None else None
-        return Read(self.names[i].decode('ascii'), self.bases[lo:hi].tobytes().decode('ascii'), qual)
+        qual = self.qual(i)
+        return Read(self.name(i).decode('ascii'), self.bases[lo:hi].tobytes().decode('ascii'),
+                    qual.decode('ascii') if qual is not None else None)
 
 
 def batch_from_sequences(seqs, names=None, quals=None):
@@ -51,8 +101,6 @@ def batch_from_sequences(seqs, names=None, quals=None):
         np.cumsum(np.fromiter((len(b) for b in bs), dtype=np.uint64, count=len(bs)), out=offsets[1:])
     joined = b''.join(bs)
     bases = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(0, dtype=np.uint8)
-    if names is None:
-        names = [b''] * len(bs)
     return SeqBatch(bases, offsets, names, quals)
 
 
@@ -177,4 +225,69 @@ class FastxReader(object):
             yield batch_from_sequences(seqs, names, quals)
 
 
-ReadParser = FastxReader
+
+class NativeFastxReader(object):
+    """The same interface on top of the native parser in libkvsketch.so (kv_reader_*, zlib + a
+    memchr line splitter): ~10x the throughput of the pure-Python reader above, which remains as
+    the reference implementation the tests compare it with."""
+
+    def __init__(self, filename):
+        from kevlar_b200 import _lib
+        self._lib = _lib
+        self.filename = filename
+        self.num_reads = 0
+        self._lock = threading.Lock()
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().kv_reader_open(str(filename).encode(), ctypes.byref(self._h)))
+        self._records = None   # record-at-a-time iteration state: (batch, next index)
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h is not None and h.value and self._lib._lib is not None:
+            self._lib._lib.kv_reader_close(h)
+
+    def _next(self, max_bases, keep_text):
+        """One kv_reader_next call; copies the reader-owned buffers into numpy / bytes."""
+        c = ctypes
+        bases, offs, names, noffs, quals, qoffs, isfq = (c.c_void_p() for _ in range(7))
+        n = c.c_uint64()
+        self._lib.check(self._lib.lib().kv_reader_next(self._h, int(max_bases), c.byref(bases), c.byref(offs), c.byref(n),
+                                                       c.byref(names), c.byref(noffs), c.byref(quals), c.byref(qoffs),
+                                                       c.byref(isfq)))
+        n = n.value
+        if n == 0:
+            return None
+        offsets = np.ctypeslib.as_array(c.cast(offs, c.POINTER(c.c_uint64)), shape=(n + 1,)).copy()
+        total = int(offsets[-1])
+        b = np.ctypeslib.as_array(c.cast(bases, c.POINTER(c.c_uint8)), shape=(max(total, 1),))[:total].copy()
+        packed = None
+        if keep_text:
+            no = np.ctypeslib.as_array(c.cast(noffs, c.POINTER(c.c_uint64)), shape=(n + 1,)).copy()
+            qo = np.ctypeslib.as_array(c.cast(qoffs, c.POINTER(c.c_uint64)), shape=(n + 1,)).copy()
+            fq = np.ctypeslib.as_array(c.cast(isfq, c.POINTER(c.c_uint8)), shape=(n,)).copy()
+            packed = (c.string_at(names, int(no[-1])), no, c.string_at(quals, int(qo[-1])), qo, fq)
+        self.num_reads += n
+        return SeqBatch(b, offsets, packed=packed)
+
+    def batches(self, max_bases=64 << 20, keep_text=False):
+        while True:
+            with self._lock:
+                batch = self._next(max_bases, keep_text)
+            if batch is None:
+                return
+            yield batch
+
+    def __iter__(self):
+        while True:
+            with self._lock:
+                if self._records is None or self._records[1] >= len(self._records[0]):
+                    batch = self._next(4 << 20, True)
+                    if batch is None:
+                        return
+                    self._records = [batch, 0]
+                batch, i = self._records
+                self._records[1] = i + 1
+            yield batch.record(i)
+
+
+ReadParser = NativeFastxReader

@@ -10,17 +10,16 @@ GPU-side rewrite of kevlar's loops calls.
 All arithmetic happens in the CUDA library; nothing here computes a hash or touches a
 counter on the CPU.
 """
-import ctypes
 from ctypes import byref, c_int, c_uint64, c_void_p
 
 import numpy as np
 
 from kevlar_b200 import _lib
 from kevlar_b200._lib import HASH_MURMUR, HASH_TWOBIT, MEM_DEVICE, MEM_HOST, check, lib
-from kevlar_b200.fastx import FastxReader, Read, SeqBatch, batch_from_sequences
+from kevlar_b200.fastx import FastxReader, NativeFastxReader, Read, SeqBatch, batch_from_sequences  # noqa: F401
 from kevlar_b200.khmer import khmer_args  # noqa: F401
 
-ReadParser = FastxReader
+ReadParser = NativeFastxReader
 
 _buckets_per_byte = {'countgraph': 1, 'smallcountgraph': 2, 'nodegraph': 8}
 

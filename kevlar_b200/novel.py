@@ -8,7 +8,7 @@ import numpy as np
 
 import kevlar_b200
 from kevlar_b200 import _lib, khmer
-from kevlar_b200.fastx import SeqBatch, batch_from_sequences
+from kevlar_b200.fastx import batch_from_sequences
 from kevlar_b200.sequence import Record
 
 NOVEL_BATCH_BASES = 64 << 20
@@ -103,14 +103,6 @@ def _record_batches(stream, max_bases):
         yield batch_from_sequences(seqs, names, quals)
 
 
-def _drop_reads(batch, start):
-    """The batch without its first `start` reads."""
-    offsets = batch.offsets[start:] - batch.offsets[start]
-    bases = batch.bases[int(batch.offsets[start]):]
-    quals = batch.quals[start:] if batch.quals is not None else None
-    return SeqBatch(bases, np.ascontiguousarray(offsets), batch.names[start:], quals)
-
-
 def novel(casestream, casecounts, controlcounts, ksize=31, abundscreen=None, casemin=5, ctrlmax=0, numbands=None,
           band=None, skipuntil=None):
     """Generator of annotated Records for the reads with at least one novel k-mer
@@ -143,19 +135,18 @@ def novel(casestream, casecounts, controlcounts, ksize=31, abundscreen=None, cas
         batches = _record_batches(casestream, NOVEL_BATCH_BASES)
     for batch in batches:
         if skipuntil:  # fast-forward: the matching read itself is skipped too (novel.py:125-132)
-            key = skipuntil.encode('ascii')
-            if key not in batch.names:
+            at = batch.find_name(skipuntil.encode('ascii'))
+            if at < 0:
                 seen += len(batch)
                 progress.update(len(batch))
                 continue
-            at = batch.names.index(key)
             progress.update(at + 1)
             seen += at + 1
             message = 'Found read {:s} (skipped {:d} reads)'.format(skipuntil, seen)
             kevlar_b200.plog('[kevlar::novel]', message)
             skipuntil = False
             progress.message = update_message
-            batch = _drop_reads(batch, at + 1)
+            batch = batch.tail(at + 1)
             if len(batch) == 0:
                 continue
         progress.update(len(batch))

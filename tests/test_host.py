@@ -184,25 +184,51 @@ def test_augfastx_reader_details():
 @pytest.mark.parametrize('fn', ['simple-genome-case-reads.fa.gz', 'trio1/case1.fq.gz', 'bogus-genome/refr.fa',
                                 'microtrios/trio-na-proband.fq.gz', 'ambig.fasta', 'screen-case.fa'])
 def test_fastx_reader_matches_oracle_parser(oracle, fn, monkeypatch):
+    """Both readers -- the native one in libkvsketch.so (the product's ReadParser) and the pure
+    Python one -- against the oracle's independent parser, record by record and batch by batch."""
+    assert kv.khmer.ReadParser is fastx.NativeFastxReader
     want = [(r.name, r.sequence, r.quality) for r in oracle.ReadParser(golden_data(fn))]
-    for block in (32 << 20, 4096, 333):
-        monkeypatch.setattr(fastx.FastxReader, 'BLOCK', block)
-        got = [(r.name, r.sequence, r.quality) for r in fastx.FastxReader(golden_data(fn))]
+    for cls, block in ((fastx.NativeFastxReader, None), (fastx.FastxReader, 32 << 20), (fastx.FastxReader, 4096),
+                       (fastx.FastxReader, 333)):
+        if block:
+            monkeypatch.setattr(fastx.FastxReader, 'BLOCK', block)
+        got = [(r.name, r.sequence, r.quality) for r in cls(golden_data(fn))]
         assert got == want
-        reader = fastx.FastxReader(golden_data(fn))
+        reader = cls(golden_data(fn))
         seen = 0
         for batch in reader.batches(7000, keep_text=True):
             assert batch.offsets[0] == 0 and batch.offsets[-1] == len(batch.bases)
             for i in (0, len(batch) - 1):
                 rec = batch.record(i)
                 assert (rec.name, rec.sequence, rec.quality) == want[seen + i]
+            last = want[seen + len(batch) - 1][0].encode()
+            assert batch.name(batch.find_name(last)) == last and batch.find_name(b'no such read') == -1
+            tail = batch.tail(len(batch) - 1)
+            assert len(tail) == 1 and tail.record(0).sequence == want[seen + len(batch) - 1][1]
             seen += len(batch)
         assert seen == len(want) == reader.num_reads
 
 
+def test_native_reader_edge_cases(tmp_path):
+    """CRLF line ends, blank lines, a last record without newline, an empty sequence, and a
+    missing file."""
+    path = tmp_path / 'odd.fq'
+    path.write_bytes(b'@r1 first\r\nACGT\r\n+\r\nIIII\r\n\n@r2\n\n+\n\n@r3\nGG\n+\nII')
+    for cls in (fastx.NativeFastxReader, fastx.FastxReader):
+        recs = [(r.name, r.sequence, r.quality) for r in cls(str(path))]
+        assert recs == [('r1 first', 'ACGT', 'IIII'), ('r2', '', ''), ('r3', 'GG', 'II')], cls
+    fa = tmp_path / 'multi.fa'
+    fa.write_bytes(b'>chr1 desc\nACGT\nTTGA\n\n>chr2\nGG\n>empty\n')
+    for cls in (fastx.NativeFastxReader, fastx.FastxReader):
+        recs = [(r.name, r.sequence, r.quality) for r in cls(str(fa))]
+        assert recs == [('chr1 desc', 'ACGTTTGA', None), ('chr2', 'GG', None), ('empty', '', None)], cls
+    with pytest.raises(OSError):
+        fastx.NativeFastxReader(str(tmp_path / 'missing.fq'))
+
+
 def test_fastx_reader_shared_by_threads():
     """kevlar/count.py:40-77: several consumers drain one parser; every read exactly once."""
-    reader = fastx.FastxReader(golden_data('trio1/case1.fq.gz'))
+    reader = kv.khmer.ReadParser(golden_data('trio1/case1.fq.gz'))
     got, lock = [], threading.Lock()
 
     def work():
