@@ -249,6 +249,7 @@ struct kv_sketch {
     uint64_t hot_base[KV_TABLES_DEV]; // first bit of each table inside the hot bitmap
     uint64_t state_words;
     bool track_unique, unique_valid;
+    bool state_stale;                 // tables were written behind the kernels' back: rebuild the hot bitmap before the next update
     uint64_t n_unique;                // host copy, updated at stats time
     unsigned long long *d_unique;     // device accumulator
 };
@@ -401,7 +402,8 @@ extern "C" int kv_sketch_clear(kv_sketch *s)
     CU(cudaMemsetAsync(s->flat, 0, s->flat_bytes, ctx->compute));
     if (s->state) CU(cudaMemsetAsync(s->state, 0, s->state_words * 4, ctx->compute));
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
-    s->unique_valid = true;   // first[] is all-ones between batches by construction
+    s->state_stale = false;   // all counters zero, hot bitmap zero
+    s->unique_valid = true;
     s->n_unique = 0;
     return KV_OK;
 }
@@ -464,7 +466,7 @@ extern "C" int kv_sketch_write_table(kv_sketch *s, int t, const uint8_t *host_in
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(s->flat + s->toff[t], host_in, nbytes, cudaMemcpyHostToDevice, ctx->compute));
-    KV_TRY(kv_state_rebuild_locked(ctx, s));
+    s->state_stale = true;
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -598,7 +600,7 @@ extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int
     }
     fclose(f);
     if (rc != KV_OK) { cudaFree(s->flat); cudaFree(s->state); cudaFree(s->d_unique); delete s; return rc; }
-    KV_TRY(kv_state_rebuild_locked(ctx, s));
+    s->state_stale = true;
     (void)occ;   // recomputed from table 0 whenever it is asked for
     *out = s;
     return KV_OK;
@@ -809,6 +811,10 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
 {
     if (!n) return KV_OK;
     KvView v = kv_view(s);
+    if (s->state_stale) {
+        KV_TRY(kv_state_rebuild_locked(ctx, s));
+        s->state_stale = false;
+    }
     if (s->track_unique) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n));
     else s->unique_valid = false;
     // large counter sketches: region-partitioned updates (tables must index with 32 bits, <= 4 tables)
@@ -1143,7 +1149,7 @@ extern "C" int kv_sketch_narrow(kv_sketch *s, const void *dev_in)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     LAUNCH_C(KV_PROF_MERGE, ctx, kv_narrow_kernel, kv_grid_for(ctx, s->flat_bytes, 16), 256, s->flat, s->flat_bytes, s->bits, dev_in);
-    KV_TRY(kv_state_rebuild_locked(ctx, s));
+    s->state_stale = true;
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -1174,7 +1180,7 @@ extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat,
     for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)((const uint8_t *)peer_flat[i] + byte_lo);
     uint64_t n_vec = (byte_hi - byte_lo) / 16;
     LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
-    if (byte_lo == 0 && byte_hi == s->flat_bytes) KV_TRY(kv_state_rebuild_locked(ctx, s));   // sliced merges: rebuilt after the gather phase
+    s->state_stale = true;
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
@@ -1191,7 +1197,7 @@ extern "C" int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uin
     CU(cudaSetDevice(s->device));
     CU(cudaMemcpyAsync(s->flat + byte_lo, (const uint8_t *)peer_flat + byte_lo, byte_hi - byte_lo,
                        cudaMemcpyDeviceToDevice, ctx->compute));
-    KV_TRY(kv_state_rebuild_locked(ctx, s));
+    s->state_stale = true;
     CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
