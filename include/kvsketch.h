@@ -211,6 +211,10 @@ int kv_sync(int device);
 #define KV_PROF_CLASSES 8
 int kv_profile(int device, int enable, double *ms_out, uint64_t *n_out);
 
+/* How many chunks had to be rolled back and redone with the exact update path because the
+ * speculative pass saw a counter overflow (diagnostics; tests assert the path is exercised). */
+int kv_redo_count(int device, uint64_t *n);
+
 /* Number of kernels this library has launched on `device` since load (bench accounting). */
 int kv_launch_count(int device, uint64_t *n);
 

@@ -76,6 +76,7 @@ SYMBOLS = [
     ('kv_stream', c_int, [c_int, POINTER(_P)]),
     ('kv_sync', c_int, [c_int]),
     ('kv_launch_count', c_int, [c_int, POINTER(c_uint64)]),
+    ('kv_redo_count', c_int, [c_int, POINTER(c_uint64)]),
     ('kv_profile', c_int, [c_int, c_int, POINTER(ctypes.c_double), POINTER(c_uint64)]),
 ]
 
@@ -165,6 +166,13 @@ def profile(enable, device=None):
     n = (c_uint64 * len(PROF_CLASSES))()
     check(lib().kv_profile(current_device() if device is None else device, int(enable), ms, n))
     return {name: (ms[i], n[i]) for i, name in enumerate(PROF_CLASSES)}
+
+
+def redo_count(device=None):
+    """Chunks rolled back and redone exactly after a speculative counter overflow."""
+    n = c_uint64()
+    check(lib().kv_redo_count(current_device() if device is None else device, byref(n)))
+    return n.value
 
 
 def as_u8(a):

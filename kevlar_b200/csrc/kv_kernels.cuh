@@ -123,9 +123,10 @@ template <int BITS, bool HAS_VALID, bool EXACT>
 __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
                                                            const uint32_t *__restrict__ valid, uint64_t total,
                                                            uint32_t *__restrict__ added, uint64_t added_stride,
-                                                           unsigned *dirty)
+                                                           unsigned *dirty, unsigned long long *n_redone)
 {
     if (EXACT && *dirty == 0) return;   // redo pass of a clean chunk
+    if (EXACT && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_redone, 1ULL);
     const unsigned maxv = BITS == 8 ? 255u : 15u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
@@ -437,9 +438,10 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
 template <int BITS, int MODE>
 __global__ void __launch_bounds__(256) kv_part_apply_kernel(KvView v, const uint32_t *__restrict__ items,
                                                             const uint32_t *__restrict__ meta, uint32_t *__restrict__ added,
-                                                            unsigned *dirty)
+                                                            unsigned *dirty, unsigned long long *n_redone)
 {
     if (MODE != 0 && *dirty == 0) return;
+    if (MODE == 2 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_redone, 1ULL);
     const unsigned maxv = BITS == 8 ? 255u : 15u;
     const uint64_t n = meta[0];
     // each CTA iteration covers 4 consecutive groups of 256 items; a thread owns one item in each

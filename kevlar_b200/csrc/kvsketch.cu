@@ -89,7 +89,7 @@ struct KvCtx {
     int part_region_log2 = 24;                // buckets per region (8-bit: 16 MB)
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
-    unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied
+    unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied  [5] redone chunks
     unsigned long long *h_counters = nullptr; // pinned mirror
     uint8_t *h_stage = nullptr;               // pinned staging for sketch file I/O (lazily allocated)
     uint64_t launches = 0;
@@ -711,8 +711,9 @@ static int kv_launch_increment(KvCtx *ctx, const KvView &v, uint64_t flat_bytes,
         }
         dirty = ctx->dirty + ctx->dirty_next++;
     }
-#define KV_INC(CLS_, VALID_, EXACT_)                                                                              \
-    LAUNCH_C(CLS_, ctx, (kv_increment_kernel<BITS, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, added, stride, dirty)
+#define KV_INC(CLS_, VALID_, EXACT_)                                                                                  \
+    LAUNCH_C(CLS_, ctx, (kv_increment_kernel<BITS, VALID_, EXACT_>), grid, 256, v, d_hashes, d_valid, n, added, stride, dirty, \
+             ctx->counters + 5)
     kv_l2_window(ctx, v.tab[0], flat_bytes);
     if (d_valid) KV_INC(KV_PROF_INCREMENT, true, false); else KV_INC(KV_PROF_INCREMENT, false, false);
     if (BITS != 1) {
@@ -767,9 +768,9 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
     KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_scatter_kernel, grid, 256, (size_t)P * 4, v, pi, d_hashes, d_valid,
                           n, slice, rows, runbase, items));
     const unsigned agrid = kv_grid_for(ctx, max_items);
-    LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_part_apply_kernel<BITS, 0>), agrid, 256, v, items, meta, added, dirty);
-    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 1>), agrid, 256, v, items, meta, added, dirty);
-    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 2>), agrid, 256, v, items, meta, added, dirty);
+    LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_part_apply_kernel<BITS, 0>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
+    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 1>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
+    LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 2>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
     return KV_OK;
 }
 
@@ -1276,6 +1277,18 @@ extern "C" int kv_profile(int device, int enable, double *ms_out, uint64_t *n_ou
         if (enable != 2) { ctx->prof_ms[c] = 0; ctx->prof_n[c] = 0; }   // 2 = read without resetting
     }
     if (enable != 2) ctx->profiling = enable != 0;
+    return KV_OK;
+}
+
+extern "C" int kv_redo_count(int device, uint64_t *n)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpyAsync(ctx->h_counters + 5, ctx->counters + 5, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (n) *n = ctx->h_counters[5];
     return KV_OK;
 }
 

@@ -199,10 +199,14 @@ def test_consume_saturation(kv, oracle, name):
     bases, offs = oracle.reads_to_batch(reads)
     g = getattr(kv.khmer, name)(21, 500, 4)
     c = getattr(oracle, name)(21, 500, 4)
+    redone = kv._lib.redo_count()
     assert g.consume_batch(bases, offs) == c.consume_batch(bases, offs)
     assert_same_sketch(g, c)
     top = 15 if name.startswith('Small') else 255
     assert g.get('ACGTTGCAAGGCTTAACCGGT') == top
+    # > 1000 concurrent adds per bucket overflow the speculative path: the chunk must have been
+    # rolled back and redone exactly (this is what makes the optimistic update safe)
+    assert kv._lib.redo_count() > redone
 
 
 @pytest.mark.parametrize('name', ['Counttable', 'Nodegraph'])
