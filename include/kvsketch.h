@@ -171,7 +171,8 @@ int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, const uint64_
  * [byte_lo, byte_hi) of n_peers flat tables into this sketch (multiples of 256; hi = 0 means
  * the whole table).  With each rank merging only its own 1/N slice and then pulling the
  * finished slices of its peers with kv_sketch_copy_from_peer, this is a reduce-scatter +
- * all-gather made of plain NVLink loads, with no staging copy. */
+ * all-gather made of plain NVLink loads, with no staging copy.  Both calls are asynchronous
+ * (kv_sync before telling the peers that the data may be read / overwritten). */
 int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, int *elem_bytes);
 int kv_sketch_narrow(kv_sketch *s, const void *dev_in);
 int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi);

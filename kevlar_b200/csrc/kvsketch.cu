@@ -1182,7 +1182,6 @@ extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat,
     uint64_t n_vec = (byte_hi - byte_lo) / 16;
     LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
     s->state_stale = true;
-    CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
 }
@@ -1199,7 +1198,6 @@ extern "C" int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uin
     CU(cudaMemcpyAsync(s->flat + byte_lo, (const uint8_t *)peer_flat + byte_lo, byte_hi - byte_lo,
                        cudaMemcpyDeviceToDevice, ctx->compute));
     s->state_stale = true;
-    CU(cudaStreamSynchronize(ctx->compute));
     s->unique_valid = false;
     return KV_OK;
 }

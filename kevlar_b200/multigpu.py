@@ -108,6 +108,7 @@ class GpuSketchAdapter(object):
             group = tensors[i:i + 8]
             ptrs = (c_void_p * len(group))(*[t.data_ptr() for t in group])
             check(lib().kv_sketch_merge_peers(self.sketch._h, ptrs, len(group), 0, 0))
+        _lib.sync(self.sketch.device)
 
 
 def merge_allreduce(adapter, group=None):
@@ -192,12 +193,14 @@ def merge_p2p(sketches, group=None):
             grp = order[i:i + 8]
             ptrs = (c_void_p * len(grp))(*[p.value for p in grp])
             check(lib().kv_sketch_merge_peers(sk._h, ptrs, len(grp), lo, hi))
+    _lib.sync(sketches[0].device)
     td.barrier(group=group)                           # every slice is reduced
     for sk, pr in zip(sketches, peers):
         _, nbytes = sk.flat_device_buffer()
         for r in sorted(pr):
             plo, phi = slice_bounds(nbytes, r, world)
             check(lib().kv_sketch_copy_from_peer(sk._h, pr[r], plo, phi))
+    _lib.sync(sketches[0].device)
     td.barrier(group=group)                           # nobody still reads my table
 
 
