@@ -721,3 +721,58 @@ def test_partitioned_update_path_is_exact():
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
     assert res.returncode == 0, res.stdout[-3000:]
     assert ' passed' in res.stdout
+
+
+def test_khmer_namespace_drop_in(kv, tmp_path):
+    """INTEGRATION.md route 1: code written against the `khmer` namespace the way the reference
+    uses it -- threads sharing one ReadParser into consume_seqfile, then one get() per k-mer per
+    sample (kevlar/count.py:40-77, kevlar/novel.py:134-162) -- runs on kevlar_b200.khmer and
+    reproduces the golden sketch and the golden novel output."""
+    import sys
+    import threading
+    saved = {name: sys.modules.get(name) for name in ('khmer', 'khmer.khmer_args')}
+    sys.modules['khmer'] = kv.khmer
+    sys.modules['khmer.khmer_args'] = kv.khmer.khmer_args
+    try:
+        import khmer
+        from khmer import khmer_args
+        assert khmer_args.memory_setting('10K') == 1e4
+        # --- count, reference style
+        tablesize = khmer_args.memory_setting('10K') / 4 * khmer._buckets_per_byte['countgraph']
+        sketch = khmer.Counttable(25, tablesize, 4)
+        parser = khmer.ReadParser(golden_data('simple-genome-case-reads.fa.gz'))
+        workers = [threading.Thread(target=sketch.consume_seqfile, args=(parser,)) for _ in range(2)]
+        [w.start() for w in workers]
+        [w.join() for w in workers]
+        assert parser.num_reads == 600
+        out = str(tmp_path / 'case.ct')
+        sketch.save(out)
+        assert filecmp.cmp(out, golden_data('simple-genome-case.ct'), shallow=False)
+        fpr = (sketch.n_occupied() / min(sketch.hashsizes())) ** len(sketch.hashsizes())
+        assert '{:1.3f}'.format(fpr) == '0.011'
+        # --- novel, reference style: per read, per k-mer, per sample
+        cases = [khmer.Counttable.load(golden_data('simple-genome-case.ct'))]
+        ctrls = [khmer.Counttable.load(golden_data('simple-genome-ctrl{}.ct'.format(i))) for i in (1, 2)]
+        lines = []
+        for fn in ('simple-genome-case-reads.fa.gz', 'ambig.fasta'):
+            for record in khmer.ReadParser(golden_data(fn)):
+                if len(record.sequence) < 25 or re.search('[^ACGT]', record.sequence):
+                    continue
+                annots = []
+                for i, kmer in enumerate(cases[0].get_kmers(record.sequence)):
+                    abunds = [ct.get(kmer) for ct in cases]
+                    if min(abunds) < 6:
+                        continue
+                    cab = [ct.get(kmer) for ct in ctrls]
+                    if max(cab) > 1:
+                        continue
+                    annots.append(' ' * i + kmer + ' ' * 10 + ' '.join(str(a) for a in abunds + cab) + '#')
+                if annots:
+                    lines += ['>' + record.name, record.sequence] + annots
+        assert '\n'.join(lines) + '\n' == open(golden_gen('novel_load_counts.out')).read()
+    finally:
+        for name, mod in saved.items():
+            if mod is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = mod
