@@ -331,12 +331,27 @@ struct KvPartInfo {
 // b produces, after kv_part_rowscan_kernel the number produced before it inside the run.
 #define KV_PART_WARPS 8
 
+// lanes of the warp that hold the same key (and are live): one ballot per key bit.  The hardware
+// MATCH.ANY does the same job but measured several hundred cycles per call here with ~25
+// distinct keys per warp (profiles/r01_notes.md).
+__device__ __forceinline__ unsigned kv_warp_peers(uint32_t key, bool live, int nbits)
+{
+    unsigned peers = __ballot_sync(0xffffffffu, live);
+    for (int b = 0; b < nbits; b++) {
+        const bool bit = (key >> b) & 1u;
+        const unsigned vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return live ? peers : 0u;
+}
+
 __global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
                                                            const uint32_t *__restrict__ valid, uint64_t total, uint64_t slice,
                                                            uint32_t *__restrict__ rows)
 {
     extern __shared__ uint32_t sm_cnt[];
     const int P = (int)pi.pbase[v.n_tables];
+    const int nbits = 32 - __clz(P - 1 > 0 ? P - 1 : 1);
     for (int q = threadIdx.x; q < KV_PART_WARPS * P; q += blockDim.x) sm_cnt[q] = 0;
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
@@ -347,8 +362,8 @@ __global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo 
         const bool live = g < hi && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
         const uint64_t h = live ? __ldcs(hashes + g) : 0;
         for (int t = 0; t < v.n_tables; t++) {
-            const uint32_t run = live ? pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(0xffffffffu, run);
+            const uint32_t run = live ? pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb) : 0u;
+            const unsigned peers = kv_warp_peers(run, live, nbits);
             if (live && lane == (unsigned)(__ffs(peers) - 1)) mine[run] += (uint32_t)__popc(peers);
         }
         __syncwarp();
@@ -428,6 +443,7 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
 {
     extern __shared__ uint32_t sm_cur[];
     const int P = (int)pi.pbase[v.n_tables];
+    const int nbits = 32 - __clz(P - 1 > 0 ? P - 1 : 1);
     for (int idx = threadIdx.x; idx < KV_PART_WARPS * P; idx += blockDim.x) {
         const int w = idx / P, q = idx - w * P;
         sm_cur[idx] = runbase[q] + rows[((size_t)q * gridDim.x + blockIdx.x) * KV_PART_WARPS + w];
@@ -442,9 +458,9 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
         const uint64_t h = live ? __ldcs(hashes + g) : 0;
         for (int t = 0; t < v.n_tables; t++) {
             const uint32_t bin = live ? (uint32_t)kv_mod(h, v.size[t], v.magic[t]) : 0u;
-            const uint32_t run = live ? pi.pbase[t] + (bin >> pi.rb) : 0xffffffffu;
-            const unsigned peers = __match_any_sync(0xffffffffu, run);
-            const int leader = __ffs(peers) - 1;
+            const uint32_t run = live ? pi.pbase[t] + (bin >> pi.rb) : 0u;
+            const unsigned peers = kv_warp_peers(run, live, nbits);
+            const int leader = live ? __ffs(peers) - 1 : (int)lane;
             uint32_t slot = 0;
             if (live && (int)lane == leader) {
                 slot = mine[run];
