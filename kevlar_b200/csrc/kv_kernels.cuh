@@ -316,104 +316,68 @@ __global__ void kv_expand_bits_kernel(const uint32_t *__restrict__ valid, uint64
 //            16 MB region, which therefore stays L2- and TLB-resident while it is hit; same
 //            speculative / exact update logic, rollback and redo as the direct kernel.
 
-#define KV_PART_MAX 1024        // (table, region) runs: 8 warps x 1024 private counters = 32 KB of shared memory
+#define KV_PART_MAX 4096        // (table, region) runs
 
 struct KvPartInfo {
     int rb;                        // log2(buckets per region)
     uint32_t pbase[KV_TABLES_DEV + 1];   // first run of table t; pbase[n_tables] = number of runs
 };
 
-// CTA b owns positions [b*slice, (b+1)*slice) in BOTH hist and scatter, and inside the CTA warp w
-// owns the same positions in both.  Every warp keeps PRIVATE run counters in shared memory: the
-// lanes of a warp that feed the same run are found with __match_any_sync and their leader does
-// a plain read-modify-write, so neither pass needs a single atomic and the item layout is
-// deterministic.  rows[(run * G + b) * 8 + w] first holds how many items of `run` warp w of CTA
-// b produces, after kv_part_rowscan_kernel the number produced before it inside the run.
-#define KV_PART_WARPS 8
-
-// lanes of the warp that hold the same key (and are live): one ballot per key bit.  The hardware
-// MATCH.ANY does the same job but measured several hundred cycles per call here with ~25
-// distinct keys per warp (profiles/r01_notes.md).
-__device__ __forceinline__ unsigned kv_warp_peers(uint32_t key, bool live, int nbits)
-{
-    unsigned peers = __ballot_sync(0xffffffffu, live);
-    for (int b = 0; b < nbits; b++) {
-        const bool bit = (key >> b) & 1u;
-        const unsigned vote = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? vote : ~vote;
-    }
-    return live ? peers : 0u;
-}
-
+// CTA b owns positions [b*slice, (b+1)*slice) in BOTH hist and scatter.  rows[run * G + b] first
+// holds how many items of `run` CTA b produces, after kv_part_rowscan_kernel the number produced
+// by CTAs before b (exclusive prefix inside the run).
 __global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
                                                            const uint32_t *__restrict__ valid, uint64_t total, uint64_t slice,
                                                            uint32_t *__restrict__ rows)
 {
     extern __shared__ uint32_t sm_cnt[];
     const int P = (int)pi.pbase[v.n_tables];
-    const int nbits = 32 - __clz(P - 1 > 0 ? P - 1 : 1);
-    for (int q = threadIdx.x; q < KV_PART_WARPS * P; q += blockDim.x) sm_cnt[q] = 0;
+    for (int q = threadIdx.x; q < P; q += blockDim.x) sm_cnt[q] = 0;
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
-    const unsigned lane = threadIdx.x & 31;
-    uint32_t *mine = sm_cnt + (threadIdx.x >> 5) * P;
-    for (uint64_t g0 = lo; g0 < hi; g0 += blockDim.x) {     // slice is a multiple of 32: whole warps stay together
+    for (uint64_t g0 = lo; g0 < hi; g0 += blockDim.x) {
         const uint64_t g = g0 + threadIdx.x;
         const bool live = g < hi && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
         const uint64_t h = live ? __ldcs(hashes + g) : 0;
-        for (int t = 0; t < v.n_tables; t++) {
-            const uint32_t run = live ? pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb) : 0u;
-            const unsigned peers = kv_warp_peers(run, live, nbits);
-            if (live && lane == (unsigned)(__ffs(peers) - 1)) mine[run] += (uint32_t)__popc(peers);
-        }
-        __syncwarp();
+        if (live)
+            for (int t = 0; t < v.n_tables; t++)
+                atomicAdd(&sm_cnt[pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb)], 1u);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < KV_PART_WARPS * P; idx += blockDim.x) {
-        const int w = idx / P, q = idx - w * P;
-        rows[((size_t)q * gridDim.x + blockIdx.x) * KV_PART_WARPS + w] = sm_cnt[idx];
-    }
+    for (int q = threadIdx.x; q < P; q += blockDim.x) rows[(size_t)q * gridDim.x + blockIdx.x] = sm_cnt[q];
 }
 
-// one CTA per run: exclusive scan of its n per-warp counts (n = G * 8), run total to runsum[run]
-__global__ void __launch_bounds__(256) kv_part_rowscan_kernel(uint32_t *__restrict__ rows, int n, uint32_t *__restrict__ runsum)
+// one CTA per run: exclusive scan of its G per-CTA counts, run total to runsum[run]  (G <= 2048)
+__global__ void __launch_bounds__(256) kv_part_rowscan_kernel(uint32_t *__restrict__ rows, int G, uint32_t *__restrict__ runsum)
 {
     __shared__ uint32_t warp_tot[8];
-    __shared__ uint32_t carry;
-    uint32_t *row = rows + (size_t)blockIdx.x * n;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += 2048) {
-        uint32_t val[8], mine = 0;
+    uint32_t *row = rows + (size_t)blockIdx.x * G;
+    uint32_t val[8], mine = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int i = base + threadIdx.x * 8 + j;
-            val[j] = i < n ? row[i] : 0u;
-            mine += val[j];
-        }
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
-        }
-        if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
-        uint32_t before = carry;
-        for (int w = 0; w < wid; w++) before += warp_tot[w];
-        uint32_t run = before + incl - mine;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int i = base + threadIdx.x * 8 + j;
-            if (i < n) row[i] = run;
-            run += val[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 255) carry = before + incl;
-        __syncthreads();
+    for (int j = 0; j < 8; j++) {
+        int i = threadIdx.x * 8 + j;
+        val[j] = i < G ? row[i] : 0u;
+        mine += val[j];
     }
-    if (threadIdx.x == 0) runsum[blockIdx.x] = carry;
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < wid; w++) before += warp_tot[w];
+    uint32_t run = before + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int i = threadIdx.x * 8 + j;
+        if (i < G) row[i] = run;
+        run += val[j];
+    }
+    if (threadIdx.x == 255) runsum[blockIdx.x] = before + incl;
 }
 
 // meta[0] = number of items, meta[1 + t] = index of the first item of table t (t <= n_tables)
@@ -433,8 +397,9 @@ __global__ void kv_part_scan_kernel(KvPartInfo pi, int n_tables, const uint32_t 
     meta[0] = run;
 }
 
-// Each warp re-walks its positions with a private cursor per run that hands out absolute item
-// slots: the items a warp sends to one run are written next to each other, in position order.
+// Each CTA re-walks its slice; a shared-memory cursor per run hands out absolute item slots, so
+// the CTA's items of one run are written next to each other (L2 merges them into full sectors)
+// and no global atomic is needed.
 __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartInfo pi, const uint64_t *__restrict__ hashes,
                                                               const uint32_t *__restrict__ valid, uint64_t total,
                                                               uint64_t slice, const uint32_t *__restrict__ rows,
@@ -443,33 +408,18 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
 {
     extern __shared__ uint32_t sm_cur[];
     const int P = (int)pi.pbase[v.n_tables];
-    const int nbits = 32 - __clz(P - 1 > 0 ? P - 1 : 1);
-    for (int idx = threadIdx.x; idx < KV_PART_WARPS * P; idx += blockDim.x) {
-        const int w = idx / P, q = idx - w * P;
-        sm_cur[idx] = runbase[q] + rows[((size_t)q * gridDim.x + blockIdx.x) * KV_PART_WARPS + w];
-    }
+    for (int q = threadIdx.x; q < P; q += blockDim.x) sm_cur[q] = runbase[q] + rows[(size_t)q * gridDim.x + blockIdx.x];
     __syncthreads();
     const uint64_t lo = (uint64_t)blockIdx.x * slice, hi = lo + slice < total ? lo + slice : total;
-    const unsigned lane = threadIdx.x & 31;
-    uint32_t *mine = sm_cur + (threadIdx.x >> 5) * P;
     for (uint64_t g0 = lo; g0 < hi; g0 += blockDim.x) {
         const uint64_t g = g0 + threadIdx.x;
         const bool live = g < hi && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
         const uint64_t h = live ? __ldcs(hashes + g) : 0;
-        for (int t = 0; t < v.n_tables; t++) {
-            const uint32_t bin = live ? (uint32_t)kv_mod(h, v.size[t], v.magic[t]) : 0u;
-            const uint32_t run = live ? pi.pbase[t] + (bin >> pi.rb) : 0u;
-            const unsigned peers = kv_warp_peers(run, live, nbits);
-            const int leader = live ? __ffs(peers) - 1 : (int)lane;
-            uint32_t slot = 0;
-            if (live && (int)lane == leader) {
-                slot = mine[run];
-                mine[run] = slot + (uint32_t)__popc(peers);
+        if (live)
+            for (int t = 0; t < v.n_tables; t++) {
+                const uint32_t bin = (uint32_t)kv_mod(h, v.size[t], v.magic[t]);
+                items[atomicAdd(&sm_cur[pi.pbase[t] + (bin >> pi.rb)], 1u)] = bin;
             }
-            slot = __shfl_sync(0xffffffffu, slot, leader);
-            if (live) items[slot + __popc(peers & ((1u << lane) - 1u))] = bin;
-        }
-        __syncwarp();
     }
 }
 

@@ -751,9 +751,9 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
     const unsigned grid = kv_grid_for(ctx, n);                       // <= 8 CTAs per SM
     const uint64_t slice = (((n + grid - 1) / grid) + 31) & ~(uint64_t)31;   // positions per CTA
     KV_TRY(kv_buf_ensure(ctx->part_items, max_items * 4));
-    KV_TRY(kv_buf_ensure(ctx->part_small, ((size_t)P * grid * KV_PART_WARPS + 2 * (size_t)P + 16) * 4));
+    KV_TRY(kv_buf_ensure(ctx->part_small, ((size_t)P * grid + 2 * (size_t)P + 16) * 4));
     KV_TRY(kv_buf_ensure(ctx->added, (max_items / 32 + 64) * 4));
-    uint32_t *rows = (uint32_t *)ctx->part_small.p, *runsum = rows + (size_t)P * grid * KV_PART_WARPS, *runbase = runsum + P,
+    uint32_t *rows = (uint32_t *)ctx->part_small.p, *runsum = rows + (size_t)P * grid, *runbase = runsum + P,
              *meta = runbase + P;
     uint32_t *items = (uint32_t *)ctx->part_items.p, *added = (uint32_t *)ctx->added.p;
     if (ctx->dirty_next == 64) {
@@ -761,12 +761,12 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
         ctx->dirty_next = 0;
     }
     unsigned *dirty = ctx->dirty + ctx->dirty_next++;
-    KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_hist_kernel, grid, 256, (size_t)P * 4 * KV_PART_WARPS, v, pi, d_hashes,
-                          d_valid, n, slice, rows));
-    LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_rowscan_kernel, (unsigned)P, 256, rows, (int)(grid * KV_PART_WARPS), runsum);
+    KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_hist_kernel, grid, 256, (size_t)P * 4, v, pi, d_hashes, d_valid, n,
+                          slice, rows));
+    LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_rowscan_kernel, (unsigned)P, 256, rows, (int)grid, runsum);
     LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_scan_kernel, 1, 32, pi, v.n_tables, runsum, runbase, meta);
-    KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_scatter_kernel, grid, 256, (size_t)P * 4 * KV_PART_WARPS, v, pi,
-                          d_hashes, d_valid, n, slice, rows, runbase, items));
+    KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_scatter_kernel, grid, 256, (size_t)P * 4, v, pi, d_hashes, d_valid,
+                          n, slice, rows, runbase, items));
     const unsigned agrid = kv_grid_for(ctx, max_items);
     LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_part_apply_kernel<BITS, 0>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
     LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 1>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
