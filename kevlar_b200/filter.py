@@ -98,22 +98,23 @@ def second_pass(reads, counts, casemin, ctrlmax, timer):
     kevlar_b200.plog('[kevlar::filter]', message)
 
 
+def _records(readfile):
+    return kevlar_b200.parse_augmented_fastx(kevlar_b200.open(readfile, 'r'))
+
+
 def filter(readfile, mask=None, memory=1e6, maxfpr=0.01, casemin=6, ctrlmax=1):
-    timer = kevlar_b200.Timer()
-    timer.start()
-    reader = kevlar_b200.parse_augmented_fastx(kevlar_b200.open(readfile, 'r'))
-    counts = first_pass(reader, mask, memory, timer)
+    """Generator over the reads of `readfile` that keep at least one k-mer after the recount."""
+    clock = kevlar_b200.Timer()
+    clock.start()
+    counts = first_pass(_records(readfile), mask, memory, clock)
     check_fpr(counts, maxfpr)
-    reader = kevlar_b200.parse_augmented_fastx(kevlar_b200.open(readfile, 'r'))
-    for read in second_pass(reader, counts, casemin, ctrlmax, timer):
-        yield read
-    kevlar_b200.plog('[kevlar::filter]', 'Total time: {:.2f} seconds'.format(timer.stop()))
+    yield from second_pass(_records(readfile), counts, casemin, ctrlmax, clock)
+    kevlar_b200.plog('[kevlar::filter]', 'Total time: {:.2f} seconds'.format(clock.stop()))
 
 
 def main(args):
     mask = kevlar_b200.sketch.load(args.mask)
     outstream = kevlar_b200.open(args.out, 'w')
-    filterstream = filter(args.augfastq, mask=mask, memory=args.memory, maxfpr=args.max_fpr,
-                          casemin=args.case_min, ctrlmax=args.ctrl_max)
-    for record in filterstream:
+    for record in filter(args.augfastq, mask=mask, memory=args.memory, maxfpr=args.max_fpr,
+                         casemin=args.case_min, ctrlmax=args.ctrl_max):
         kevlar_b200.print_augmented_fastx(record, outstream)

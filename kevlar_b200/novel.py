@@ -39,30 +39,28 @@ def kmer_is_interesting(kmer, casecounts, controlcounts, case_min=5, ctrl_max=1,
 
 def load_samples(counttables=None, filelists=None, ksize=31, memory=1e6, maxfpr=0.2, numbands=None, band=None,
                  numthreads=1, outfilelist=None):
-    """Sketches for a list of samples: loaded from files if given, else counted from reads --
-    always into 8-bit Counttables (kevlar/novel.py:56-77)."""
+    """One sketch per sample: read from `counttables` when given (any reads are then ignored),
+    otherwise counted from the files in `filelists` -- always into 8-bit Counttables
+    (kevlar/novel.py:56-77) -- and optionally saved to `outfilelist`."""
     assert counttables or filelists
     if counttables:
-        message = 'counttables for {:d} sample(s) provided'.format(len(counttables))
-        message += ', any corresponding FASTA/FASTQ input will be ignored for computing k-mer abundances'
-        kevlar_b200.plog('[kevlar::novel]    INFO:', message)
+        kevlar_b200.plog('[kevlar::novel]    INFO:',
+                         'counttables for {:d} sample(s) provided, any corresponding FASTA/FASTQ input will be '
+                         'ignored for computing k-mer abundances'.format(len(counttables)))
         return kevlar_b200.sketch.load_sketchfiles(counttables, maxfpr)
-    samples = [
-        kevlar_b200.count.load_sample_seqfile(filelist, ksize, memory, maxfpr=maxfpr, numbands=numbands, band=band,
-                                              numthreads=numthreads)
-        for filelist in filelists
-    ]
+    counting = dict(maxfpr=maxfpr, numbands=numbands, band=band, numthreads=numthreads)
+    samples = [kevlar_b200.count.load_sample_seqfile(files, ksize, memory, **counting) for files in filelists]
     if outfilelist:
         save_counts(outfilelist, samples)
     return samples
 
 
 def save_counts(filelist, tablelist):
+    """Write each sample's sketch; refuses (with a warning) when the counts do not line up."""
     if len(filelist) != len(tablelist):
-        message = 'number of filenames provided ({:d})'.format(len(filelist))
-        message += 'does not match the number of samples provided ({:d})'.format(len(tablelist))
-        message += '; stubbornly refusing to save k-mer counts'
-        kevlar_b200.plog('[kevlar::novel] WARNING:', message)
+        kevlar_b200.plog('[kevlar::novel] WARNING:',
+                         'number of filenames provided ({:d})does not match the number of samples provided ({:d}); '
+                         'stubbornly refusing to save k-mer counts'.format(len(filelist), len(tablelist)))
         return
     for outfile, counttable in zip(filelist, tablelist):
         if not outfile.endswith(('.ct', '.counttable')):
@@ -184,40 +182,34 @@ def novel(casestream, casecounts, controlcounts, ksize=31, abundscreen=None, cas
 
 
 def main(args):
-    timer = kevlar_b200.Timer()
-    timer.start()
+    clock = kevlar_b200.Timer()
+    clock.start()
     if (not args.num_bands) is not (not args.band):
         raise ValueError('Must specify --num-bands and --band together')
-    myband = args.band - 1 if args.band else None
+    band = args.band - 1 if args.band else None   # 1-based on the command line
+    shared = (args.ksize, args.memory, args.max_fpr, args.num_bands, band, args.threads)
 
-    timer.start('loadall')
-    kevlar_b200.plog('[kevlar::novel] Loading control samples')
-    timer.start('loadctrl')
-    controls = load_samples(args.control_counts, args.control, args.ksize, args.memory, args.max_fpr,
-                            args.num_bands, myband, args.threads, args.save_ctrl_counts)
-    elapsed = timer.stop('loadctrl')
-    kevlar_b200.plog('[kevlar::novel]', 'Control samples loaded in {:.2f} sec'.format(elapsed))
+    def load(what, key, sketchfiles, readfiles, savefiles, done):
+        kevlar_b200.plog('[kevlar::novel] Loading {} samples'.format(what))
+        clock.start(key)
+        sketches = load_samples(sketchfiles, readfiles, *shared, savefiles)
+        kevlar_b200.plog(done.format(clock.stop(key)))
+        return sketches
 
-    kevlar_b200.plog('[kevlar::novel] Loading case samples')
-    timer.start('loadcases')
-    cases = load_samples(args.case_counts, args.case, args.ksize, args.memory, args.max_fpr, args.num_bands,
-                         myband, args.threads, args.save_case_counts)
-    elapsed = timer.stop('loadcases')
-    kevlar_b200.plog('[kevlar::novel] Case samples loaded in {:.2f} sec'.format(elapsed))
-    elapsed = timer.stop('loadall')
-    kevlar_b200.plog('[kevlar::novel] All samples loaded in {:.2f} sec'.format(elapsed))
+    clock.start('loadall')
+    controls = load('control', 'loadctrl', args.control_counts, args.control, args.save_ctrl_counts,
+                    '[kevlar::novel] Control samples loaded in {:.2f} sec')
+    cases = load('case', 'loadcases', args.case_counts, args.case, args.save_case_counts,
+                 '[kevlar::novel] Case samples loaded in {:.2f} sec')
+    kevlar_b200.plog('[kevlar::novel] All samples loaded in {:.2f} sec'.format(clock.stop('loadall')))
 
-    timer.start('iter')
-    message = 'Iterating over reads from {:d} case sample(s)'.format(len(args.case))
-    kevlar_b200.plog('[kevlar::novel]', message)
+    clock.start('iter')
+    kevlar_b200.plog('[kevlar::novel]', 'Iterating over reads from {:d} case sample(s)'.format(len(args.case)))
     outstream = kevlar_b200.open(args.out, 'w')
-    caserecords = ReadBatches(f for filelist in args.case for f in filelist)
-    readstream = novel(caserecords, cases, controls, ksize=args.ksize, abundscreen=args.abund_screen,
-                       casemin=args.case_min, ctrlmax=args.ctrl_max, numbands=args.num_bands, band=myband,
-                       skipuntil=args.skip_until)
-    for augmented_read in readstream:
-        kevlar_b200.print_augmented_fastx(augmented_read, outstream)
-
-    elapsed = timer.stop('iter')
-    kevlar_b200.plog('[kevlar::novel]', 'Iterated over all case reads in {:.2f} seconds'.format(elapsed))
-    kevlar_b200.plog('[kevlar::novel]', 'Total time: {:.2f} seconds'.format(timer.stop()))
+    casereads = ReadBatches(f for filelist in args.case for f in filelist)
+    for annotated in novel(casereads, cases, controls, ksize=args.ksize, abundscreen=args.abund_screen,
+                           casemin=args.case_min, ctrlmax=args.ctrl_max, numbands=args.num_bands, band=band,
+                           skipuntil=args.skip_until):
+        kevlar_b200.print_augmented_fastx(annotated, outstream)
+    kevlar_b200.plog('[kevlar::novel]', 'Iterated over all case reads in {:.2f} seconds'.format(clock.stop('iter')))
+    kevlar_b200.plog('[kevlar::novel]', 'Total time: {:.2f} seconds'.format(clock.stop()))

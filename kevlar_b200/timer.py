@@ -1,31 +1,32 @@
-"""Keyed wall-clock timers (mirrors kevlar/timer.py:13-39)."""
+"""Named stopwatches for the log lines (same behaviour as kevlar/timer.py:13-39)."""
 import time
+
+_DEFAULT = ''
 
 
 class Timer(object):
-    def __init__(self):
-        self._started = {}
-        self._stopped = {}
+    """`start(key)` / `stop(key)` / `probe(key)`; the unnamed stopwatch is the key ''."""
 
-    @staticmethod
-    def _key(key):
-        return '' if key is None else key
+    def __init__(self):
+        self._began = {}
+        self._ended = {}
+
+    def _require(self, key):
+        key = _DEFAULT if key is None else key
+        if key not in self._began:
+            raise ValueError('No timer started for "{}"'.format(key))
+        return key
 
     def start(self, key=None):
-        key = self._key(key)
-        if key in self._started:
-            raise ValueError('Timer already started for "' + key + '"')
-        self._started[key] = time.time()
+        key = _DEFAULT if key is None else key
+        if key in self._began:
+            raise ValueError('Timer already started for "{}"'.format(key))
+        self._began[key] = time.time()
 
     def stop(self, key=None):
-        key = self._key(key)
-        if key not in self._started:
-            raise ValueError('No timer started for "' + key + '"')
-        self._stopped[key] = time.time()
-        return self._stopped[key] - self._started[key]
+        key = self._require(key)
+        self._ended[key] = now = time.time()
+        return now - self._began[key]
 
     def probe(self, key=None):
-        key = self._key(key)
-        if key not in self._started:
-            raise ValueError('No timer started for "' + key + '"')
-        return time.time() - self._started[key]
+        return time.time() - self._began[self._require(key)]
