@@ -177,6 +177,38 @@ int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, int *elem_by
 int kv_sketch_narrow(kv_sketch *s, const void *dev_in);
 int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi);
 int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uint64_t byte_lo, uint64_t byte_hi);
+/* Bin-range-sharded sketches (plan B; needed when one sketch exceeds one GPU): shard i
+ * of n holds, of every table, a contiguous range of bins (multiples of 8 bins, so the shards'
+ * bytes concatenate to khmer's exact table bytes).  A k-mer's buckets generally live on different
+ * shards, so every shard must see the whole hash stream: ranks hash their own reads into device
+ * buffers (kv_hash_batch_dev), exchange the buffers (NCCL all-gather, run by the host), and each
+ * applies all of them to its ranges (kv_add_hashes_dev; hashes that fall outside the shard's
+ * ranges are skipped in-kernel).  Queries return the minimum over the buckets held locally, 255
+ * when none is (kv_get_hashes_dev); an element-wise MIN all-reduce over the shards gives the true
+ * abundance, which kv_novel_from_counts turns into hits exactly like kv_novel_batch.
+ * n_unique_kmers is not available on shards; n_occupied is the local count (sum over shards). */
+int kv_sketch_create_shard(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int shard,
+                           int n_shards, int device, kv_sketch **out);
+int kv_sketch_shard_info(const kv_sketch *s, int *shard, int *n_shards, uint64_t *lo, uint64_t *count);
+/* one piece of an OXLI file written cooperatively: 0 header (shard 0, creates the file; n_occupied =
+ * sum over shards), 1 size field of table t (shard 0), 2 this shard's bytes of table t (all shards,
+ * in shard order), 3 trailer (shard 0) */
+int kv_sketch_save_part(kv_sketch *s, const char *path, int piece, int t, uint64_t n_occupied);
+/* dev_hashes: capacity u64, dev_valid: capacity/32+1 u32 (device memory of `device`); capacity must cover
+ * the batch rounded up to 1024 positions.  Synchronous. */
+int kv_hash_batch_dev(int hasher, int ksize, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                      int where, int num_bands, int band, int device, uint64_t *dev_hashes, uint32_t *dev_valid,
+                      uint64_t capacity, uint64_t *n_positions, uint64_t *n_kmers);
+int kv_add_hashes_dev(kv_sketch *s, const uint64_t *dev_hashes, const uint32_t *dev_valid, uint64_t n);
+int kv_get_hashes_dev(const kv_sketch *s, const uint64_t *dev_hashes, const uint32_t *dev_valid, uint64_t n,
+                      uint8_t *dev_counts);
+/* kv_novel_batch with the abundances of sample i at every base position of the batch given in
+ * dev_counts[i] (device pointers, one byte per position); `like` supplies k, hasher and device. */
+int kv_novel_from_counts(const kv_sketch *like, int n_case, int n_ctrl, const uint8_t *const *dev_counts,
+                         const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where, int case_min,
+                         int ctrl_max, int screen, int num_bands, int64_t band_minus_1, kv_hit *hits,
+                         uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos);
+
 /* CUDA IPC plumbing for kv_sketch_merge_peers: export this sketch's flat allocation
  * (64-byte handle) / map a peer's.  */
 int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);

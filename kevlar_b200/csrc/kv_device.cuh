@@ -15,8 +15,10 @@
 
 struct KvView {
     uint8_t *tab[KV_TABLES_DEV];   // khmer layout: u8[p] | nibbles (even bin = high) | bits (LSB first)
-    uint64_t size[KV_TABLES_DEV];  // buckets per table (the primes)
-    uint64_t magic[KV_TABLES_DEV]; // floor((2^64-1)/size) for the Barrett reduction below
+    uint64_t size[KV_TABLES_DEV];  // buckets of table t held HERE (all of them, or this shard's bin range)
+    uint64_t msize[KV_TABLES_DEV]; // the table's full size (the prime): bin = hash % msize
+    uint64_t magic[KV_TABLES_DEV]; // floor((2^64-1)/msize) for the Barrett reduction below
+    uint64_t lo[KV_TABLES_DEV];    // first bin held here (0 unless the sketch is bin-range sharded)
     uint32_t *occ[KV_TABLES_DEV];  // 1 bit per bucket: counter != 0 (8/4-bit sketches; NULL for bit tables)
     uint32_t *hotf;                // "maybe hot" bitmap: one bit per 8 ADJACENT buckets of a table
     uint64_t hot_base[KV_TABLES_DEV];   // first bit of table t in hotf
@@ -74,6 +76,15 @@ __device__ __forceinline__ uint64_t kv_mod(uint64_t h, uint64_t p, uint64_t magi
     return r;
 }
 
+// Bucket of hash h in table t, as an index into the storage held here.  Returns false when the
+// bucket belongs to another shard (bin-range sharded sketches, SURVEY 8e plan B); always true
+// for an ordinary sketch.
+__device__ __forceinline__ bool kv_bin(const KvView &v, int t, uint64_t h, uint64_t &bin)
+{
+    bin = kv_mod(h, v.msize[t], v.magic[t]) - v.lo[t];
+    return bin < v.size[t];
+}
+
 // Counter read for one table (khmer Storage::get_count inner step, App. A.4).
 __device__ __forceinline__ unsigned kv_bucket_get(const KvView &v, int t, uint64_t bin)
 {
@@ -92,10 +103,12 @@ __device__ __forceinline__ unsigned kv_get(const KvView &v, uint64_t h)
     unsigned m = 0xffffffffu;
 #pragma unroll 4
     for (int t = 0; t < v.n_tables; t++) {
-        unsigned c = kv_bucket_get(v, t, kv_mod(h, v.size[t], v.magic[t]));
+        uint64_t bin;
+        if (!kv_bin(v, t, h, bin)) continue;   // another shard answers for this table
+        unsigned c = kv_bucket_get(v, t, bin);
         m = c < m ? c : m;
     }
-    return m;
+    return m;   // 0xffffffff (255 as a byte) if no table of this k-mer lives here
 }
 
 // Saturating increment of one bucket.  CUDA has no 8-/4-bit atomics and a plain 32-bit

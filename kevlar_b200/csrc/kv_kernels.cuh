@@ -141,27 +141,27 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
             // trips), only then look at what they returned
             unsigned *w[4], sh[4], ob[4];
             uint64_t bin[4];
-            bool did[4], hot[4];
+            bool did[4], hot[4], own[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 did[t] = false;
                 ob[t] = 0;
                 hot[t] = true;
-                if (live) {
-                    bin[t] = kv_mod(h, v.size[t], v.magic[t]);
+                own[t] = live && kv_bin(v, t, h, bin[t]);
+                if (own[t]) {
                     kv_word_addr<BITS>(v, t, bin[t], w[t], sh[t]);
                     hot[t] = kv_maybe_hot(v, t, bin[t]);
                 }
             }
 #pragma unroll
             for (int t = 0; t < 4; t++)
-                if (live && !hot[t]) {
+                if (own[t] && !hot[t]) {
                     ob[t] = (atomicAdd(w[t], 1u << sh[t]) >> sh[t]) & maxv;
                     did[t] = true;
                 }
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                if (live) {
+                if (own[t]) {
                     if (hot[t]) {
                         did[t] = kv_sat_inc_exact<BITS>(w[t], sh[t], ob[t]);
                         if (did[t]) kv_state_publish<BITS>(v, t, bin[t], ob[t]);
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint6
 #pragma unroll 4
         for (int t = 0; t < v.n_tables; t++) {
             bool did = false;
-            if (live) {
-                const uint64_t bin = kv_mod(h, v.size[t], v.magic[t]);
+            uint64_t bin;
+            if (live && kv_bin(v, t, h, bin)) {
                 unsigned *w, sh;
                 kv_word_addr<BITS>(v, t, bin, w, sh);
                 if (BITS == 1) {
@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(256) kv_rollback_kernel(KvView v, const uint64
         for (int t = 0; t < v.n_tables; t++) {
             if (!((added[t * added_stride + (g >> 5)] >> (g & 31)) & 1u)) continue;
             unsigned *w, sh;
-            kv_word_addr<BITS>(v, t, kv_mod(h, v.size[t], v.magic[t]), w, sh);
+            uint64_t bin;
+            kv_bin(v, t, h, bin);   // a recorded add was an owned bucket
+            kv_word_addr<BITS>(v, t, bin, w, sh);
             atomicAdd(w, 0u - (1u << sh));
         }
     }
@@ -340,8 +342,10 @@ __global__ void __launch_bounds__(256) kv_part_hist_kernel(KvView v, KvPartInfo 
         const bool live = g < hi && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
         const uint64_t h = live ? __ldcs(hashes + g) : 0;
         if (live)
-            for (int t = 0; t < v.n_tables; t++)
-                atomicAdd(&sm_cnt[pi.pbase[t] + (uint32_t)(kv_mod(h, v.size[t], v.magic[t]) >> pi.rb)], 1u);
+            for (int t = 0; t < v.n_tables; t++) {
+                uint64_t bin;
+                if (kv_bin(v, t, h, bin)) atomicAdd(&sm_cnt[pi.pbase[t] + (uint32_t)(bin >> pi.rb)], 1u);
+            }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < P; q += blockDim.x) rows[(size_t)q * gridDim.x + blockIdx.x] = sm_cnt[q];
@@ -417,8 +421,8 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
         const uint64_t h = live ? __ldcs(hashes + g) : 0;
         if (live)
             for (int t = 0; t < v.n_tables; t++) {
-                const uint32_t bin = (uint32_t)kv_mod(h, v.size[t], v.magic[t]);
-                items[atomicAdd(&sm_cur[pi.pbase[t] + (bin >> pi.rb)], 1u)] = bin;
+                uint64_t bin;
+                if (kv_bin(v, t, h, bin)) items[atomicAdd(&sm_cur[pi.pbase[t] + (uint32_t)(bin >> pi.rb)], 1u)] = (uint32_t)bin;
             }
     }
 }
@@ -508,11 +512,10 @@ __global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint
                                                            const uint32_t *__restrict__ valid, uint64_t total)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t size = v.size[t], magic = v.magic[t];
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
         if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
-        const uint64_t bin = kv_mod(__ldcs(hashes + g), size, magic);
-        if (kv_bucket_empty(v, t, bin)) atomicMin(first + bin, (uint32_t)g);
+        uint64_t bin;
+        if (kv_bin(v, t, __ldcs(hashes + g), bin) && kv_bucket_empty(v, t, bin)) atomicMin(first + bin, (uint32_t)g);
     }
 }
 
@@ -582,6 +585,8 @@ struct KvNovelParams {
     uint32_t *read_flags;       // u32 per read (no byte atomics on the device)
     uint32_t *discard_pos;      // per read, atomicMin; NULL when screen <= 0
     KvView sk[KV_MAX_SAMPLES];  // cases then controls
+    const uint8_t *pre[KV_MAX_SAMPLES];   // non-NULL: abundance of sample s at every base position, already
+                                          // computed (sharded sketches: all-reduced partial minima)
 };
 
 template <int HASHER, int KW>
@@ -613,7 +618,7 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
         uint8_t ab[KV_MAX_SAMPLES];
         bool interesting = true;
         for (int s = 0; s < p.n_case; s++) {
-            int a = (int)kv_get(p.sk[s], h);
+            int a = p.pre[s] ? (int)p.pre[s][g] : (int)kv_get(p.sk[s], h);
             if (a < p.case_min) {
                 interesting = false;
                 if (p.screen > 0 && a < p.screen) atomicMin(p.discard_pos + read, (uint32_t)(g - rs));
@@ -623,7 +628,7 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
         }
         if (!interesting) continue;
         for (int s = 0; s < p.n_ctrl; s++) {
-            int a = (int)kv_get(p.sk[p.n_case + s], h);
+            int a = p.pre[p.n_case + s] ? (int)p.pre[p.n_case + s][g] : (int)kv_get(p.sk[p.n_case + s], h);
             if (a > p.ctrl_max) { interesting = false; break; }
             ab[p.n_case + s] = (uint8_t)a;
         }

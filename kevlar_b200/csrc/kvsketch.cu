@@ -238,8 +238,11 @@ static inline unsigned kv_grid_for(const KvCtx *c, uint64_t n, int per_sm = 8)
 
 struct kv_sketch {
     int hasher, bits, ksize, n_tables, device;
-    uint64_t sizes[KV_TABLES_DEV];
-    uint64_t nbytes[KV_TABLES_DEV];   // khmer byte length of each table
+    uint64_t sizes[KV_TABLES_DEV];    // buckets held here (the whole table, or this shard's bin range)
+    uint64_t msizes[KV_TABLES_DEV];   // full table sizes (the primes)
+    uint64_t lo[KV_TABLES_DEV];       // first bin held here
+    int shard, n_shards;              // 0 of 1 for an ordinary sketch
+    uint64_t nbytes[KV_TABLES_DEV];   // khmer byte length of each (local) table
     uint64_t toff[KV_TABLES_DEV];     // offset of each table in the flat allocation
     uint64_t flat_bytes;
     uint8_t *flat;
@@ -272,7 +275,9 @@ static KvView kv_view(const kv_sketch *s)
     for (int t = 0; t < s->n_tables; t++) {
         v.tab[t] = s->flat + s->toff[t];
         v.size[t] = s->sizes[t];
-        v.magic[t] = UINT64_MAX / s->sizes[t];
+        v.msize[t] = s->msizes[t];
+        v.lo[t] = s->lo[t];
+        v.magic[t] = UINT64_MAX / s->msizes[t];
         v.occ[t] = s->state ? s->state + s->soff[t] : nullptr;
     }
     return v;
@@ -313,8 +318,17 @@ extern "C" int kv_device_count(int *n)
     return KV_OK;
 }
 
+// bins [lo, hi) of a table of `size` buckets that shard `shard` of `n_shards` holds: contiguous,
+// multiples of 8 so that every shard's bytes are whole bytes for all counter widths
+static void kv_shard_range(uint64_t size, int shard, int n_shards, uint64_t *lo, uint64_t *hi)
+{
+    uint64_t per = ((size + n_shards - 1) / n_shards + 7) & ~(uint64_t)7;
+    *lo = std::min<uint64_t>(size, per * (uint64_t)shard);
+    *hi = std::min<uint64_t>(size, per * (uint64_t)(shard + 1));
+}
+
 static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int device,
-                           bool zero, kv_sketch **out)
+                           bool zero, kv_sketch **out, int shard = 0, int n_shards = 1)
 {
     if (!out || !sizes) return kv_fail(KV_EINVAL, "null argument");
     if (hasher != KV_HASH_MURMUR && hasher != KV_HASH_TWOBIT) return kv_fail(KV_EINVAL, "unknown hasher %d", hasher);
@@ -330,17 +344,27 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     kv_sketch *s = new kv_sketch();
     memset(s, 0, sizeof *s);
     s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
+    s->shard = shard; s->n_shards = n_shards;
     uint64_t off = 0, soff = 0, hotbits = 0;
     for (int t = 0; t < n_tables; t++) {
         if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete s; return kv_fail(KV_EINVAL, "bad table size"); }
-        s->sizes[t] = sizes[t];
-        s->nbytes[t] = kv_table_bytes(bits, sizes[t]);
+        uint64_t lo = 0, hi = sizes[t];
+        if (n_shards > 1) kv_shard_range(sizes[t], shard, n_shards, &lo, &hi);
+        s->msizes[t] = sizes[t];
+        s->lo[t] = lo;
+        s->sizes[t] = hi - lo;     // 0 if this shard holds nothing of the table (tiny tables, many shards)
+        // this shard's bytes inside khmer's table layout; whoever holds the table's end also holds
+        // the trailing byte of the nibble / bit layouts
+        const uint64_t lo_bytes = lo * (uint64_t)bits / 8;
+        if (hi <= lo) s->nbytes[t] = 0;
+        else if (hi == sizes[t]) s->nbytes[t] = kv_table_bytes(bits, sizes[t]) - lo_bytes;
+        else s->nbytes[t] = (hi - lo) * (uint64_t)bits / 8;
         s->toff[t] = off;
-        off += (s->nbytes[t] + 255) & ~(uint64_t)255;
+        off += (s->nbytes[t] + 256) & ~(uint64_t)255;
         s->soff[t] = soff;
-        soff += ((sizes[t] + 31) / 32 + 63) & ~(uint64_t)63;
+        soff += ((s->sizes[t] + 31) / 32 + 64) & ~(uint64_t)63;
         s->hot_base[t] = hotbits;
-        hotbits += ((sizes[t] >> 3) + 1 + 2047) & ~(uint64_t)2047;
+        hotbits += ((s->sizes[t] >> 3) + 1 + 2047) & ~(uint64_t)2047;
     }
     s->hot_off = soff;
     s->state_words = bits == 1 ? 0 : soff + hotbits / 32;
@@ -365,8 +389,8 @@ static int kv_sketch_alloc(int hasher, int bits, int ksize, int n_tables, const 
     }
     CU(cudaMalloc((void **)&s->d_unique, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
-    s->track_unique = true;
-    s->unique_valid = true;
+    s->track_unique = n_shards == 1;   // the order-dependent statistic needs all buckets of a k-mer in one place
+    s->unique_valid = n_shards == 1;
     *out = s;
     return KV_OK;
 }
@@ -375,6 +399,25 @@ extern "C" int kv_sketch_create(int hasher, int bits, int ksize, int n_tables, c
                                 kv_sketch **out)
 {
     return kv_sketch_alloc(hasher, bits, ksize, n_tables, sizes, device, true, out);
+}
+
+extern "C" int kv_sketch_create_shard(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int shard,
+                                      int n_shards, int device, kv_sketch **out)
+{
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return kv_fail(KV_EINVAL, "shard %d of %d", shard, n_shards);
+    return kv_sketch_alloc(hasher, bits, ksize, n_tables, sizes, device, true, out, shard, n_shards);
+}
+
+extern "C" int kv_sketch_shard_info(const kv_sketch *s, int *shard, int *n_shards, uint64_t *lo, uint64_t *count)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (shard) *shard = s->shard;
+    if (n_shards) *n_shards = s->n_shards;
+    for (int t = 0; t < s->n_tables; t++) {
+        if (lo) lo[t] = s->lo[t];
+        if (count) count[t] = s->sizes[t];
+    }
+    return KV_OK;
 }
 
 extern "C" int kv_sketch_destroy(kv_sketch *s)
@@ -417,7 +460,7 @@ extern "C" int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *k
     if (ksize) *ksize = s->ksize;
     if (n_tables) *n_tables = s->n_tables;
     if (device) *device = s->device;
-    if (sizes) for (int t = 0; t < s->n_tables; t++) sizes[t] = s->sizes[t];
+    if (sizes) for (int t = 0; t < s->n_tables; t++) sizes[t] = s->msizes[t];
     return KV_OK;
 }
 
@@ -550,6 +593,52 @@ extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
         }
     }
     if (rc == KV_OK && s->bits == 8) { uint64_t nbig = 0; fwrite(&nbig, 8, 1, f); }
+    if (rc == KV_OK && ferror(f)) rc = kv_fail(KV_EIO, "write error on %s", path);
+    fclose(f);
+    return rc;
+}
+
+// One piece of an OXLI v4 file written cooperatively by the shards of a sketch (the caller orders the
+// calls: header by shard 0, then per table its size field by shard 0 and the shards' bytes in shard
+// order, finally the trailer by shard 0).  piece: 0 header (creates the file), 1 size field of table t,
+// 2 this shard's bytes of table t, 3 trailer.
+extern "C" int kv_sketch_save_part(kv_sketch *s, const char *path, int piece, int t, uint64_t n_occupied)
+{
+    if (!s || !path) return kv_fail(KV_EINVAL, "null argument");
+    if ((piece == 1 || piece == 2) && (t < 0 || t >= s->n_tables)) return kv_fail(KV_EINVAL, "bad table index");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    FILE *f = fopen(path, piece == 0 ? "wb" : "ab");
+    if (!f) return kv_fail(KV_EIO, "cannot open %s for writing", path);
+    int rc = KV_OK;
+    if (piece == 0) {
+        uint8_t version = 4, type = s->bits == 8 ? 1 : (s->bits == 4 ? 7 : 2);
+        fwrite("OXLI", 1, 4, f);
+        fwrite(&version, 1, 1, f);
+        fwrite(&type, 1, 1, f);
+        if (s->bits == 8) { uint8_t big = 0; fwrite(&big, 1, 1, f); }
+        uint32_t k = (uint32_t)s->ksize;
+        uint8_t nt = (uint8_t)s->n_tables;
+        fwrite(&k, 4, 1, f);
+        fwrite(&nt, 1, 1, f);
+        fwrite(&n_occupied, 8, 1, f);
+    } else if (piece == 1) {
+        fwrite(&s->msizes[t], 8, 1, f);
+    } else if (piece == 2) {
+        uint8_t *stage = nullptr;
+        rc = kv_io_stage(ctx, &stage);
+        for (uint64_t o = 0; o < s->nbytes[t] && rc == KV_OK; o += KV_IO_STAGE) {
+            size_t n = (size_t)std::min<uint64_t>(KV_IO_STAGE, s->nbytes[t] - o);
+            if (cudaMemcpyAsync(stage, s->flat + s->toff[t] + o, n, cudaMemcpyDeviceToHost, ctx->compute) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "D2H copy failed"); break; }
+            if (fwrite(stage, 1, n, f) != n) rc = kv_fail(KV_EIO, "short write to %s", path);
+        }
+    } else if (piece == 3) {
+        if (s->bits == 8) { uint64_t nbig = 0; fwrite(&nbig, 8, 1, f); }
+    } else
+        rc = kv_fail(KV_EINVAL, "unknown piece %d", piece);
     if (rc == KV_OK && ferror(f)) rc = kv_fail(KV_EIO, "write error on %s", path);
     fclose(f);
     return rc;
@@ -919,10 +1008,10 @@ static int kv_launch_novel(KvCtx *ctx, const KvNovelParams &p)
     return KV_OK;
 }
 
-extern "C" int kv_novel_batch(const kv_sketch *const *cases, int n_case, const kv_sketch *const *ctrls, int n_ctrl,
-                              const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where, int case_min,
-                              int ctrl_max, int screen, int num_bands, int64_t band_minus_1, kv_hit *hits,
-                              uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos)
+static int kv_novel_impl(const kv_sketch *const *cases, int n_case, const kv_sketch *const *ctrls, int n_ctrl,
+                         const uint8_t *const *pre, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                         int where, int case_min, int ctrl_max, int screen, int num_bands, int64_t band_minus_1,
+                         kv_hit *hits, uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos)
 {
     if (n_hits) *n_hits = 0;
     if (n_case < 1 || !cases || !cases[0]) return kv_fail(KV_EINVAL, "need at least one case sketch");
@@ -939,6 +1028,7 @@ extern "C" int kv_novel_batch(const kv_sketch *const *cases, int n_case, const k
         if (s->ksize != c0->ksize || s->hasher != c0->hasher)
             return kv_fail(KV_EINVAL, "all sketches of a scan must share k-mer size and hash function");
         p.sk[i] = kv_view(s);
+        p.pre[i] = pre ? pre[i] : nullptr;
     }
     if (n_reads == 0) return KV_OK;
     if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
@@ -1010,6 +1100,112 @@ extern "C" int kv_novel_batch(const kv_sketch *const *cases, int n_case, const k
     });
     if (kept) memcpy(hits, hh.data(), kept * sizeof(kv_hit));
     *n_hits = kept;
+    return KV_OK;
+}
+
+extern "C" int kv_novel_batch(const kv_sketch *const *cases, int n_case, const kv_sketch *const *ctrls, int n_ctrl,
+                              const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where, int case_min,
+                              int ctrl_max, int screen, int num_bands, int64_t band_minus_1, kv_hit *hits,
+                              uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos)
+{
+    for (int i = 0; i < n_case + n_ctrl && i < KV_MAX_SAMPLES; i++) {
+        const kv_sketch *s = i < n_case ? (cases ? cases[i] : nullptr) : (ctrls ? ctrls[i - n_case] : nullptr);
+        if (s && s->n_shards > 1)
+            return kv_fail(KV_EINVAL, "sharded sketches are scanned with kv_get_hashes_dev + kv_novel_from_counts");
+    }
+    return kv_novel_impl(cases, n_case, ctrls, n_ctrl, nullptr, bases, offsets, n_reads, where, case_min, ctrl_max, screen,
+                         num_bands, band_minus_1, hits, max_hits, n_hits, read_flags, discard_pos);
+}
+
+extern "C" int kv_novel_from_counts(const kv_sketch *like, int n_case, int n_ctrl, const uint8_t *const *dev_counts,
+                                    const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int where,
+                                    int case_min, int ctrl_max, int screen, int num_bands, int64_t band_minus_1,
+                                    kv_hit *hits, uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags,
+                                    uint32_t *discard_pos)
+{
+    if (!like || !dev_counts) return kv_fail(KV_EINVAL, "null argument");
+    if (n_case < 1 || n_ctrl < 0 || n_case + n_ctrl > KV_MAX_SAMPLES) return kv_fail(KV_EINVAL, "bad sample counts");
+    const kv_sketch *all[KV_MAX_SAMPLES];
+    for (int i = 0; i < n_case + n_ctrl; i++) {
+        if (!dev_counts[i]) return kv_fail(KV_EINVAL, "null count array");
+        all[i] = like;   // only k, the hasher and the device are taken from it: every abundance comes from dev_counts
+    }
+    return kv_novel_impl(all, n_case, all + n_case, n_ctrl, dev_counts, bases, offsets, n_reads, where, case_min, ctrl_max,
+                         screen, num_bands, band_minus_1, hits, max_hits, n_hits, read_flags, discard_pos);
+}
+
+// ------------------------------------------------------------------ device-resident hash streams (sharded sketches)
+
+extern "C" int kv_hash_batch_dev(int hasher, int ksize, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                                 int where, int num_bands, int band, int device, uint64_t *dev_hashes,
+                                 uint32_t *dev_valid, uint64_t capacity, uint64_t *n_positions, uint64_t *n_kmers)
+{
+    if (n_positions) *n_positions = 0;
+    if (n_kmers) *n_kmers = 0;
+    if (!n_reads) return KV_OK;
+    if (!bases || !offsets || !dev_hashes || !dev_valid) return kv_fail(KV_EINVAL, "null argument");
+    int kmax = hasher == KV_HASH_TWOBIT ? KV_MAX_KSIZE_TWOBIT : KV_MAX_KSIZE_MURMUR;
+    if (ksize < 1 || ksize > kmax) return kv_fail(KV_EINVAL, "k-mer size %d not supported", ksize);
+    uint64_t lo = 0, hi = 0;
+    if (num_bands > 0) KV_TRY(kv_band_interval(num_bands, band, &lo, &hi));
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+    if (b.n_tiles * KV_TILE > capacity) {
+        kv_stage_done(ctx, &b);
+        return kv_fail(KV_EOVERFLOW, "hash buffer holds %llu positions, the batch needs %llu", (unsigned long long)capacity,
+                       (unsigned long long)(b.n_tiles * KV_TILE));
+    }
+    CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
+    if (b.total) {
+        KvHashParams p;
+        memset(&p, 0, sizeof p);
+        p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+        p.total = b.total; p.tile0 = 0; p.k = ksize;
+        p.banded = num_bands > 0; p.band_lo = lo; p.band_hi = hi;
+        p.hashes = dev_hashes; p.valid = dev_valid; p.n_valid = ctx->counters;
+        if (hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)b.n_tiles));
+        else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)b.n_tiles));
+    }
+    kv_stage_done(ctx, &b);
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (n_positions) *n_positions = b.total;
+    if (n_kmers) *n_kmers = ctx->h_counters[0];
+    return KV_OK;
+}
+
+extern "C" int kv_add_hashes_dev(kv_sketch *s, const uint64_t *dev_hashes, const uint32_t *dev_valid, uint64_t n)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (!n) return KV_OK;
+    if (!dev_hashes || !dev_valid) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    const uint64_t step = std::min<uint64_t>(ctx->chunk_bases, (0xfffffff0ull / (uint64_t)s->n_tables) / KV_TILE * KV_TILE);
+    for (uint64_t o = 0; o < n; o += step)   // step is a multiple of 32: valid words stay aligned
+        KV_TRY(kv_apply_hashes(ctx, s, dev_hashes + o, dev_valid + o / 32, std::min(step, n - o)));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+extern "C" int kv_get_hashes_dev(const kv_sketch *s, const uint64_t *dev_hashes, const uint32_t *dev_valid, uint64_t n,
+                                 uint8_t *dev_counts)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    if (!n) return KV_OK;
+    if (!dev_hashes || !dev_counts) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    LAUNCH(ctx, kv_get_kernel, kv_grid_for(ctx, n), 256, kv_view(s), dev_hashes, dev_valid, n, dev_counts);
+    CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }
 

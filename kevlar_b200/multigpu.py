@@ -237,3 +237,149 @@ def gather_hits(hits, read_base, group=None):
     parts = [None] * td.get_world_size(group)
     td.all_gather_object(parts, local, group=group)
     return np.concatenate(parts)
+
+
+# ----------------------------------------------------------------------------------------------
+# Plan B: bin-range-sharded sketches -- for sketches that do not fit one GPU.
+# Every rank holds 1/world of every table; reads stay sharded across ranks; what crosses NVLink
+# is the hash stream (8 bytes per k-mer position, one NCCL all-gather per batch) and, for the
+# novel scan, one byte per position and sample (MIN all-reduce of the partial abundances).
+
+class HashStream(object):
+    """The canonical hashes of this rank's batch, gathered from every rank (device tensors)."""
+
+    def __init__(self, sketch, bases, offsets, num_bands=None, band=None, group=None):
+        import torch
+        td = dist()
+        bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+        self.world = td.get_world_size(group) if td.is_initialized() else 1
+        self.rank = td.get_rank(group) if td.is_initialized() else 0
+        dev = torch.device('cuda', sketch.device)
+        total = int(offsets[-1]) if len(offsets) else 0
+        cap = torch.tensor([(total + 1023) // 1024 * 1024], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            td.all_reduce(cap, op=td.ReduceOp.MAX, group=group)
+        self.cap = max(int(cap.item()), 1024)
+        mine_h = torch.zeros(self.cap, dtype=torch.int64, device=dev)
+        mine_v = torch.zeros(self.cap // 32 + 1, dtype=torch.int32, device=dev)
+        npos, nk = c_uint64(), c_uint64()
+        torch.cuda.synchronize(dev)
+        check(lib().kv_hash_batch_dev(sketch._hasher, sketch.ksize(), bases.ctypes.data, offsets.ctypes.data,
+                                      len(offsets) - 1, _lib.MEM_HOST, int(num_bands or 0), int(band or 0), sketch.device,
+                                      mine_h.data_ptr(), mine_v.data_ptr(), self.cap, byref(npos), byref(nk)))
+        self.n_kmers = nk.value
+        if self.world > 1:
+            self.hashes = [torch.empty_like(mine_h) for _ in range(self.world)]
+            self.valid = [torch.empty_like(mine_v) for _ in range(self.world)]
+            td.all_gather(self.hashes, mine_h, group=group)
+            td.all_gather(self.valid, mine_v, group=group)
+            torch.cuda.synchronize(dev)
+        else:
+            self.hashes, self.valid = [mine_h], [mine_v]
+        self.device = dev
+
+
+class ShardedSketch(object):
+    """A khmer-style sketch whose tables are split by bin range over the ranks of `group`.
+    `consume_batch` takes THIS rank's reads; afterwards every rank's shard has seen the k-mers
+    of all ranks.  `save` writes one ordinary OXLI file, byte-identical to the unsharded one."""
+
+    def __init__(self, cls, ksize, starting_size, n_tables, primes=None, group=None):
+        td = dist()
+        self.group = group
+        self.world = td.get_world_size(group) if td.is_initialized() else 1
+        self.rank = td.get_rank(group) if td.is_initialized() else 0
+        sizes = [int(p) for p in primes] if primes else _lib.primes_below(int(starting_size), int(n_tables))
+        arr = (c_uint64 * len(sizes))(*sizes)
+        handle = c_void_p()
+        check(lib().kv_sketch_create_shard(cls._hasher, cls._bits, int(ksize), len(sizes), arr, self.rank, self.world,
+                                           _lib.current_device(), byref(handle)))
+        self.local = cls(0, 0, 0, _handle=handle)
+
+    def ksize(self):
+        return self.local.ksize()
+
+    def hashsizes(self):
+        return self.local.hashsizes()
+
+    def consume_batch(self, bases, offsets, num_bands=None, band=None):
+        """Count this rank's reads into the sharded sketch; returns the k-mers counted by all ranks."""
+        import torch
+        td = dist()
+        stream = HashStream(self.local, bases, offsets, num_bands, band, self.group)
+        for h, v in zip(stream.hashes, stream.valid):
+            check(lib().kv_add_hashes_dev(self.local._h, h.data_ptr(), v.data_ptr(), stream.cap))
+        total = torch.tensor([stream.n_kmers], dtype=torch.int64, device=stream.device)
+        if self.world > 1:
+            td.all_reduce(total, op=td.ReduceOp.SUM, group=self.group)
+        return int(total.item())
+
+    def n_occupied(self):
+        import torch
+        td = dist()
+        n = torch.tensor([self.local.n_occupied()], dtype=torch.int64, device=torch.device('cuda', self.local.device))
+        if self.world > 1:
+            td.all_reduce(n, op=td.ReduceOp.SUM, group=self.group)
+        return int(n.item())
+
+    def counts(self, stream):
+        """Abundance of every position of `stream` (this rank's part): partial minima over the
+        buckets held here, MIN-all-reduced over the shards."""
+        import torch
+        td = dist()
+        parts = []
+        for h, v in zip(stream.hashes, stream.valid):
+            c = torch.empty(stream.cap, dtype=torch.uint8, device=stream.device)
+            check(lib().kv_get_hashes_dev(self.local._h, h.data_ptr(), v.data_ptr(), stream.cap, c.data_ptr()))
+            parts.append(c)
+        allc = torch.stack(parts)
+        if self.world > 1:
+            td.all_reduce(allc, op=td.ReduceOp.MIN, group=self.group)
+        return allc[stream.rank].contiguous()
+
+    def save(self, filename):
+        """One OXLI v4 file (on a filesystem all ranks share), shards appended in rank order."""
+        td = dist()
+        occupied = self.n_occupied()
+        path = str(filename).encode()
+
+        def turn(piece, t, writer):
+            if self.rank == writer:
+                check(lib().kv_sketch_save_part(self.local._h, path, piece, t, occupied))
+            if self.world > 1:
+                td.barrier(group=self.group)
+        turn(0, 0, 0)
+        for t in range(len(self.hashsizes())):
+            turn(1, t, 0)
+            for r in range(self.world):
+                turn(2, t, r)
+        turn(3, 0, 0)
+
+
+def novel_batch_sharded(cases, ctrls, bases, offsets, case_min, ctrl_max, screen=None, num_bands=None, band_minus_1=0,
+                        max_hits=None):
+    """kevlar_b200.khmer.novel_batch for ShardedSketch samples: this rank's reads against sketches
+    spread over all ranks.  Same return value (hits, read_flags, discard_pos) for this rank's reads."""
+    samples = list(cases) + list(ctrls)
+    like = samples[0].local
+    bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+    stream = HashStream(like, bases, offsets, group=samples[0].group)
+    counts = [s.counts(stream) for s in samples]
+    n_reads = len(offsets) - 1
+    ptrs = (c_void_p * len(counts))(*[c.data_ptr() for c in counts])
+    flags = np.zeros(max(1, n_reads), dtype=np.uint8)
+    discard = np.full(max(1, n_reads), 0xffffffff, dtype=np.uint32)
+    if max_hits is None:
+        max_hits = max(4096, len(bases) // 64)
+    while True:
+        hits = np.empty(max_hits, dtype=_lib.HIT_DTYPE)
+        n = c_uint64()
+        rc = lib().kv_novel_from_counts(like._h, len(cases), len(ctrls), ptrs, bases.ctypes.data, offsets.ctypes.data,
+                                        n_reads, _lib.MEM_HOST, int(case_min), int(ctrl_max), int(screen or 0),
+                                        int(num_bands or 0), int(band_minus_1), hits.ctypes.data, max_hits, byref(n),
+                                        flags.ctypes.data, discard.ctypes.data if screen else None)
+        if rc == _lib.KV_EOVERFLOW:
+            max_hits = int(n.value) + 1024
+            continue
+        check(rc)
+        return hits[:n.value], flags[:n_reads], discard[:n_reads]
