@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--hasher', default='murmur', choices=['murmur', 'twobit'],
                     help='murmur = Counttable (what `kevlar count` builds); twobit = Countgraph')
-    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p'])
+    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p', 'sharded'],
+                    help="N>1: how per-GPU work is combined; 'sharded' = plan B, bin-range-sharded sketches")
     ap.add_argument('--reads-per-sample', type=int, default=READS_PER_SAMPLE)
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -185,8 +186,12 @@ class GpuTrio(object):
         self.args, self.world = args, world
         self.device = _lib.current_device()
         cls = khmer.Counttable if args.hasher == 'murmur' else khmer.Countgraph
-        self.sketches = [cls(K, MEMORY / N_TABLES, N_TABLES) for _ in range(3)]
-        if args.no_unique:
+        self.sharded = world > 1 and args.merge == 'sharded'
+        if self.sharded:   # plan B: every rank holds 1/world of every table; reads stay sharded
+            self.sketches = [multigpu.ShardedSketch(cls, K, MEMORY / N_TABLES, N_TABLES) for _ in range(3)]
+        else:
+            self.sketches = [cls(K, MEMORY / N_TABLES, N_TABLES) for _ in range(3)]
+        if args.no_unique and not self.sharded:
             for sk in self.sketches:
                 sk.set_unique_tracking(False)
         self.trio = trio
@@ -198,7 +203,23 @@ class GpuTrio(object):
         self.stream = torch.cuda.ExternalStream(_lib.stream_ptr(self.device), device=dev)
         self.last_hits = None
 
+    def step_sharded(self):
+        # host buffers in both arms: hash locally, all-gather the hash stream, apply to the local bin
+        # ranges; novel from MIN-all-reduced partial abundances
+        for sk in self.sketches:
+            sk.local.clear()
+        for i, sk in enumerate(self.sketches):
+            b, o = self.pinned[i]
+            sk.consume_batch(b.numpy(), o.numpy().view(np.uint64))
+        b, o = self.pinned[0]
+        hits, _, _ = self.multigpu.novel_batch_sharded(self.sketches[:1], self.sketches[1:], b.numpy(),
+                                                       o.numpy().view(np.uint64), CASE_MIN, CTRL_MAX)
+        self.last_hits = hits
+        return hits
+
     def step(self, resident):
+        if self.sharded:
+            return self.step_sharded()
         khmer = self.khmer
         for sk in self.sketches:
             sk.clear()
