@@ -168,6 +168,27 @@ class _Sketch(object):
     def get_kmer_counts(self, sequence):
         return [int(c) for c in self._per_position(sequence, False, True)[1]]
 
+    def get_kmer_counts_many(self, sequences):
+        """get_kmer_counts for a list of sequences in ONE GPU call (e.g. all call windows of a
+        `simlike` run); returns one uint8 array per sequence.  Sequences shorter than k give an
+        empty array."""
+        batch = batch_from_sequences(sequences)
+        n, total = len(sequences), len(batch.bases)
+        if total == 0:
+            return [np.zeros(0, dtype=np.uint8) for _ in sequences]
+        counts = np.empty(total, dtype=np.uint8)
+        valid = np.empty(total, dtype=np.uint8)
+        check(lib().kv_kmer_counts_batch(self._h, batch.bases.ctypes.data, batch.offsets.ctypes.data, n, MEM_HOST, None,
+                                         counts.ctypes.data, valid.ctypes.data))
+        out = []
+        for i in range(n):
+            lo, hi = int(batch.offsets[i]), int(batch.offsets[i + 1])
+            nk = max(0, hi - lo - self._ksize + 1)
+            if nk and not valid[lo:lo + nk].all():
+                raise ValueError('invalid DNA character in sequence {}'.format(i))
+            out.append(counts[lo:lo + nk])
+        return out
+
     # --------------------------------------------------------------- point ops
     def _to_hashes(self, items):
         if isinstance(items, np.ndarray) and items.dtype == np.uint64:

