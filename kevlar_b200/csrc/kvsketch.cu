@@ -870,7 +870,10 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
     if (maxsize * 4 > ctx->first.cap) {   // (re)allocated: establish the all-ones invariant the passes maintain
-        KV_TRY(kv_buf_ensure(ctx->first, maxsize * 4));
+        if (kv_buf_ensure(ctx->first, maxsize * 4) != KV_OK)
+            return kv_fail(KV_ENOMEM, "exact n_unique_kmers tracking needs %llu bytes of scratch HBM (4 per bucket of the "
+                           "largest table); switch it off with kv_sketch_set_unique_tracking(sketch, 0)",
+                           (unsigned long long)(maxsize * 4));
         CU(cudaMemsetAsync(ctx->first.p, 0xff, ctx->first.cap, ctx->compute));
     }
     const uint64_t n_words = (n + 31) / 32;
