@@ -509,42 +509,13 @@ __global__ void __launch_bounds__(256) kv_part_apply_kernel(KvView v, const uint
 // bucket region instead of spreading over all tables at once.
 __global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint32_t *__restrict__ first,
                                                            const uint64_t *__restrict__ hashes,
-                                                           const uint32_t *__restrict__ valid,
-                                                           const uint32_t *__restrict__ skip, uint64_t total)
+                                                           const uint32_t *__restrict__ valid, uint64_t total)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
         if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
-        if (skip && ((__ldg(skip + (g >> 5)) >> (g & 31)) & 1u)) continue;   // a repeat of an earlier identical k-mer
         uint64_t bin;
         if (kv_bin(v, t, __ldcs(hashes + g), bin) && kv_bucket_empty(v, t, bin)) atomicMin(first + bin, (uint32_t)g);
-    }
-}
-
-// After the table-0 pass: position g is a REPEAT if the owner of its table-0 bucket is an earlier
-// position holding the very same hash.  A repeat has the same buckets as that owner and a larger
-// position, so it can never own a bucket in any table and may sit out the remaining passes
-// (at 30x coverage ~4 of 5 positions are repeats).  The owner itself is never marked, so every
-// repeat keeps a representative in the later passes and the minima are unchanged.
-__global__ void __launch_bounds__(256) kv_first_repeat_kernel(KvView v, const uint32_t *__restrict__ first,
-                                                              const uint64_t *__restrict__ hashes,
-                                                              const uint32_t *__restrict__ valid, uint64_t total,
-                                                              uint32_t *__restrict__ skip)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        bool repeat = false;
-        if (g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u))) {
-            const uint64_t h = __ldcs(hashes + g);
-            uint64_t bin;
-            if (kv_bin(v, 0, h, bin)) {
-                const uint32_t owner = __ldcg(first + bin);
-                repeat = owner < (uint32_t)g && __ldg(hashes + owner) == h;
-            }
-        }
-        unsigned bal = __ballot_sync(0xffffffffu, repeat);
-        if ((threadIdx.x & 31) == 0) skip[g >> 5] = bal;
     }
 }
 

@@ -82,7 +82,7 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, fresh, repeat, first, hits, flags, discard, misc, added, part_items, part_small;
+    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small;
     // sketches between these sizes take the region-partitioned update path (measured: 1.2-1.7x over
     // direct random atomics from 256 MB to 4 GB, break-even at 16 GB; profiles/r01_notes.md)
     uint64_t part_min_bytes = 128ull << 20, part_max_bytes = 8ull << 30;
@@ -887,14 +887,8 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
             else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<4>, kv_grid_for(ctx, n_words, 16), 256, v, t);
         }
     kv_l2_window(ctx, ctx->first.p, maxsize * 4);
-    KV_TRY(kv_buf_ensure(ctx->repeat, (n_words + 1) * 4));
-    uint32_t *repeat = s->n_tables > 1 ? (uint32_t *)ctx->repeat.p : nullptr;
     for (int t = 0; t < s->n_tables; t++) {
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid,
-                 t == 0 ? (const uint32_t *)nullptr : (const uint32_t *)repeat, n);
-        if (t == 0 && repeat)   // who is a repeat of an earlier identical k-mer (reads first[] before it is reset)
-            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_repeat_kernel, grid, 256, v, (const uint32_t *)ctx->first.p, d_hashes,
-                     d_valid, n, repeat);
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n);
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, kv_grid_for(ctx, s->sizes[t] / 4 + 1), 256,
                  (uint32_t *)ctx->first.p, s->sizes[t], (uint32_t *)ctx->fresh.p);
     }
