@@ -280,6 +280,20 @@ def load_traffic(kernel):
     return None
 
 
+def load_atomic_peak(table_mb=64):
+    """Measured L2 atomic throughput for a table of this size (tools/atomic_microbench.cu, committed
+    under profiles/): G updates/s for ATOM.ADD (the primitive the update kernel issues) and RED.ADD."""
+    path = os.path.join(REPO, 'profiles', 'r01_atomic_microbench.csv')
+    peaks = {}
+    if os.path.exists(path):
+        with open(path) as fh:
+            for line in fh:
+                f = line.strip().split(',')
+                if len(f) >= 4 and f[1] == str(table_mb) and f[0] in ('atom_add', 'red_add'):
+                    peaks[f[0]] = float(f[3])
+    return peaks
+
+
 def run_ours(args):
     import torch
     from kevlar_b200 import _lib, multigpu, simtrio
@@ -362,6 +376,14 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': alg_bytes[dominant] / kernels[dominant]['launches_per_step'],
                 'launches_per_step': kernels[dominant]['launches_per_step'],
                 'avg_launch_ms': kernels[dominant]['ms_per_launch']}
+    # L2-resident case: update rate against the microbenchmarked L2 atomic peak for a 64 MB table
+    atomic = load_atomic_peak(64)
+    updates_per_s = N_TABLES * kmers_count * 3 / (prof['increment'][0] / args.steps / 1e3)
+    roofline_l2 = {'kernel': 'kv_increment_kernel<8>', 'bound': 'l2_atomic', 'achieved': updates_per_s / 1e9,
+                   'unit': 'G updates/s', 'peak': atomic.get('atom_add'), 'peak_red_add': atomic.get('red_add'),
+                   'frac': updates_per_s / 1e9 / atomic['atom_add'] if atomic.get('atom_add') else None,
+                   'peak_source': 'tools/atomic_microbench.cu on this pool (profiles/r01_atomic_microbench.csv): random '
+                                  'ATOM.ADD / RED.ADD over a 64 MB table'}
     # the count path (hash + unique + increment per sample) and the novel path against 8d's figures
     count_ms = sum(prof[c][0] for c in ('hash', 'unique', 'increment', 'fixup')) / (3.0 * args.steps)
     novel_ms = prof['novel'][0] / args.steps
@@ -390,6 +412,7 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roofline,
+        'roofline_l2': roofline_l2,
         'kernels': kernels,
         'paths': paths,
         'novel_hits_per_step': int(len(hits_value)),
