@@ -706,21 +706,32 @@ def test_full_size_properties(kv, oracle):
     assert min(counts) >= 1
 
 
-def test_partitioned_update_path_is_exact():
-    """Sketches larger than L2 use the region-partitioned update kernels (hist / scan / scatter /
-    apply).  The path is chosen per process from the sketch size, so a child process with the
-    threshold forced to zero and tiny regions re-runs the count parity tests through it."""
+def _rerun_in_child(selection, **env_overrides):
+    """Library tunables are read once per process, so variants run in a child pytest."""
     import subprocess
     import sys
-    env = dict(os.environ, KV_PART_MIN_BYTES='0', KV_PART_REGION_LOG2='10')
-    if env.get('KV_PART_CHILD'):
-        pytest.skip('already inside the forced-partition child')
-    env['KV_PART_CHILD'] = '1'
-    res = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-x', '-q', '-k',
-                          'consume or saturation or add_get or count_simple or full_size'],
+    if os.environ.get('KV_TEST_CHILD'):
+        pytest.skip('already inside a child run')
+    env = dict(os.environ, KV_TEST_CHILD='1', **env_overrides)
+    res = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-x', '-q', '-k', selection],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
     assert res.returncode == 0, res.stdout[-3000:]
     assert ' passed' in res.stdout
+
+
+def test_partitioned_update_path_is_exact():
+    """Sketches larger than L2 use the region-partitioned update kernels (hist / scan / scatter /
+    apply).  The path is chosen from the sketch size, so a child process with the threshold
+    forced to zero and tiny regions re-runs the count parity tests through it."""
+    _rerun_in_child('consume or saturation or add_get or count_simple or full_size',
+                    KV_PART_MIN_BYTES='0', KV_PART_REGION_LOG2='10')
+
+
+def test_multi_chunk_batches_are_exact():
+    """A batch larger than the per-chunk scratch is hashed and applied chunk by chunk; the
+    order-dependent n_unique_kmers must survive the chunk boundaries.  Child process with a
+    2048-position chunk (a few reads per chunk)."""
+    _rerun_in_child('consume or count_simple or novel_cli_microtrio or count_cli_with_mask', KV_CHUNK_BASES='2048')
 
 
 def test_khmer_namespace_drop_in(kv, tmp_path):
