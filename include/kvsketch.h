@@ -158,6 +158,15 @@ int kv_add_hashes(kv_sketch *s, const uint64_t *hashes, uint64_t n);
 int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
                          int where, uint64_t *hashes_out, uint8_t *counts_out, uint8_t *valid_out);
 
+/* khmer `counts.abundance_distribution(parser, tracking)` for one batch of reads (kevlar/dist.py:55,
+ * SURVEY 8f rank 4): in read order, every k-mer not yet present in `tracking` (any of its buckets
+ * empty) is added to it and dist_out[counts.get(kmer)] is incremented.  dist_out[256] (host) is
+ * OVERWRITTEN with this batch's histogram -- khmer's list has 65536 entries, all beyond 255 are 0.
+ * `tracking` is updated in place (kevlar builds it as Nodetable(k, 1, 1, primes=counts.hashsizes())),
+ * so consecutive batches continue one another exactly like consecutive reads of one parser. */
+int kv_abund_dist_batch(const kv_sketch *counts, kv_sketch *tracking, const uint8_t *bases, const uint64_t *offsets,
+                        uint64_t n_reads, int where, uint64_t *dist_out);
+
 /* Multi-GPU merge of per-GPU partial sketches (plan A).  The host runs the
  * collective (NCCL via torch.distributed) on a widened copy between these two kernels:
  *   kv_sketch_widen:  counters -> one IEEE half (8-bit counters; NCCL has no 16-bit integer

@@ -30,6 +30,7 @@ from kevlar_b200 import count
 from kevlar_b200 import novel
 from kevlar_b200 import filter
 from kevlar_b200 import unband
+from kevlar_b200 import dist
 from kevlar_b200 import cli
 
 __version__ = '0.1.0+b200'

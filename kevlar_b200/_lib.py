@@ -61,6 +61,7 @@ SYMBOLS = [
     ('kv_get_hashes', c_int, [_P, _P, c_uint64, _P]),
     ('kv_add_hashes', c_int, [_P, _P, c_uint64]),
     ('kv_kmer_counts_batch', c_int, [_P, _P, _P, c_uint64, c_int, _P, _P, _P]),
+    ('kv_abund_dist_batch', c_int, [_P, _P, _P, _P, c_uint64, c_int, _P]),
     ('kv_sketch_widen', c_int, [_P, _P, POINTER(c_uint64), POINTER(c_int)]),
     ('kv_sketch_narrow', c_int, [_P, _P]),
     ('kv_sketch_merge_peers', c_int, [_P, POINTER(_P), c_int, c_uint64, c_uint64]),

@@ -1,16 +1,17 @@
-"""Command-line front end: the `count`, `novel`, `filter` and `unband` subcommands with the
+"""Command-line front end: the `count`, `novel`, `filter`, `unband` and `dist` subcommands with the
 flags, defaults and dispatch of kevlar/cli/__init__.py:31-108."""
 import argparse
 import sys
 
 import kevlar_b200
-from . import count, novel, filter, unband
+from . import count, novel, filter, unband, dist
 
 mains = {
     'count': kevlar_b200.count.main,
     'novel': kevlar_b200.novel.main,
     'filter': kevlar_b200.filter.main,
     'unband': kevlar_b200.unband.main,
+    'dist': kevlar_b200.dist.main,
 }
 
 subparser_funcs = {
@@ -18,6 +19,7 @@ subparser_funcs = {
     'novel': novel.subparser,
     'filter': filter.subparser,
     'unband': unband.subparser,
+    'dist': dist.subparser,
 }
 
 

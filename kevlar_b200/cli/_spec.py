@@ -1,7 +1,8 @@
 """Declarative description of the command-line surface.
 
 The flags, metavars, defaults and types are the reference's (kevlar/cli/count.py:42-80,
-kevlar/cli/novel.py:65-155, kevlar/cli/filter.py:23-52, kevlar/cli/unband.py) because scripts and
+kevlar/cli/novel.py:65-155, kevlar/cli/filter.py:23-52, kevlar/cli/unband.py,
+kevlar/cli/dist.py:14-46) because scripts and
 workflows depend on them; everything is data here and `build` turns a spec into an argparse
 sub-parser."""
 import argparse
@@ -104,6 +105,24 @@ UNBAND = {
             help='number of temporary batches the records are spread over by read name; default 16'),
         OUT,
         opt('infile', nargs='+', help='augmented FASTA/FASTQ files'),
+    ])],
+}
+
+DIST = {
+    'name': 'dist',
+    'description': 'Abundance distribution of the k-mers a mask selects (e.g. single-copy exonic k-mers): '
+                   'mean, standard deviation and optionally the whole table.',
+    'groups': [(None, [
+        OUT, KSIZE,
+        opt('-M', '--memory', type=khmer_args.memory_setting, default=1e6, metavar='MEM',
+            help='bytes of sketch for the masked count'),
+        THREADS,
+        opt('-p', '--plot', metavar='PNG', help='draw the distribution into PNG (needs matplotlib)'),
+        opt('--tsv', metavar='TSV', help='write the distribution as a tab-separated table'),
+        opt('--plot-xlim', metavar=('MIN', 'MAX'), type=int, nargs=2, default=(0, 100),
+            help='abundance range of the plot; default `0 100`'),
+        opt('mask', help='nodetable of the k-mers to count'),
+        opt('infiles', nargs='+', help='FASTA/FASTQ input, plain or gzipped'),
     ])],
 }
 

@@ -11,6 +11,7 @@
 //   K4  kv_novel_kernel         fused hash + case/control lookups + thresholds
 //                               (kevlar/novel.py:21-53,123-169)
 //   K5  kv_occ_rebuild / kv_first_min / kv_first_resolve / kv_popcount   exact n_unique_kmers;
+//       kv_abund_dist_kernel    abundance histogram of first-seen k-mers (kevlar dist)
 //       kv_occupied_kernel      n_occupied
 //   K6  kv_widen / kv_narrow / kv_merge_peers kernels   multi-GPU saturating merge
 //   +   kv_get_kernel, kv_gather_kernel, kv_expand_bits_kernel, kv_state_rebuild_kernel   helpers
@@ -552,6 +553,22 @@ __global__ void kv_popcount_kernel(const uint32_t *__restrict__ words, uint64_t 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) mine += __popc(words[i]);
     mine = __reduce_add_sync(0xffffffffu, mine);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
+}
+
+// khmer abundance_distribution (kevlar/dist.py:55): hist[counts.get(h)] += 1 for every position the
+// first-touch passes marked fresh in the TRACKING sketch.  Per-CTA histogram in shared memory.
+__global__ void __launch_bounds__(256) kv_abund_dist_kernel(KvView counts, const uint64_t *__restrict__ hashes,
+                                                            const uint32_t *__restrict__ fresh, uint64_t n,
+                                                            unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride)
+        if ((__ldg(fresh + (g >> 5)) >> (g & 31)) & 1u) atomicAdd(&sh[kv_get(counts, hashes[g]) & 255u], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
 }
 
 // khmer _occupied_bins: non-zero buckets of table 0

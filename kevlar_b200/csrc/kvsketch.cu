@@ -82,7 +82,7 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small;
+    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small, hist;
     // sketches between these sizes take the region-partitioned update path (measured: 1.2-1.7x over
     // direct random atomics from 256 MB to 4 GB, break-even at 16 GB; profiles/r01_notes.md)
     uint64_t part_min_bytes = 128ull << 20, part_max_bytes = 8ull << 30;
@@ -864,8 +864,9 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
 }
 
 // exact n_unique_kmers contribution of one chunk (must run before the chunk's increments)
+// dist_counts != NULL: also histogram dist_counts.get(h) over the fresh positions into d_hist[256]
 static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid,
-                          uint64_t n)
+                          uint64_t n, const kv_sketch *dist_counts = nullptr, unsigned long long *d_hist = nullptr)
 {
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
@@ -895,12 +896,16 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
     kv_l2_window(ctx, nullptr, 0);
     LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_popcount_kernel, kv_grid_for(ctx, n_words), 256, (const uint32_t *)ctx->fresh.p, n_words,
              s->d_unique);
+    if (dist_counts)
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_abund_dist_kernel, grid, 256, kv_view(dist_counts), d_hashes,
+                 (const uint32_t *)ctx->fresh.p, n, d_hist);
     return KV_OK;
 }
 
 // apply one chunk of hashes (device, n < 2^32) to the sketch: exact-unique bookkeeping first
 // (it must see the buckets as they were before this chunk), then the saturating increments
-static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n)
+static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n,
+                           const kv_sketch *dist_counts = nullptr, unsigned long long *d_hist = nullptr)
 {
     if (!n) return KV_OK;
     KvView v = kv_view(s);
@@ -908,8 +913,10 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
         KV_TRY(kv_state_rebuild_locked(ctx, s));
         s->state_stale = false;
     }
-    if (s->track_unique) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n));
-    else s->unique_valid = false;
+    if (s->track_unique || dist_counts) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n, dist_counts, d_hist));
+    if (!s->track_unique) s->unique_valid = false;
+    // abundance_distribution counts a k-mer into the tracking sketch only when it was new there
+    if (dist_counts) d_valid = (const uint32_t *)ctx->fresh.p;
     // large counter sketches: region-partitioned updates (tables must index with 32 bits, <= 4 tables)
     bool partitioned = s->bits != 1 && s->flat_bytes >= ctx->part_min_bytes && s->flat_bytes <= ctx->part_max_bytes &&
                        s->n_tables <= 4;
@@ -1319,6 +1326,57 @@ extern "C" int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, co
     if (hashes_out) CU(cudaMemcpyAsync(hashes_out, p.hashes, b.total * 8, cudaMemcpyDeviceToHost, ctx->compute));
     if (counts_out) CU(cudaMemcpyAsync(counts_out, d_counts, b.total, cudaMemcpyDeviceToHost, ctx->compute));
     if (valid_out) CU(cudaMemcpyAsync(valid_out, d_valid8, b.total, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ abundance distribution
+
+extern "C" int kv_abund_dist_batch(const kv_sketch *counts, kv_sketch *tracking, const uint8_t *bases,
+                                   const uint64_t *offsets, uint64_t n_reads, int where, uint64_t *dist_out)
+{
+    if (!counts || !tracking || !dist_out) return kv_fail(KV_EINVAL, "null argument");
+    if (counts == tracking) return kv_fail(KV_EINVAL, "the tracking sketch must not be the counts sketch");
+    if (tracking->device != counts->device) return kv_fail(KV_EINVAL, "tracking sketch lives on another device");
+    if (tracking->ksize != counts->ksize || tracking->hasher != counts->hasher)
+        return kv_fail(KV_EINVAL, "tracking sketch must use the same k-mer size and hash function as the counts");
+    if (counts->n_shards > 1 || tracking->n_shards > 1)
+        return kv_fail(KV_EINVAL, "abundance distribution is not defined on bin-range shards");
+    memset(dist_out, 0, 256 * sizeof(uint64_t));
+    if (n_reads == 0) return KV_OK;
+    if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(counts->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(counts->device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+    if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
+    KV_TRY(kv_buf_ensure(ctx->hist, 256 * sizeof(unsigned long long)));
+    unsigned long long *d_hist = (unsigned long long *)ctx->hist.p;
+    CU(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), ctx->compute));
+    CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
+    // same chunking as kv_consume_batch: the tracking updates of chunk i are in place before the
+    // first-touch passes of chunk i+1
+    const uint64_t chunk_limit = std::min<uint64_t>(ctx->chunk_bases, (0xfffffff0ull / (uint64_t)tracking->n_tables) / KV_TILE * KV_TILE);
+    const uint64_t chunk_tiles = chunk_limit / KV_TILE;
+    const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
+    KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
+    KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
+        uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
+        uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
+        KvHashParams p;
+        memset(&p, 0, sizeof p);
+        p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+        p.total = b.total; p.tile0 = t0; p.k = counts->ksize;
+        p.hashes = (uint64_t *)ctx->hashes.p; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+        if (counts->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)nt));
+        else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)nt));
+        KV_TRY(kv_apply_hashes(ctx, tracking, p.hashes, p.valid, npos, counts, d_hist));
+    }
+    kv_stage_done(ctx, &b);
+    CU(cudaMemcpyAsync(dist_out, d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }

@@ -274,6 +274,30 @@ class _Sketch(object):
             raise ValueError('Band number must be less than number of bands')
         return self._consume_parser(parser, num_bands, band, mask, threshold, consume_masked)
 
+    def abundance_distribution_batch(self, bases, offsets, tracking, where=MEM_HOST):
+        """One kv_abund_dist_batch call: numpy uint64[256] histogram of ``self.get(kmer)`` over the
+        k-mers of the batch that ``tracking`` had not seen yet (``tracking`` is updated)."""
+        if not isinstance(tracking, _Sketch):
+            raise TypeError('tracking must be a sketch')
+        if where == MEM_HOST:
+            bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+            bptr, optr, n_reads = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1
+        else:
+            bptr, (optr, n_reads) = bases, offsets
+        dist = np.zeros(256, dtype=np.uint64)
+        check(lib().kv_abund_dist_batch(self._h, tracking._h, bptr, optr, n_reads, where, dist.ctypes.data))
+        return dist
+
+    def abundance_distribution(self, parser, tracking):
+        """khmer ``abundance_distribution(parser, tracking)`` (kevlar/dist.py:55): list of 65536
+        counts, entry i = number of distinct (first-seen in ``tracking``) k-mers with abundance i."""
+        if isinstance(parser, str):
+            parser = ReadParser(parser)
+        total = np.zeros(256, dtype=np.uint64)
+        for batch in parser.batches(BATCH_BASES):
+            total += self.abundance_distribution_batch(batch.bases, batch.offsets, tracking)
+        return [int(x) for x in total] + [0] * (65536 - 256)
+
     # --------------------------------------------------------------------- I/O
     def save(self, filename):
         check(lib().kv_sketch_save(self._h, str(filename).encode()))

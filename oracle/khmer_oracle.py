@@ -76,6 +76,8 @@ def _load():
     lib.ko_consume_batch.restype = c_uint64
     lib.ko_consume_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int, c_void_p,
                                      c_int, c_int, c_int]
+    lib.ko_abund_dist_batch.restype = None
+    lib.ko_abund_dist_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]
     lib.ko_novel_batch.restype = c_uint64
     lib.ko_novel_batch.argtypes = [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int, c_void_p, c_void_p,
                                    c_uint64, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_uint64,
@@ -317,6 +319,24 @@ class _Sketch(object):
         return _lib.ko_consume_batch(self._h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1,
                                      num_bands or 0, band or 0, mask._h if mask is not None else None,
                                      int(threshold), int(bool(consume_masked)), threads)
+
+    def abundance_distribution(self, parser, tracking):
+        """khmer abundance_distribution (kevlar/dist.py:55): list of 65536 counts."""
+        if isinstance(parser, str):
+            parser = ReadParser(parser)
+        dist = np.zeros(256, dtype=np.uint64)
+        seqs = [read.sequence for read in parser.shared_iter()]
+        if seqs:
+            bases, offs = reads_to_batch(seqs)
+            self.abundance_distribution_batch(bases, offs, tracking, dist)
+        return [int(x) for x in dist] + [0] * (65536 - 256)
+
+    def abundance_distribution_batch(self, bases, offs, tracking, dist):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        _lib.ko_abund_dist_batch(self._h, tracking._h, bases.ctypes.data, offs.ctypes.data, len(offs) - 1,
+                                 dist.ctypes.data)
+        return dist
 
     # -- I/O
     def save(self, filename):

@@ -469,6 +469,44 @@ uint64_t ko_consume_batch(ko_sketch *s, const uint8_t *bases, const uint64_t *of
     return j.consumed;
 }
 
+/* ---------------------------------------------------- abundance distribution */
+
+/* khmer Hashtable::abundance_distribution(parser, tracking), the call kevlar/dist.py:55 makes
+ * (dib-lab/khmer, oxli/hashtable.cc) -- restated for a batch of reads, single-threaded, file order:
+ *     for each k-mer hash h of the (cleaned) read, in order:
+ *         if tracking.get_count(h) == 0:  tracking.count(h);  dist[counts.get_count(h)] += 1
+ * dist has 65536 entries in khmer (MAX_BIGCOUNT + 1); counts here never exceed 255, so the caller
+ * passes 256 and pads.  UNPINNED corner: reads with bytes outside ACGT -- restated with the same
+ * cleaning as the count path; no reference fixture for `kevlar dist` holds one. */
+typedef struct {
+    const ko_sketch *counts;
+    ko_sketch *tracking;
+    uint64_t *dist;
+} dist_ctx;
+
+static void dist_cb(void *vctx, uint64_t h)
+{
+    dist_ctx *c = (dist_ctx *)vctx;
+    if (ko_get_hash(c->tracking, h) != 0) return;
+    ko_add_hash(c->tracking, h);
+    c->dist[ko_get_hash(c->counts, h)]++;
+}
+
+void ko_abund_dist_batch(const ko_sketch *counts, ko_sketch *tracking, const uint8_t *bases,
+                         const uint64_t *offs, uint64_t n_reads, uint64_t *dist /* [256], added to */)
+{
+    dist_ctx c = {counts, tracking, dist};
+    uint8_t *buf = NULL; uint64_t cap = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        uint64_t len = offs[r + 1] - offs[r];
+        if (len < (uint64_t)counts->ksize) continue;
+        if (len > cap) { cap = len * 2; buf = (uint8_t *)realloc(buf, cap); }
+        for (uint64_t i = 0; i < len; i++) buf[i] = clean_base(bases[offs[r] + i]);
+        for_each_hash(counts->hasher, counts->ksize, buf, len, dist_cb, &c);
+    }
+    free(buf);
+}
+
 /* --------------------------------------------------------------- novel scan */
 
 typedef struct {

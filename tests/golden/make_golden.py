@@ -47,7 +47,8 @@ COPY = [
     'collect.alpha.txt', 'worm.augfasta', 'trio1/novel_3_1,2.txt',
     'screen-case.fa', 'screen-ctrl.fa', 'ambig.fasta',
     'example1.augfastq', 'example2.augfastq', 'example2.augfastq.gz',
-    'minitrio/mask.nt', 'minitrio/trio-proband-mask-counts.ct',
+    'minitrio/mask.nt', 'minitrio/trio-proband-mask-counts.ct', 'minitrio/trio-proband.fq.gz',
+    'minitrio/trio-proband-dist.tsv',
     'case-low-abund/case.sct', 'ctrl-high-abund/ctrl1.sct',
 ]
 COPY_GZ = ['trio1/case1.fq', 'trio1/ctrl1.fq', 'trio1/ctrl2.fq']
@@ -190,12 +191,17 @@ def generate(env, root):
     subprocess.check_call([sys.executable, drv, REFDATA, gen], env=env, cwd=root)
     tests = ['test_count.py', 'test_sketch.py', 'test_novel.py', 'test_filter.py', 'test_seqio.py',
              'test_unband.py']
+    # test_dist.py: the tests that go through compute_dist() need DataFrame.append, which the pandas
+    # in this image (3.x) no longer has, and test_calc_mu_sigma asserts on a bare pytest.approx(),
+    # which pytest 9 rejects -- the reference itself cannot run those here
+    dist_tests = ['test_dist.py::' + t for t in ('test_count_first_pass', 'test_count_second_pass',
+                                                 'test_musigma_empty_dist')]
     res = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-p', 'no:cacheprovider', '-W',
-                          'ignore'] + ['kevlar/tests/' + t for t in tests],
+                          'ignore'] + ['kevlar/tests/' + t for t in tests + dist_tests],
                          env=env, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(os.path.join(HERE, 'reference_tests_over_oracle.log'), 'w') as fh:
         fh.write('# reference pytest files run UNMODIFIED with oracle/khmer_oracle.py as `khmer`\n')
-        fh.write('# files: ' + ' '.join(tests) + '\n')
+        fh.write('# files: ' + ' '.join(tests + dist_tests) + '\n')
         keep = [ln for ln in res.stdout.splitlines() if 'passed' in ln or 'failed' in ln or 'error' in ln.lower()]
         fh.write('\n'.join(keep[-5:]) + '\n')
     print(res.stdout.splitlines()[-1])

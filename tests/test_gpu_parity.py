@@ -723,7 +723,7 @@ def test_partitioned_update_path_is_exact():
     """Sketches larger than L2 use the region-partitioned update kernels (hist / scan / scatter /
     apply).  The path is chosen from the sketch size, so a child process with the threshold
     forced to zero and tiny regions re-runs the count parity tests through it."""
-    _rerun_in_child('consume or saturation or add_get or count_simple or full_size',
+    _rerun_in_child('consume or saturation or add_get or count_simple or full_size or abundance_distribution',
                     KV_PART_MIN_BYTES='0', KV_PART_REGION_LOG2='10')
 
 
@@ -732,7 +732,8 @@ def test_multi_chunk_batches_are_exact():
     order-dependent n_unique_kmers must survive the chunk boundaries.  Child process with a
     2048-position chunk (a few reads per chunk)."""
     # (the saturation test is left out: it asserts that the overflow redo fires, which needs big chunks)
-    _rerun_in_child('(consume and not saturation) or count_simple or novel_cli_microtrio or count_cli_with_mask',
+    _rerun_in_child('(consume and not saturation) or count_simple or novel_cli_microtrio or count_cli_with_mask '
+                    'or abundance_distribution or dist_passes',
                     KV_CHUNK_BASES='2048')
 
 
@@ -837,3 +838,78 @@ def test_get_kmer_counts_many(kv, oracle):
         assert list(counts) == c.get_kmer_counts(seq)
     with pytest.raises(ValueError):
         g.get_kmer_counts_many(['ACGT' * 10, 'ACGTN' * 10])
+
+
+# ------------------------------------------------------------------ kevlar dist
+
+DIST_ABUND_10K = {10: 6, 11: 10, 12: 12, 13: 18, 14: 16, 15: 11, 16: 9, 17: 9, 18: 11, 19: 8, 20: 9, 21: 7, 22: 3}
+
+
+def test_dist_passes_golden(kv, tmp_path):
+    """kevlar/tests/test_dist.py:25-43: the masked first pass byte-for-byte, then the second pass's
+    abundance dictionary."""
+    from kevlar_b200.dist import count_first_pass, count_second_pass
+    mask = kv.khmer.Nodetable.load(golden_data('minitrio/mask.nt'))
+    counts = kv.khmer.Counttable(31, 1e4, 4)
+    reads = golden_data('minitrio/trio-proband.fq.gz')
+    count_first_pass([reads], counts, mask)
+    out = str(tmp_path / 'first.ct')
+    counts.save(out)
+    assert filecmp.cmp(out, golden_data('minitrio/trio-proband-mask-counts.ct'), shallow=False)
+    loaded = kv.khmer.Counttable.load(golden_data('minitrio/trio-proband-mask-counts.ct'))
+    assert count_second_pass([reads], loaded) == DIST_ABUND_10K
+
+
+def test_dist_cli_golden(kv, tmp_path):
+    """kevlar/tests/test_dist.py:69-122: mu/sigma on stdout; the TSV equals the file shipped with
+    the reference (minitrio/trio-proband-dist.tsv) byte for byte."""
+    import json
+    tsv = str(tmp_path / 'dist.tsv')
+    out, _ = _run_cli(kv, ['dist', '--tsv', tsv, golden_data('minitrio/mask.nt'),
+                           golden_data('minitrio/trio-proband.fq.gz')])
+    js = json.loads(out)
+    assert open(tsv).read() == open(golden_data('minitrio/trio-proband-dist.tsv')).read()
+    from kevlar_b200.dist import dist
+    mask = kv.khmer.Nodetable.load(golden_data('minitrio/mask.nt'))
+    mu, sigma, data = dist([golden_data('minitrio/trio-proband.fq.gz')], mask, memory=4e4)
+    assert mu == pytest.approx(15.32558, abs=1e-5) and sigma == pytest.approx(3.280581, abs=1e-5)
+    assert list(data['Count'][-5:]) == [11.0, 8.0, 9.0, 7.0, 3.0]
+    assert js['mu'] > 0 and js['sigma'] > 0
+
+
+def test_dist_empty(kv):
+    """kevlar/tests/test_dist.py:78-85."""
+    from kevlar_b200.dist import dist, KevlarZeroAbundanceDistError
+    mask = kv.khmer.Nodetable(31, 1e4, 4)
+    mask.consume('GATTACA' * 10)
+    mask.consume('A' * 50)
+    with pytest.raises(KevlarZeroAbundanceDistError):
+        dist([golden_data('minitrio/trio-proband.fq.gz')], mask, memory=4e4)
+
+
+@pytest.mark.parametrize('counts_cls,track_cls', [('Counttable', 'Nodetable'), ('SmallCounttable', 'Nodetable'),
+                                                  ('Countgraph', 'Nodegraph'), ('Counttable', 'Counttable')])
+def test_abundance_distribution_matches_oracle(kv, oracle, counts_cls, track_cls):
+    """Random ragged reads with repeats, heavy table collisions (tiny tracking tables), dirty bases
+    and several batches sharing one tracking sketch: histogram and tracking tables bit-exact."""
+    k = 21
+    genome = LETTERS[np.random.default_rng(3).integers(0, 4, size=4000)]
+    reads = random_reads(11, 900, lo=10, hi=150, genome=genome) + random_reads(12, 60, alphabet=b'ACGTNacgt')
+    from oracle.khmer_oracle import reads_to_batch
+    g_counts, c_counts = getattr(kv.khmer, counts_cls)(k, 3000, 4), getattr(oracle, counts_cls)(k, 3000, 4)
+    bases, offs = reads_to_batch(reads)
+    g_counts.consume_batch(bases, offs)
+    c_counts.consume_batch(bases, offs)
+    g_track = getattr(kv.khmer, track_cls)(k, 1, 1, primes=[1009, 997, 991])
+    c_track = getattr(oracle, track_cls)(k, 1, 1, primes=[1009, 997, 991])
+    for part in (reads[:300], reads[300:301], [], reads[301:]):
+        bases, offs = reads_to_batch(part)
+        want = np.zeros(256, dtype=np.uint64)
+        if part:
+            c_counts.abundance_distribution_batch(bases, offs, c_track, want)
+        got = g_counts.abundance_distribution_batch(bases, offs, g_track)
+        assert got.tolist() == want.tolist()
+        assert_same_sketch(g_track, c_track)
+    assert_same_sketch(g_counts, c_counts)   # the counts sketch is only read
+    with pytest.raises(ValueError):
+        g_counts.abundance_distribution_batch(bases, offs, getattr(kv.khmer, track_cls)(k + 2, 1000, 2))

@@ -373,3 +373,44 @@ def test_gloo_two_rank_merge_equals_single_process(oracle, tmp_path):
         if name == 'Counttable':
             assert max(max(t) for t in want) == 255      # saturation really happened
     assert res[0]['hit_reads'] == [0, 1, 2, 2000, 2001, 2002] == res[1]['hit_reads']
+
+
+# ------------------------------------------------------------------ kevlar dist host logic
+
+DIST_ABUND = {10: 6, 11: 10, 12: 12, 13: 18, 14: 16, 15: 11, 16: 9, 17: 9, 18: 11, 19: 8, 20: 9, 21: 7, 22: 3}
+
+
+def test_dist_mu_sigma():
+    """kevlar/tests/test_dist.py:46-56."""
+    from kevlar_b200.dist import calc_mu_sigma, KevlarZeroAbundanceDistError
+    mu, sigma = calc_mu_sigma(DIST_ABUND)
+    assert mu == pytest.approx(15.32558, abs=1e-5)
+    assert sigma == pytest.approx(3.280581, abs=1e-5)
+    with pytest.raises(KevlarZeroAbundanceDistError, match='all k-mer abundances are 0'):
+        calc_mu_sigma({})
+
+
+def test_dist_table_matches_shipped_tsv(tmp_path):
+    """kevlar/tests/test_dist.py:59-66 and the byte layout of minitrio/trio-proband-dist.tsv."""
+    from kevlar_b200.dist import compute_dist
+    data = compute_dist(DIST_ABUND)
+    assert list(data['Count'][:5]) == [6.0, 10.0, 12.0, 18.0, 16.0]
+    assert list(data['CumulativeCount'][:5]) == [6.0, 16.0, 28.0, 46.0, 62.0]
+    shipped = open(golden_data('minitrio/trio-proband-dist.tsv')).read()
+    rows = [line.split('\t') for line in shipped.splitlines()[1:]]
+    abundance = {int(float(r[0])): int(float(r[1])) for r in rows}
+    out = str(tmp_path / 'dist.tsv')
+    compute_dist(abundance).to_csv(out, sep='\t', index=False)
+    assert open(out).read() == shipped
+
+
+def test_dist_cli_arguments():
+    """kevlar/cli/dist.py:14-46: flags and defaults."""
+    import kevlar_b200
+    args = kevlar_b200.cli.parser().parse_args(['dist', 'mask.nt', 'a.fq', 'b.fq'])
+    assert (args.cmd, args.mask, args.infiles) == ('dist', 'mask.nt', ['a.fq', 'b.fq'])
+    assert (args.ksize, args.memory, args.threads, args.plot, args.tsv, tuple(args.plot_xlim)) == \
+        (31, 1e6, 1, None, None, (0, 100))
+    args = kevlar_b200.cli.parser().parse_args(['dist', '-k', '25', '-M', '4M', '--tsv', 'o.tsv', '--plot-xlim', '0', '50',
+                                                'mask.nt', 'a.fq'])
+    assert (args.ksize, args.memory, args.tsv, list(args.plot_xlim)) == (25, 4e6, 'o.tsv', [0, 50])

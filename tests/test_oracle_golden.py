@@ -187,4 +187,42 @@ def test_manifest_and_reference_run():
         checked += 1
     assert checked > 40
     log = open(os.path.join(GOLDEN, 'reference_tests_over_oracle.log')).read()
-    assert '83 passed' in log and 'failed' not in log
+    assert '86 passed' in log and 'failed' not in log
+
+
+DIST_ABUND_10K = {10: 6, 11: 10, 12: 12, 13: 18, 14: 16, 15: 11, 16: 9, 17: 9, 18: 11, 19: 8, 20: 9, 21: 7, 22: 3}
+
+
+def test_dist_first_pass_golden(oracle, tmp_path):
+    """kevlar/tests/test_dist.py:25-33: masked count of the minitrio proband, byte-for-byte."""
+    mask = oracle.Nodetable.load(golden_data('minitrio/mask.nt'))
+    counts = oracle.Counttable(31, 1e4, 4)
+    counts.consume_seqfile_with_mask(oracle.ReadParser(golden_data('minitrio/trio-proband.fq.gz')), mask,
+                                     threshold=1, consume_masked=True)
+    out = str(tmp_path / 'first.ct')
+    counts.save(out)
+    assert filecmp.cmp(out, golden_data('minitrio/trio-proband-mask-counts.ct'), shallow=False)
+
+
+def test_dist_second_pass_golden(oracle):
+    """kevlar/tests/test_dist.py:36-43: abundance_distribution with a tracking Nodetable built on
+    the counts' table sizes."""
+    counts = oracle.Counttable.load(golden_data('minitrio/trio-proband-mask-counts.ct'))
+    tracking = oracle.Nodetable(31, 1, 1, primes=counts.hashsizes())
+    assert tracking.hashsizes() == counts.hashsizes()
+    dist = counts.abundance_distribution(oracle.ReadParser(golden_data('minitrio/trio-proband.fq.gz')), tracking)
+    assert len(dist) == 65536
+    assert {a: c for a, c in enumerate(dist) if a > 0 and c > 0} == DIST_ABUND_10K
+
+
+def test_dist_default_memory_matches_shipped_tsv(oracle):
+    """kevlar/tests/test_dist.py:106-122 + the shipped minitrio/trio-proband-dist.tsv: both passes
+    at the CLI's default --memory 1M."""
+    mask = oracle.Nodetable.load(golden_data('minitrio/mask.nt'))
+    reads = golden_data('minitrio/trio-proband.fq.gz')
+    counts = oracle.Counttable(31, 1e6 / 4, 4)
+    counts.consume_seqfile_with_mask(oracle.ReadParser(reads), mask, threshold=1, consume_masked=True)
+    tracking = oracle.Nodetable(31, 1, 1, primes=counts.hashsizes())
+    dist = counts.abundance_distribution(oracle.ReadParser(reads), tracking)
+    rows = [line.split('\t') for line in open(golden_data('minitrio/trio-proband-dist.tsv')).read().splitlines()[1:]]
+    assert {a: c for a, c in enumerate(dist) if a > 0 and c > 0} == {int(float(r[0])): int(float(r[1])) for r in rows}
