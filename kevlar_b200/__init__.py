@@ -31,6 +31,7 @@ from kevlar_b200 import novel
 from kevlar_b200 import filter
 from kevlar_b200 import unband
 from kevlar_b200 import dist
+from kevlar_b200 import simlike
 from kevlar_b200 import cli
 
 __version__ = '0.1.0+b200'

@@ -2,6 +2,7 @@
 on top of the GPU-backed classes in kevlar_b200.khmer."""
 import kevlar_b200
 from kevlar_b200 import khmer
+from kevlar_b200.fastx import batch_from_sequences
 
 # (count, graph, smallcount) -> class; the reference nests three dicts (kevlar/sketch.py:29-51)
 _CLASS_BY_TRAIT = {
@@ -83,3 +84,27 @@ def load_sketchfiles(sketchfiles, maxfpr=0.2):
         kevlar_b200.plog(message)
         sketches.append(sketch)
     return sketches
+
+
+def mask_from_windows(windows, ksize, maskmem, maskfile=None, maxfpr=0.01, logprefix='[kevlar::call]'):
+    """Nodetable of the k-mers spanning called variants -- the `--gen-mask` step of `kevlar call`
+    and `kevlar alac` (kevlar/call.py:136-172, kevlar/alac.py:49-65), which the reference feeds
+    one `mask.consume(window)` at a time: here all windows go to the GPU as one batch.  Windows
+    that are None or shorter than k are ignored, like there; the FPR warning text is unchanged."""
+    kevlar_b200.plog(logprefix, 'generating mask of variant-spanning k-mers')
+    numtables = 4
+    buckets = maskmem * khmer._buckets_per_byte['nodegraph'] / numtables
+    mask = khmer.Nodetable(ksize, buckets, numtables)
+    usable = [w for w in windows if w is not None and len(w) >= ksize]
+    bad = [w for w in usable if set(w) - set('ACGT')]
+    if bad:   # khmer's consume(str) raises on these
+        raise ValueError('invalid DNA character in sequence')
+    if usable:
+        batch = batch_from_sequences(usable)
+        mask.consume_batch(batch.bases, batch.offsets)
+    fpr = khmer.calc_expected_collisions(mask, max_false_pos=1.0)
+    if fpr > maxfpr:
+        kevlar_b200.plog(logprefix, 'WARNING: mask FPR is {:.4f}; exceeds user-specified limit of {:.4f}'.format(fpr, maxfpr))
+    if maskfile:
+        mask.save(maskfile)
+    return mask

@@ -48,10 +48,10 @@ COPY = [
     'screen-case.fa', 'screen-ctrl.fa', 'ambig.fasta',
     'example1.augfastq', 'example2.augfastq', 'example2.augfastq.gz',
     'minitrio/mask.nt', 'minitrio/trio-proband-mask-counts.ct', 'minitrio/trio-proband.fq.gz',
-    'minitrio/trio-proband-dist.tsv',
+    'minitrio/trio-proband-dist.tsv', 'minitrio/trio-mother.fq.gz', 'minitrio/trio-father.fq.gz',
     'case-low-abund/case.sct', 'ctrl-high-abund/ctrl1.sct',
 ]
-COPY_GZ = ['trio1/case1.fq', 'trio1/ctrl1.fq', 'trio1/ctrl2.fq']
+COPY_GZ = ['trio1/case1.fq', 'trio1/ctrl1.fq', 'trio1/ctrl2.fq', 'minitrio/refr.fa']
 
 
 def sha(path):
@@ -178,6 +178,35 @@ def run_filter(name, readfile, **kw):
 run_filter('filter_alpha', D + 'collect.alpha.txt', memory=500)
 run_filter('filter_worm', D + 'worm.augfasta', memory=1000, casemin=5, ctrlmax=0)
 run_filter('filter_trio1_nomask', D + 'trio1/novel_3_1,2.txt', memory=1e7)
+
+# simlike sketch queries: the reference's own spanning_kmer_abundances (kevlar/simlike.py:51-96)
+# on the minitrio sketches of kevlar/tests/test_simlike.py:21-31
+import khmer, random
+from kevlar.simlike import spanning_kmer_abundances
+kid, mom, dad = (khmer.Counttable(31, 1e6, 4) for _ in range(3))
+ref = khmer.SmallCounttable(31, 125000, 4)
+for sk, fn in ((kid, 'trio-proband.fq.gz'), (mom, 'trio-mother.fq.gz'), (dad, 'trio-father.fq.gz'), (ref, 'refr.fa')):
+    sk.consume_seqfile(D + 'minitrio/' + fn)
+ALT = 'TGTCTCCCTCCCCTCCACCCCCAGAAATGGGTTTTTGATAGTCTTCCAAAGTTAGGGTAGT'
+windows = [(ALT, 'TGTCTCCCTCCCCTCCACCCCCAGAAATGGCTTTTTGATAGTCTTCCAAAGTTAGGGTAGT'),
+           (ALT, 'TGTCTCCCTCCCCTCCACCCCCAGAAATGGGAAATTTTTGATAGTCTTCCAAAGTTAGGGTAGT')]
+rng = random.Random(2018)
+genome = ''.join(line.strip() for line in open(D + 'minitrio/refr.fa') if not line.startswith('>')).upper()
+for _ in range(12):   # SNV-like and deletion-like windows cut from the genome
+    at = rng.randrange(100, len(genome) - 200)
+    refw = genome[at:at + 61]
+    alt = refw[:30] + rng.choice([c for c in 'ACGT' if c != refw[30]]) + refw[31:]
+    windows.append((alt, refw))
+    windows.append((refw[:28] + refw[33:], refw))
+cases = []
+for alt, refw in windows:
+    for drop in (False, True):
+        abunds, refrabunds, ndropped = spanning_kmer_abundances(alt, refw, kid, (mom, dad), ref, dropoutliers=drop)
+        cases.append({'alt': alt, 'refr': refw, 'dropoutliers': drop, 'abundances': abunds,
+                      'refr_abunds': refrabunds, 'ndropped': ndropped})
+assert cases[0]['ndropped'] == 3 and cases[0]['abundances'][0][:4] == [7, 6, 6, 6]   # test_simlike.py:88-91
+with open(OUT + 'simlike_spanning.json', 'w') as fh:
+    json.dump(cases, fh, indent=0)
 '''
 
 

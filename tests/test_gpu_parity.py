@@ -913,3 +913,54 @@ def test_abundance_distribution_matches_oracle(kv, oracle, counts_cls, track_cls
     assert_same_sketch(g_counts, c_counts)   # the counts sketch is only read
     with pytest.raises(ValueError):
         g_counts.abundance_distribution_batch(bases, offs, getattr(kv.khmer, track_cls)(k + 2, 1000, 2))
+
+
+# ------------------------------------------------------------------ simlike queries, mask generation
+
+def test_simlike_spanning_abundances_golden(kv):
+    """kevlar/simlike.py:22-96 on the minitrio sketches of kevlar/tests/test_simlike.py:21-31: equal
+    to the reference's own function over the oracle (gen/simlike_spanning.json, whose first entry
+    is the literal expectation of test_simlike.py:88-100), one window at a time and batched."""
+    import json
+    from kevlar_b200.simlike import spanning_kmer_abundances, spanning_kmer_abundances_many
+    kid, mom, dad = (kv.khmer.Counttable(31, 1e6, 4) for _ in range(3))
+    ref = kv.khmer.SmallCounttable(31, 125000, 4)
+    for sk, fn in ((kid, 'trio-proband.fq.gz'), (mom, 'trio-mother.fq.gz'), (dad, 'trio-father.fq.gz'), (ref, 'refr.fa.gz')):
+        sk.consume_seqfile(golden_data('minitrio/' + fn))
+    cases = json.load(open(golden_gen('simlike_spanning.json')))
+    assert len(cases) == 52
+    for drop in (False, True):
+        subset = [c for c in cases if c['dropoutliers'] == drop]
+        many = spanning_kmer_abundances_many([(c['alt'], c['refr']) for c in subset], kid, (mom, dad), ref, dropoutliers=drop)
+        for c, (abunds, refr_abunds, ndropped) in zip(subset, many):
+            assert (abunds, refr_abunds, ndropped) == (c['abundances'], c['refr_abunds'], c['ndropped'])
+    for c in cases[:6]:
+        got = spanning_kmer_abundances(c['alt'], c['refr'], kid, (mom, dad), ref, dropoutliers=c['dropoutliers'])
+        assert got == (c['abundances'], c['refr_abunds'], c['ndropped'])
+
+
+def test_mask_from_windows(kv, oracle, tmp_path):
+    """kevlar/call.py:136-172 / kevlar/alac.py:49-65: the --gen-mask Nodetable, byte-identical to
+    consuming the windows one by one on the CPU."""
+    from kevlar_b200.sketch import mask_from_windows
+    genome = LETTERS[np.random.default_rng(8).integers(0, 4, size=5000)]
+    windows = [w.decode() for w in random_reads(21, 300, lo=25, hi=90, genome=genome)] + [None, 'ACGT', '']
+    out = str(tmp_path / 'mask.nt')
+    log = io.StringIO()
+    saved, kv.logstream = kv.logstream, log
+    try:
+        mask = mask_from_windows(windows, 31, 2000, maskfile=out, maxfpr=0.001)
+    finally:
+        kv.logstream = saved
+    want = oracle.Nodetable(31, 2000 * 8 / 4, 4)
+    for w in windows:
+        if w is not None and len(w) >= 31:
+            want.consume(w)
+    assert_same_sketch(mask, want)
+    ref_out = str(tmp_path / 'want.nt')
+    want.save(ref_out)
+    assert filecmp.cmp(out, ref_out, shallow=False)
+    assert 'generating mask of variant-spanning k-mers' in log.getvalue()
+    assert 'WARNING: mask FPR is' in log.getvalue() and 'exceeds user-specified limit of 0.0010' in log.getvalue()
+    with pytest.raises(ValueError):
+        mask_from_windows(['ACGTN' * 10], 31, 2000)

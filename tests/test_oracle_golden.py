@@ -226,3 +226,26 @@ def test_dist_default_memory_matches_shipped_tsv(oracle):
     dist = counts.abundance_distribution(oracle.ReadParser(reads), tracking)
     rows = [line.split('\t') for line in open(golden_data('minitrio/trio-proband-dist.tsv')).read().splitlines()[1:]]
     assert {a: c for a, c in enumerate(dist) if a > 0 and c > 0} == {int(float(r[0])): int(float(r[1])) for r in rows}
+
+
+def test_simlike_spanning_abundances_literal(oracle):
+    """kevlar/tests/test_simlike.py:82-107: the literal abundance lists of the minitrio window, as
+    produced by the reference's own spanning_kmer_abundances over the oracle (gen/simlike_spanning.json)
+    and directly through the oracle's get_kmer_counts here."""
+    cases = json.load(open(golden_gen('simlike_spanning.json')))
+    first = cases[0]
+    assert first['ndropped'] == 3 and not first['dropoutliers']
+    assert first['abundances'] == [
+        [7, 6, 6, 6, 6, 6, 6, 6, 6, 6, 7, 9, 8, 8, 9, 9, 9, 7, 7, 8, 8, 8, 7, 7, 7, 7, 7, 7],
+        [1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1],
+        [0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+    ]
+    assert first['refr_abunds'] == [2, 2, 1, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1]
+    indel = cases[2]
+    assert indel['ndropped'] == 3 and indel['refr_abunds'] == [None] * 28
+    kid = oracle.Counttable(31, 1e6, 4)
+    kid.consume_seqfile(oracle.ReadParser(golden_data('minitrio/trio-proband.fq.gz')))
+    ref = oracle.SmallCounttable(31, 125000, 4)
+    ref.consume_seqfile(oracle.ReadParser(golden_data('minitrio/refr.fa.gz')))
+    keep = [r == 0 for r in ref.get_kmer_counts(first['alt'])]
+    assert [c for c, ok in zip(kid.get_kmer_counts(first['alt']), keep) if ok] == first['abundances'][0]
