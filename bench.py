@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--hasher', default='murmur', choices=['murmur', 'twobit'],
                     help='murmur = Counttable (what `kevlar count` builds); twobit = Countgraph')
-    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p', 'sharded'],
+    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p', 'p2p_host', 'sharded'],
                     help="N>1: how per-GPU work is combined; 'sharded' = plan B, bin-range-sharded sketches")
     ap.add_argument('--reads-per-sample', type=int, default=READS_PER_SAMPLE)
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
@@ -231,7 +231,8 @@ class GpuTrio(object):
                 b, o = self.pinned[i]
                 sk.consume_batch(b.numpy(), o.numpy().view(np.uint64), wait=False)
         if self.world > 1:
-            self.lib.sync(self.device)
+            if self.args.merge != 'p2p':   # NCCL runs on torch's stream; 'p2p' stays on the library's own stream
+                self.lib.sync(self.device)
             self.multigpu.merge_sketches(self.sketches, how=self.args.merge)
         if resident:
             b, o = self.dev[0]
@@ -452,8 +453,12 @@ def run_ours(args):
             variants[label] = {'value': nk * args.steps / (ms2 / 1e3), 'ms_per_step': ms2 / args.steps}
             del r2
         line['variants'] = variants
+    if world > 1 and args.merge == 'p2p':
+        runner.multigpu.peer_sync_status()   # raises if a device-side barrier ever timed out
     print(json.dumps(line))
     if world > 1:
+        if args.merge == 'p2p':
+            runner.multigpu.release_peer_sync()
         torch.distributed.destroy_process_group()
 
 

@@ -224,6 +224,22 @@ int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);
 int kv_ipc_open(int device, const uint8_t handle[64], void **dev_ptr);
 int kv_ipc_close(int device, void *dev_ptr);
 
+/* Device-side barrier between the ranks of a multi-GPU merge (no reference counterpart; it replaces
+ * host barriers between the merge phases).  Every rank creates one object -- a small flag array in
+ * its HBM, exported as a CUDA IPC handle --, connects the handles of all its peers, and then
+ * kv_peer_barrier() ENQUEUES one tiny kernel on the device's compute stream that publishes "I am
+ * here" into every peer's array and spins until every peer has done the same: work enqueued after
+ * it starts only when all ranks' earlier work is complete and visible.  Calls are collective (same
+ * number on every rank).  A peer that does not arrive within the timeout (KV_PEER_TIMEOUT_MS,
+ * default 30000) makes the kernel give up; kv_peer_sync_status() then returns KV_ECUDA after
+ * draining the stream (0 when every barrier so far completed). */
+typedef struct kv_peer_sync kv_peer_sync;
+int kv_peer_sync_create(int device, int rank, int world, kv_peer_sync **out, uint8_t handle_out[64]);
+int kv_peer_sync_connect(kv_peer_sync *ps, int peer_rank, const uint8_t handle[64]);
+int kv_peer_barrier(kv_peer_sync *ps);
+int kv_peer_sync_status(kv_peer_sync *ps);
+int kv_peer_sync_destroy(kv_peer_sync *ps);
+
 /* khmer.ReadParser(filename) (kevlar/count.py:40, kevlar/__init__.py:125-128): FASTA/FASTQ, plain or
  * gzip.  kv_reader_next parses at least one and at most ~max_bases bases' worth of records, in
  * file order, straight into the batch layout above; n_reads = 0 means end of file.  All output

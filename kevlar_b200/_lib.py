@@ -69,6 +69,11 @@ SYMBOLS = [
     ('kv_sketch_create_shard', c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64), c_int, c_int, c_int, POINTER(_P)]),
     ('kv_sketch_shard_info', c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64)]),
     ('kv_sketch_save_part', c_int, [_P, c_char_p, c_int, c_int, c_uint64]),
+    ('kv_peer_sync_create', c_int, [c_int, c_int, c_int, POINTER(_P), _P]),
+    ('kv_peer_sync_connect', c_int, [_P, c_int, _P]),
+    ('kv_peer_barrier', c_int, [_P]),
+    ('kv_peer_sync_status', c_int, [_P]),
+    ('kv_peer_sync_destroy', c_int, [_P]),
     ('kv_hash_batch_dev', c_int, [c_int, c_int, _P, _P, c_uint64, c_int, c_int, c_int, c_int, _P, _P, c_uint64,
                                   POINTER(c_uint64), POINTER(c_uint64)]),
     ('kv_add_hashes_dev', c_int, [_P, _P, _P, c_uint64]),

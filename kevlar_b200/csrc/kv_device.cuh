@@ -10,6 +10,7 @@
 #include "../../include/kvsketch.h"
 
 #define KV_TABLES_DEV 8          // tables per sketch view carried in kernel parameters
+#define KV_MAX_RANKS 16          // ranks of one device-side barrier (one NVSwitch domain)
 
 // ------------------------------------------------------------------ sketch view
 

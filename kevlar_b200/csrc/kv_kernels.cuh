@@ -727,3 +727,36 @@ __global__ void kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec,
     }
 }
 
+
+// ------------------------------------------------------------------ device-side rank barrier
+//
+// Every rank owns an array of u32 flags in its HBM that its peers map over CUDA IPC; flag[p] is
+// written only by rank p.  Barrier number `epoch` (1, 2, ...; the same count on every rank because
+// barriers are collective): thread p publishes `epoch` into MY slot of peer p's array (release,
+// system scope -- everything earlier kernels of this stream wrote is visible to the peer before
+// the flag is) and then spins on peer p's slot of my array.  A peer can be at most one barrier
+// ahead, so ">= epoch" is the condition.  No host round trip; the next kernel in the stream
+// starts when all peers have arrived.
+struct KvPeerFlags {
+    uint32_t *peer[KV_MAX_RANKS];   // peer p's flag array (mapped), NULL for p == rank
+    uint32_t *mine;
+    int rank, world;
+};
+
+__global__ void kv_peer_barrier_kernel(KvPeerFlags f, uint32_t epoch, unsigned long long timeout_ns, unsigned *timed_out)
+{
+    const int p = threadIdx.x;
+    if (p >= f.world || p == f.rank) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.peer[p] + f.rank), "r"(epoch) : "memory");
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f.mine + p) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) { atomicExch(timed_out, 1u); break; }
+        __nanosleep(200);
+    }
+}

@@ -1489,6 +1489,100 @@ extern "C" int kv_ipc_close(int device, void *dev_ptr)
     return KV_OK;
 }
 
+// ------------------------------------------------------------------ device-side rank barrier
+
+struct kv_peer_sync {
+    int device, rank, world;
+    uint32_t *flags;            // my array (KV_MAX_RANKS slots used), own 2 MB allocation so the IPC handle maps nothing else
+    unsigned *timed_out;        // device flag raised by a barrier kernel that gave up
+    void *peer[KV_MAX_RANKS];   // mapped peer arrays
+    uint32_t epoch;
+    unsigned long long timeout_ns;
+};
+
+extern "C" int kv_peer_sync_create(int device, int rank, int world, kv_peer_sync **out, uint8_t handle_out[64])
+{
+    if (!out || !handle_out) return kv_fail(KV_EINVAL, "null argument");
+    if (world < 1 || world > KV_MAX_RANKS || rank < 0 || rank >= world)
+        return kv_fail(KV_EINVAL, "device-side barriers support 1..%d ranks", KV_MAX_RANKS);
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    kv_peer_sync *ps = new kv_peer_sync();
+    memset(ps, 0, sizeof *ps);
+    ps->device = device; ps->rank = rank; ps->world = world;
+    ps->timeout_ns = 30000ull * 1000000ull;
+    if (const char *e = getenv("KV_PEER_TIMEOUT_MS")) ps->timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
+    const size_t bytes = 2u << 20;
+    if (cudaMalloc((void **)&ps->flags, bytes) != cudaSuccess) { delete ps; return kv_fail(KV_ENOMEM, "cannot allocate barrier flags"); }
+    cudaMemset(ps->flags, 0, bytes);
+    ps->timed_out = (unsigned *)(ps->flags + 1024);   // same allocation, never touched by peers
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ps->flags));
+    memcpy(handle_out, &h, 64);
+    *out = ps;
+    return KV_OK;
+}
+
+extern "C" int kv_peer_sync_connect(kv_peer_sync *ps, int peer_rank, const uint8_t handle[64])
+{
+    if (!ps || !handle) return kv_fail(KV_EINVAL, "null argument");
+    if (peer_rank < 0 || peer_rank >= ps->world || peer_rank == ps->rank) return kv_fail(KV_EINVAL, "bad peer rank");
+    if (ps->peer[peer_rank]) return kv_fail(KV_EINVAL, "peer %d is already connected", peer_rank);
+    CU(cudaSetDevice(ps->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(&ps->peer[peer_rank], h, cudaIpcMemLazyEnablePeerAccess));
+    return KV_OK;
+}
+
+extern "C" int kv_peer_barrier(kv_peer_sync *ps)
+{
+    if (!ps) return kv_fail(KV_EINVAL, "null argument");
+    KvPeerFlags f;
+    memset(&f, 0, sizeof f);
+    for (int p = 0; p < ps->world; p++) {
+        if (p != ps->rank && !ps->peer[p]) return kv_fail(KV_EINVAL, "peer %d is not connected", p);
+        f.peer[p] = (uint32_t *)ps->peer[p];
+    }
+    f.mine = ps->flags; f.rank = ps->rank; f.world = ps->world;
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(ps->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ps->device));
+    ps->epoch++;
+    LAUNCH_C(KV_PROF_MERGE, ctx, kv_peer_barrier_kernel, 1, 32, f, ps->epoch, ps->timeout_ns, ps->timed_out);
+    return KV_OK;
+}
+
+extern "C" int kv_peer_sync_status(kv_peer_sync *ps)
+{
+    if (!ps) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(ps->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ps->device));
+    unsigned flag = 0;
+    CU(cudaMemcpyAsync(&flag, ps->timed_out, sizeof flag, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    if (flag) return kv_fail(KV_ECUDA, "a device-side barrier timed out waiting for a peer rank (KV_PEER_TIMEOUT_MS)");
+    return KV_OK;
+}
+
+extern "C" int kv_peer_sync_destroy(kv_peer_sync *ps)
+{
+    if (!ps) return KV_OK;
+    cudaSetDevice(ps->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < ps->world; p++)
+        if (ps->peer[p]) cudaIpcCloseMemHandle(ps->peer[p]);
+    cudaFree(ps->flags);
+    delete ps;
+    return KV_OK;
+}
+
 // ------------------------------------------------------------------ plumbing
 
 extern "C" int kv_stream(int device, void **cuda_stream)

@@ -170,21 +170,77 @@ def release_p2p(sketch):
             check(lib().kv_ipc_close(sketch.device, ptr))
 
 
-def merge_p2p(sketches, group=None):
+_PEER_SYNC = {}   # (device, group id) -> kv_peer_sync handle with every peer connected
+
+
+def _peer_sync(device, group=None):
+    """This rank's device-side barrier object (created and connected once per device and group)."""
+    key = (device, id(group))
+    if key in _PEER_SYNC:
+        return _PEER_SYNC[key]
+    td = dist()
+    world, rank = td.get_world_size(group), td.get_rank(group)
+    ps, handle = c_void_p(), (ctypes.c_uint8 * 64)()
+    check(lib().kv_peer_sync_create(device, rank, world, byref(ps), handle))
+    handles = [None] * world
+    td.all_gather_object(handles, bytes(handle), group=group)
+    for r, h in enumerate(handles):
+        if r != rank:
+            check(lib().kv_peer_sync_connect(ps, r, (ctypes.c_uint8 * 64)(*h)))
+    _PEER_SYNC[key] = ps
+    return ps
+
+
+def peer_sync_status(device=None):
+    """Drain the compute stream and raise if a device-side barrier gave up waiting for a peer."""
+    for (dev, _), ps in _PEER_SYNC.items():
+        if device is None or dev == device:
+            check(lib().kv_peer_sync_status(ps))
+
+
+def release_peer_sync():
+    """Unmap the peers' barrier flags (collective: call on every rank, after the last merge)."""
+    td = dist()
+    for ps in _PEER_SYNC.values():
+        check(lib().kv_peer_sync_status(ps))
+    if _PEER_SYNC and td.is_initialized():
+        td.barrier()                                   # nobody still spins on flags about to be unmapped
+    for ps in _PEER_SYNC.values():
+        check(lib().kv_peer_sync_destroy(ps))
+    _PEER_SYNC.clear()
+
+
+def merge_p2p(sketches, group=None, host_barriers=False):
     """Peer-to-peer merge with no NCCL on the data path.  Ranks exchange CUDA IPC handles of
     their table storage once; then, for all sketches together,
       phase 1 (reduce-scatter): rank r folds bytes slice(r) of every peer's table into its own
                table with one kernel of NVLink loads (kv_sketch_merge_peers) -- peers only ever
                write their OWN slice, so nobody reads bytes that are being written;
       phase 2 (all-gather): rank r pulls the finished slice(p) from every peer p.
-    Barriers separate the phases."""
+    Three barriers separate the phases (partial tables complete / slices reduced / nobody still
+    reads my table).  By default they are device-side (kv_peer_barrier: flags in peer-mapped HBM,
+    enqueued on the compute stream like the kernels around them), so the whole merge is
+    asynchronous to the host; ``host_barriers=True`` (how='p2p_host') synchronises the stream and
+    uses the process group's barrier instead -- for ranks that may reach the merge more than
+    KV_PEER_TIMEOUT_MS apart."""
     td = dist()
     if not isinstance(sketches, (list, tuple)):
         sketches = [sketches]
     world, rank = td.get_world_size(group), td.get_rank(group)
+    if world > 16:
+        host_barriers = True
     peers = [_p2p_peers(sk, group) for sk in sketches]
-    _lib.sync(sketches[0].device)
-    td.barrier(group=group)                           # every partial table is complete
+    device = sketches[0].device
+    sync = None if host_barriers else _peer_sync(device, group)
+
+    def barrier():
+        if host_barriers:
+            _lib.sync(device)
+            td.barrier(group=group)
+        else:
+            check(lib().kv_peer_barrier(sync))
+
+    barrier()                                         # every partial table is complete
     for sk, pr in zip(sketches, peers):
         _, nbytes = sk.flat_device_buffer()
         lo, hi = slice_bounds(nbytes, rank, world)
@@ -193,15 +249,13 @@ def merge_p2p(sketches, group=None):
             grp = order[i:i + 8]
             ptrs = (c_void_p * len(grp))(*[p.value for p in grp])
             check(lib().kv_sketch_merge_peers(sk._h, ptrs, len(grp), lo, hi))
-    _lib.sync(sketches[0].device)
-    td.barrier(group=group)                           # every slice is reduced
+    barrier()                                         # every slice is reduced
     for sk, pr in zip(sketches, peers):
         _, nbytes = sk.flat_device_buffer()
         for r in sorted(pr):
             plo, phi = slice_bounds(nbytes, r, world)
             check(lib().kv_sketch_copy_from_peer(sk._h, pr[r], plo, phi))
-    _lib.sync(sketches[0].device)
-    td.barrier(group=group)                           # nobody still reads my table
+    barrier()                                         # nobody still reads my table
 
 
 def merge_sketches(sketches, how='p2p', group=None):
@@ -209,8 +263,8 @@ def merge_sketches(sketches, how='p2p', group=None):
     td = dist()
     if not td.is_initialized() or td.get_world_size(group) == 1:
         return sketches
-    if how == 'p2p':
-        merge_p2p(sketches, group)
+    if how in ('p2p', 'p2p_host'):
+        merge_p2p(sketches, group, host_barriers=(how == 'p2p_host'))
     elif how in ('allgather', 'allreduce'):
         for sketch in sketches:
             (merge_allgather if how == 'allgather' else merge_allreduce)(GpuSketchAdapter(sketch), group)
@@ -335,7 +389,9 @@ class ShardedSketch(object):
         allc = torch.stack(parts)
         if self.world > 1:
             td.all_reduce(allc, op=td.ReduceOp.MIN, group=self.group)
-        return allc[stream.rank].contiguous()
+        mine = allc[stream.rank].contiguous()
+        torch.cuda.synchronize(stream.device)   # the library's kernels run on its own stream, not torch's
+        return mine
 
     def save(self, filename):
         """One OXLI v4 file (on a filesystem all ranks share), shards appended in rank order."""

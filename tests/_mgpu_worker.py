@@ -35,7 +35,7 @@ def main():
     samples = [reads(child, 6000, 1) + [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT'] * 700, reads(genome, 6000, 2),
                reads(genome, 6000, 3)]
     failures = []
-    for how in ('allreduce', 'allgather', 'p2p'):
+    for how in ('allreduce', 'allgather', 'p2p', 'p2p_host'):
         for cls in ('Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'):
             gpu, cpu = [], []
             for seqs in samples:
@@ -67,9 +67,11 @@ def main():
                     (allhits['abund'][:, :3] == ohits['abund'][:, :3]).all()
                 if not same or len(ohits) == 0:
                     failures.append('{} {} novel hits differ ({} vs {})'.format(how, cls, len(allhits), len(ohits)))
+            multigpu.peer_sync_status()
             for g in gpu:
                 multigpu.release_p2p(g)
             del gpu
+    multigpu.release_peer_sync()
     # ---- plan B: bin-range-sharded sketches: count shard-local reads, exchange hashes, save one file
     import tempfile
     shared = os.environ.get('KV_TEST_SHARED_DIR') or tempfile.gettempdir()
@@ -117,7 +119,7 @@ def main():
         print('RANK', rank, 'FAILURES:', failures)
         sys.exit(1)
     if rank == 0:
-        print('multi-GPU merge OK on', world, 'ranks: allreduce/allgather/p2p x 4 sketch types, novel hits identical; '
+        print('multi-GPU merge OK on', world, 'ranks: allreduce/allgather/p2p/p2p_host x 4 sketch types, novel hits identical; '
               'bin-range-sharded count / save / novel identical to the oracle')
     torch.distributed.destroy_process_group()
 
