@@ -186,6 +186,11 @@ int kv_sketch_widen(kv_sketch *s, void *dev_out, uint64_t *n_elems, int *elem_by
 int kv_sketch_narrow(kv_sketch *s, const void *dev_in);
 int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi);
 int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uint64_t byte_lo, uint64_t byte_hi);
+/* One-pass all-reduce of a byte slice: like kv_sketch_merge_peers, and the finished slice is also
+ * STORED into every peer's table over NVLink.  Correct when every rank calls it on its own,
+ * disjoint slice between two rank barriers (nobody else reads or writes a rank's slice): the
+ * reduce-scatter and the all-gather of the merge become one kernel with no barrier in between. */
+int kv_sketch_allreduce_peers(kv_sketch *s, void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi);
 /* Bin-range-sharded sketches (plan B; needed when one sketch exceeds one GPU): shard i
  * of n holds, of every table, a contiguous range of bins (multiples of 8 bins, so the shards'
  * bytes concatenate to khmer's exact table bytes).  A k-mer's buckets generally live on different

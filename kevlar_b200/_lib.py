@@ -66,6 +66,7 @@ SYMBOLS = [
     ('kv_sketch_narrow', c_int, [_P, _P]),
     ('kv_sketch_merge_peers', c_int, [_P, POINTER(_P), c_int, c_uint64, c_uint64]),
     ('kv_sketch_copy_from_peer', c_int, [_P, _P, c_uint64, c_uint64]),
+    ('kv_sketch_allreduce_peers', c_int, [_P, POINTER(_P), c_int, c_uint64, c_uint64]),
     ('kv_sketch_create_shard', c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64), c_int, c_int, c_int, POINTER(_P)]),
     ('kv_sketch_shard_info', c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64)]),
     ('kv_sketch_save_part', c_int, [_P, c_char_p, c_int, c_int, c_uint64]),

@@ -695,7 +695,7 @@ __global__ void kv_narrow_kernel(uint8_t *__restrict__ flat, uint64_t nbytes, in
 }
 
 struct KvPeers {
-    const uint4 *peer[8];
+    uint4 *peer[KV_MAX_RANKS - 1];
     int n;
 };
 
@@ -711,6 +711,7 @@ __device__ __forceinline__ uint32_t kv_sat_merge_word(uint32_t a, uint32_t b, in
     return lo | (hi << 4);
 }
 
+template <bool PUSH>
 __global__ void kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec, int bits, KvPeers peers)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -724,6 +725,10 @@ __global__ void kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec,
             acc.w = kv_sat_merge_word(acc.w, o.w, bits);
         }
         local[i] = acc;
+        // all-reduce in one pass: this rank owns the slice, so it also stores the finished
+        // vector into every peer's table (nobody else reads or writes this slice anywhere)
+        if (PUSH)
+            for (int p = 0; p < peers.n; p++) peers.peer[p][i] = acc;
     }
 }
 

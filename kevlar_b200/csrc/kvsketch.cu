@@ -1421,11 +1421,10 @@ static int kv_check_range(const kv_sketch *s, uint64_t &lo, uint64_t &hi)
     return KV_OK;
 }
 
-extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo,
-                                     uint64_t byte_hi)
+static int kv_merge_peers_impl(kv_sketch *s, void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi, bool push)
 {
     if (!s || (n_peers && !peer_flat)) return kv_fail(KV_EINVAL, "null argument");
-    if (n_peers < 0 || n_peers > 8) return kv_fail(KV_EINVAL, "at most 8 peers per merge");
+    if (n_peers < 0 || n_peers > KV_MAX_RANKS - 1) return kv_fail(KV_EINVAL, "at most %d peers per merge", KV_MAX_RANKS - 1);
     KV_TRY(kv_check_range(s, byte_lo, byte_hi));
     if (!n_peers || byte_lo == byte_hi) return KV_OK;
     KvCtx *ctx;
@@ -1435,12 +1434,26 @@ extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat,
     KvPeers peers;
     memset(&peers, 0, sizeof peers);
     peers.n = n_peers;
-    for (int i = 0; i < n_peers; i++) peers.peer[i] = (const uint4 *)((const uint8_t *)peer_flat[i] + byte_lo);
+    for (int i = 0; i < n_peers; i++) peers.peer[i] = (uint4 *)((uint8_t *)peer_flat[i] + byte_lo);
     uint64_t n_vec = (byte_hi - byte_lo) / 16;
-    LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
+    if (push)
+        LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel<true>, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
+    else
+        LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel<false>, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
     s->state_stale = true;
     s->unique_valid = false;
     return KV_OK;
+}
+
+extern "C" int kv_sketch_merge_peers(kv_sketch *s, const void *const *peer_flat, int n_peers, uint64_t byte_lo,
+                                     uint64_t byte_hi)
+{
+    return kv_merge_peers_impl(s, (void *const *)peer_flat, n_peers, byte_lo, byte_hi, false);
+}
+
+extern "C" int kv_sketch_allreduce_peers(kv_sketch *s, void *const *peer_flat, int n_peers, uint64_t byte_lo, uint64_t byte_hi)
+{
+    return kv_merge_peers_impl(s, peer_flat, n_peers, byte_lo, byte_hi, true);
 }
 
 extern "C" int kv_sketch_copy_from_peer(kv_sketch *s, const void *peer_flat, uint64_t byte_lo, uint64_t byte_hi)

@@ -212,17 +212,18 @@ def release_peer_sync():
 
 def merge_p2p(sketches, group=None, host_barriers=False):
     """Peer-to-peer merge with no NCCL on the data path.  Ranks exchange CUDA IPC handles of
-    their table storage once; then, for all sketches together,
-      phase 1 (reduce-scatter): rank r folds bytes slice(r) of every peer's table into its own
-               table with one kernel of NVLink loads (kv_sketch_merge_peers) -- peers only ever
-               write their OWN slice, so nobody reads bytes that are being written;
-      phase 2 (all-gather): rank r pulls the finished slice(p) from every peer p.
-    Three barriers separate the phases (partial tables complete / slices reduced / nobody still
-    reads my table).  By default they are device-side (kv_peer_barrier: flags in peer-mapped HBM,
-    enqueued on the compute stream like the kernels around them), so the whole merge is
-    asynchronous to the host; ``host_barriers=True`` (how='p2p_host') synchronises the stream and
-    uses the process group's barrier instead -- for ranks that may reach the merge more than
-    KV_PEER_TIMEOUT_MS apart."""
+    their table storage once; then, for all sketches together, rank r owns byte slice(r) of every
+    table: it loads that slice from every peer over NVLink, folds it into its own table and
+
+      default:  stores the finished slice straight into every peer's table from the same kernel
+                (kv_sketch_allreduce_peers) -- nobody else reads or writes slice(r) anywhere, so
+                the whole all-reduce is ONE kernel per sketch between two barriers, and the
+                barriers are device-side (kv_peer_barrier: flags in peer-mapped HBM, enqueued on
+                the compute stream), so the merge never blocks the host;
+      host_barriers=True (how='p2p_host'):  two phases, reduce-scatter (kv_sketch_merge_peers)
+                then all-gather (kv_sketch_copy_from_peer pulls slice(p) from peer p), separated
+                by stream syncs + process-group barriers -- for ranks that may reach the merge
+                more than KV_PEER_TIMEOUT_MS apart, or more than 16 ranks."""
     td = dist()
     if not isinstance(sketches, (list, tuple)):
         sketches = [sketches]
@@ -231,18 +232,28 @@ def merge_p2p(sketches, group=None, host_barriers=False):
         host_barriers = True
     peers = [_p2p_peers(sk, group) for sk in sketches]
     device = sketches[0].device
-    sync = None if host_barriers else _peer_sync(device, group)
+
+    def slices():
+        for sk, pr in zip(sketches, peers):
+            _, nbytes = sk.flat_device_buffer()
+            yield sk, pr, nbytes
+
+    if not host_barriers:
+        sync = _peer_sync(device, group)
+        check(lib().kv_peer_barrier(sync))            # every partial table is complete
+        for sk, pr, nbytes in slices():
+            lo, hi = slice_bounds(nbytes, rank, world)
+            ptrs = (c_void_p * len(pr))(*[pr[r].value for r in sorted(pr)])
+            check(lib().kv_sketch_allreduce_peers(sk._h, ptrs, len(pr), lo, hi))
+        check(lib().kv_peer_barrier(sync))            # every slice is reduced and stored everywhere
+        return
 
     def barrier():
-        if host_barriers:
-            _lib.sync(device)
-            td.barrier(group=group)
-        else:
-            check(lib().kv_peer_barrier(sync))
+        _lib.sync(device)
+        td.barrier(group=group)
 
     barrier()                                         # every partial table is complete
-    for sk, pr in zip(sketches, peers):
-        _, nbytes = sk.flat_device_buffer()
+    for sk, pr, nbytes in slices():
         lo, hi = slice_bounds(nbytes, rank, world)
         order = [pr[r] for r in sorted(pr)]
         for i in range(0, len(order), 8):
@@ -250,8 +261,7 @@ def merge_p2p(sketches, group=None, host_barriers=False):
             ptrs = (c_void_p * len(grp))(*[p.value for p in grp])
             check(lib().kv_sketch_merge_peers(sk._h, ptrs, len(grp), lo, hi))
     barrier()                                         # every slice is reduced
-    for sk, pr in zip(sketches, peers):
-        _, nbytes = sk.flat_device_buffer()
+    for sk, pr, nbytes in slices():
         for r in sorted(pr):
             plo, phi = slice_bounds(nbytes, r, world)
             check(lib().kv_sketch_copy_from_peer(sk._h, pr[r], plo, phi))
