@@ -344,6 +344,89 @@ __device__ __forceinline__ bool kv_window_bad(const KvTileSmem &sm, int L, int k
     return (lo | (hi & (k == 64 ? 0xffffffffu : ((1u << (k - 32)) - 1u)))) != 0;
 }
 
+// The tile positions that start a k-mer (inside one read; in strict mode also free of bytes
+// outside ACGT), as an ascending list in shared memory.  With 100 bp reads and k = 31 that is 70 %
+// of the positions, in runs that never leave a whole warp idle, so the kernels do their expensive
+// per-k-mer work over this list instead of over all positions.  Built from the read boundaries:
+// start from "every existing position", then each read end e clears [e-k+1, e) -- O(reads in the
+// tile) work instead of a boundary search per position.  Returns the list length; ends with a
+// __syncthreads().
+struct KvTileList {
+    uint32_t bits[KV_TILE / 32];        // bit l: position l of the tile starts a k-mer
+    unsigned base[KV_TILE / 32 + 1];    // exclusive prefix sums of popc(bits[]), [32] = total
+    uint16_t pos[KV_TILE];
+};
+
+__device__ __forceinline__ unsigned kv_tile_kmer_list(const KvTileSmem &sm, KvTileList &ls, const uint64_t *__restrict__ offsets,
+                                                      const uint32_t *__restrict__ tile_first, uint64_t tile, uint64_t total,
+                                                      int k, bool strict)
+{
+    const uint64_t tile_start = tile * KV_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (sm.nb >= 0) {
+        if (threadIdx.x < KV_TILE / 32) {
+            uint64_t first = tile_start + 32u * threadIdx.x;
+            ls.bits[threadIdx.x] = first >= total ? 0u : (total - first >= 32 ? 0xffffffffu : ((1u << (total - first)) - 1u));
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < sm.nb; j += KV_THREADS) {
+            const uint64_t e = sm.ends[j];
+            uint64_t lo = e >= (uint64_t)(k - 1) ? e - (uint64_t)(k - 1) : 0, hi = e;
+            if (lo < tile_start) lo = tile_start;
+            if (hi > tile_start + KV_TILE) hi = tile_start + KV_TILE;
+            if (lo >= hi) continue;
+            const int a = (int)(lo - tile_start), b = (int)(hi - tile_start);   // clear bits [a, b)
+            for (int w = a >> 5; w <= (b - 1) >> 5; w++) {
+                uint32_t m = 0xffffffffu;
+                if (w == (a >> 5)) m &= 0xffffffffu << (a & 31);
+                if (w == ((b - 1) >> 5) && (b & 31)) m &= (1u << (b & 31)) - 1u;
+                atomicAnd(&ls.bits[w], ~m);
+            }
+        }
+    } else {   // more reads in the tile than the boundary cache holds: search per position
+        for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
+            const int l = it * KV_THREADS + threadIdx.x;
+            const uint64_t g = tile_start + l;
+            bool ok = false;
+            if (g < total) {
+                uint64_t read, rs, re;
+                kv_find_read(sm, offsets, tile_first, tile, g, read, rs, re);
+                ok = g + k <= re;
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) ls.bits[l >> 5] = bal;
+        }
+    }
+    __syncthreads();
+    if (strict) {
+        for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
+            const int l = it * KV_THREADS + threadIdx.x;
+            bool drop = ((ls.bits[l >> 5] >> (l & 31)) & 1u) && kv_window_bad(sm, l + KV_FRONT, k);
+            unsigned bal = __ballot_sync(0xffffffffu, drop);
+            if (lane == 0 && bal) ls.bits[l >> 5] &= ~bal;   // word l>>5 belongs to this warp in this iteration
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        unsigned c = __popc(ls.bits[lane]), x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        ls.base[lane] = x - c;
+        if (lane == 31) ls.base[32] = x;
+    }
+    __syncthreads();
+    for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
+        const int l = it * KV_THREADS + threadIdx.x;
+        const uint32_t w = ls.bits[l >> 5];
+        if ((w >> lane) & 1u) ls.pos[ls.base[l >> 5] + __popc(w & ((1u << lane) - 1u))] = (uint16_t)l;
+    }
+    __syncthreads();
+    return ls.base[32];
+}
+
 // Canonical MurmurHash of the k-mer at local position l (khmer _hash_murmur: forward XOR
 // reverse complement, App. A.2).
 template <int KW>

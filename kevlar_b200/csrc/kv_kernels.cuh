@@ -61,49 +61,51 @@ template <int HASHER, int KW>
 __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
 {
     __shared__ KvTileSmem sm;
+    __shared__ KvTileList ls;
+    __shared__ uint32_t s_valid[KV_TILE / 32];
     const uint64_t tile = p.tile0 + blockIdx.x;
     const uint64_t tile_start = tile * KV_TILE;
     const uint64_t pos0 = p.tile0 * KV_TILE;
     kv_tile_load<HASHER == KV_HASH_TWOBIT, true>(sm, p.bases, tile_start, p.total);
     kv_tile_bounds(sm, p.offsets, p.tile_first, tile);
+    if (threadIdx.x < KV_TILE / 32) s_valid[threadIdx.x] = 0;
     __syncthreads();
+    const unsigned n_list = kv_tile_kmer_list(sm, ls, p.offsets, p.tile_first, tile, p.total, p.k, p.strict != 0);
 
+    // positions that start no k-mer get hash 0 (the output stays deterministic)
+    if (p.hashes)
+        for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
+            const int l = it * KV_THREADS + threadIdx.x;
+            if (tile_start + l < p.total && !((ls.bits[l >> 5] >> (l & 31)) & 1u)) p.hashes[tile_start + l - pos0] = 0;
+        }
+
+    // hash + band / mask predicates over the k-mer list
     unsigned n_ok = 0;
 #pragma unroll 1
-    for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
-        const int l = it * KV_THREADS + threadIdx.x;
-        const uint64_t g = tile_start + l;
-        bool ok = false;
-        uint64_t h = 0;
-        if (g < p.total) {
-            uint64_t read, rs, re;
-            kv_find_read(sm, p.offsets, p.tile_first, tile, g, read, rs, re);
-            ok = g + p.k <= re;
-            if (ok && p.strict) ok = !kv_window_bad(sm, l + KV_FRONT, p.k);
-            if (ok) {
-                h = kv_tile_hash<HASHER, KW>(sm, l, p.k);
-                if (p.banded) ok = h >= p.band_lo && h < p.band_hi;
-                if (ok && p.use_mask) {
-                    int c = (int)kv_get(p.mask, h);
-                    ok = p.consume_masked ? (c >= p.mask_threshold) : (c <= p.mask_threshold);
-                }
-            }
+    for (unsigned i = threadIdx.x; i < n_list; i += KV_THREADS) {
+        const int l = ls.pos[i];
+        uint64_t h = kv_tile_hash<HASHER, KW>(sm, l, p.k);
+        bool ok = true;
+        if (p.banded) ok = h >= p.band_lo && h < p.band_hi;
+        if (ok && p.use_mask) {
+            int c = (int)kv_get(p.mask, h);
+            ok = p.consume_masked ? (c >= p.mask_threshold) : (c <= p.mask_threshold);
         }
-        unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (g < p.total) {
-            if (p.hashes) p.hashes[g - pos0] = h;
-            if ((threadIdx.x & 31) == 0) p.valid[(g - pos0) >> 5] = bal;
-        }
+        if (p.hashes) p.hashes[tile_start + l - pos0] = h;
+        if (ok) atomicOr(&s_valid[l >> 5], 1u << (l & 31));
         n_ok += ok;
     }
+    __syncthreads();
+    if (threadIdx.x < KV_TILE / 32 && tile_start + threadIdx.x * 32 < p.total)
+        p.valid[(tile_start - pos0) / 32 + threadIdx.x] = s_valid[threadIdx.x];
     // one atomic per CTA for the k-mer count
     n_ok = __reduce_add_sync(0xffffffffu, n_ok);
-    __shared__ unsigned s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ unsigned s_total;
+    if (threadIdx.x == 0) s_total = 0;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0 && n_ok) atomicAdd(&s_cnt, n_ok);
+    if ((threadIdx.x & 31) == 0 && n_ok) atomicAdd(&s_total, n_ok);
     __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) atomicAdd(p.n_valid, (unsigned long long)s_cnt);
+    if (threadIdx.x == 0 && s_total) atomicAdd(p.n_valid, (unsigned long long)s_total);
 }
 
 // ----------------------------------------------------------------------- K3
@@ -610,24 +612,30 @@ template <int HASHER, int KW>
 __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_constant__ KvNovelParams p)
 {
     __shared__ KvTileSmem sm;
+    __shared__ KvTileList ls;
     const uint64_t tile = blockIdx.x;
     const uint64_t tile_start = tile * KV_TILE;
     kv_tile_load<HASHER == KV_HASH_TWOBIT, true>(sm, p.bases, tile_start, p.total);
     kv_tile_bounds(sm, p.offsets, p.tile_first, tile);
     __syncthreads();
 
-#pragma unroll 1
+    // any byte outside ACGT poisons the whole read (kevlar/novel.py:136-139)
     for (int it = 0; it < KV_TILE / KV_THREADS; it++) {
         const int l = it * KV_THREADS + threadIdx.x;
-        const uint64_t g = tile_start + l;
-        if (g >= p.total) continue;
-        uint64_t read, rs, re;
-        kv_find_read(sm, p.offsets, p.tile_first, tile, g, read, rs, re);
-        // any byte outside ACGT poisons the whole read (kevlar/novel.py:136-139)
         const int L = l + KV_FRONT;
-        if ((sm.bad[L >> 5] >> (L & 31)) & 1u) atomicOr(p.read_flags + read, KV_READ_SKIPPED);
-        if (g + p.k > re) continue;
-        if (kv_window_bad(sm, L, p.k)) continue;
+        if (tile_start + l < p.total && ((sm.bad[L >> 5] >> (L & 31)) & 1u)) {
+            uint64_t read, rs, re;
+            kv_find_read(sm, p.offsets, p.tile_first, tile, tile_start + l, read, rs, re);
+            atomicOr(p.read_flags + read, KV_READ_SKIPPED);
+        }
+    }
+    // k-mers of the tile (none of them touches a byte outside ACGT)
+    const unsigned n_list = kv_tile_kmer_list(sm, ls, p.offsets, p.tile_first, tile, p.total, p.k, true);
+
+#pragma unroll 1
+    for (unsigned i = threadIdx.x; i < n_list; i += KV_THREADS) {
+        const int l = ls.pos[i];
+        const uint64_t g = tile_start + l;
         const uint64_t h = kv_tile_hash<HASHER, KW>(sm, l, p.k);
         if (p.banded && (long long)(h & p.band_mask) != p.band_minus_1) continue;
 
@@ -638,7 +646,11 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
             int a = p.pre[s] ? (int)p.pre[s][g] : (int)kv_get(p.sk[s], h);
             if (a < p.case_min) {
                 interesting = false;
-                if (p.screen > 0 && a < p.screen) atomicMin(p.discard_pos + read, (uint32_t)(g - rs));
+                if (p.screen > 0 && a < p.screen) {
+                    uint64_t read, rs, re;
+                    kv_find_read(sm, p.offsets, p.tile_first, tile, g, read, rs, re);
+                    atomicMin(p.discard_pos + read, (uint32_t)(g - rs));
+                }
                 break;
             }
             ab[s] = (uint8_t)a;
@@ -652,6 +664,8 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
         if (!interesting) continue;
         unsigned long long slot = atomicAdd(p.n_hits, 1ULL);
         if (slot < p.max_hits) {
+            uint64_t read, rs, re;
+            kv_find_read(sm, p.offsets, p.tile_first, tile, g, read, rs, re);
             kv_hit hit;
             hit.read = (uint32_t)read;
             hit.offset = (uint32_t)(g - rs);
