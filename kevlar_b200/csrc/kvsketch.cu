@@ -787,7 +787,16 @@ template <int BITS>
 static int kv_launch_increment(KvCtx *ctx, const KvView &v, uint64_t flat_bytes, const uint64_t *d_hashes,
                                const uint32_t *d_valid, uint64_t n)
 {
-    unsigned grid = kv_grid_for(ctx, n);
+    // grid-stride kernel: exactly one wave of resident CTAs (48 registers -> 5 CTAs of 256 threads
+    // per SM; the generic 8 per SM would run as 1.6 waves with a long tail)
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (const char *e = getenv("KV_INC_CTAS")) per_sm = atoi(e);
+        if (per_sm <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kv_increment_kernel<BITS, true, false>, 256, 0) != cudaSuccess)
+            per_sm = 0;
+        if (per_sm <= 0) per_sm = 4;
+    }
+    unsigned grid = kv_grid_for(ctx, n, per_sm);
     const uint64_t stride = (n + 31) / 32 + 1;
     uint32_t *added = nullptr;
     unsigned *dirty = nullptr;
@@ -856,7 +865,11 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
     LAUNCH_C(KV_PROF_PARTITION, ctx, kv_part_scan_kernel, 1, 32, pi, v.n_tables, runsum, runbase, meta);
     KV_TRY(kv_launch_smem(ctx, KV_PROF_PARTITION, kv_part_scatter_kernel, grid, 256, (size_t)P * 4, v, pi, d_hashes, d_valid,
                           n, slice, rows, runbase, items));
-    const unsigned agrid = kv_grid_for(ctx, max_items);
+    static int apply_per_sm = 0;   // one wave of resident CTAs, like kv_launch_increment
+    if (!apply_per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&apply_per_sm, kv_part_apply_kernel<BITS, 0>, 256, 0) != cudaSuccess ||
+                          apply_per_sm <= 0))
+        apply_per_sm = 4;
+    const unsigned agrid = kv_grid_for(ctx, max_items, apply_per_sm);
     LAUNCH_C(KV_PROF_INCREMENT, ctx, (kv_part_apply_kernel<BITS, 0>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
     LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 1>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
     LAUNCH_C(KV_PROF_FIXUP, ctx, (kv_part_apply_kernel<BITS, 2>), agrid, 256, v, items, meta, added, dirty, ctx->counters + 5);
