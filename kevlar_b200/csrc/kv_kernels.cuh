@@ -20,6 +20,10 @@
 
 #include "kv_device.cuh"
 
+#ifndef KV_INC_MIN_CTAS
+#define KV_INC_MIN_CTAS 6   // resident CTAs per SM the increment kernel is compiled for (register budget)
+#endif
+
 // ----------------------------------------------------------------------- K0
 
 // tile_first[i] = min(first read r with offsets[r+1] > i*KV_TILE, n_reads-1), i in [0, n_tiles]
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
 // happened -- and redone with the exact path by the two follow-up kernels below, which exit
 // immediately when the flag is clear.
 template <int BITS, bool HAS_VALID, bool EXACT>
-__global__ void __launch_bounds__(256) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
+__global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_increment_kernel(KvView v, const uint64_t *__restrict__ hashes,
                                                            const uint32_t *__restrict__ valid, uint64_t total,
                                                            uint32_t *__restrict__ added, uint64_t added_stride,
                                                            unsigned *dirty, unsigned long long *n_redone)
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(256) kv_part_scatter_kernel(KvView v, KvPartIn
 // Apply / undo / redo over the item array.  MODE 0: speculative update, records `added`;
 // MODE 1: rollback of a dirty chunk; MODE 2: exact redo of a dirty chunk.
 template <int BITS, int MODE>
-__global__ void __launch_bounds__(256) kv_part_apply_kernel(KvView v, const uint32_t *__restrict__ items,
+__global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_part_apply_kernel(KvView v, const uint32_t *__restrict__ items,
                                                             const uint32_t *__restrict__ meta, uint32_t *__restrict__ added,
                                                             unsigned *dirty, unsigned long long *n_redone)
 {
