@@ -6,7 +6,7 @@ call that needs it.
 """
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_int, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, byref, c_char_p, c_int, c_int64, c_uint64, c_void_p
 
 import numpy as np
 

@@ -8,7 +8,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 import numpy as np
 
