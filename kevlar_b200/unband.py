@@ -13,15 +13,20 @@ import kevlar_b200
 
 
 def batch_of(name, numbatches):
+    """Deterministic stand-in for the reference's `hash(record.name) % numbatches`
+    (kevlar/unband.py:36), which Python salts per process."""
     return zlib.crc32(name.encode('utf-8')) % numbatches
 
 
 def create_batch_files(numbatches, tempdir):
+    """One gzipped spill file per batch (kevlar/unband.py:15-23)."""
     return [kevlar_b200.open('{:s}/kevlar-unband-batch{:d}.augfastq.gz'.format(tempdir, i), 'w')
             for i in range(numbatches)]
 
 
 def write_records_to_batches(recordstream, batchfiles):
+    """Spread the records over the spill files by read name, so that all copies of a read --
+    one per band it was reported in -- meet in the same file (kevlar/unband.py:26-38)."""
     kevlar_b200.plog('[kevlar::unband]', 'writing records to {:d} temp batch files'.format(len(batchfiles)))
     progress = kevlar_b200.ProgressIndicator('[kevlar::unband]     processed {counter} reads', interval=1e5,
                                              breaks=[1e6, 1e7])
@@ -31,6 +36,8 @@ def write_records_to_batches(recordstream, batchfiles):
 
 
 def resolve_batch(batchfile):
+    """Re-read one spill file, fold the copies of each read into the first one seen, emit the reads
+    in name order with their annotations in offset order (kevlar/unband.py:41-58)."""
     filename = batchfile.name
     batchfile.close()
     merged = {}
@@ -57,6 +64,7 @@ def resolve_batches(batchfiles):
 
 
 def unband(recordstream, numbatches=16):
+    """kevlar/unband.py:72-77 (the temporary directory goes away with the generator)."""
     with TemporaryDirectory() as tempdir:
         batchfiles = create_batch_files(numbatches, tempdir)
         write_records_to_batches(recordstream, batchfiles)
@@ -65,6 +73,7 @@ def unband(recordstream, numbatches=16):
 
 
 def afxstream(filenames):
+    """All records of several augmented FASTA/FASTQ files, one stream (the record source of kevlar/unband.py:80-90)."""
     for filename in filenames:
         with kevlar_b200.open(filename, 'r') as fh:
             for record in kevlar_b200.parse_augmented_fastx(fh):
