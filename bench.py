@@ -296,6 +296,7 @@ def load_atomic_peak(table_mb=64):
 
 
 def run_ours(args):
+    t_start = time.perf_counter()
     import torch
     from kevlar_b200 import _lib, multigpu, simtrio
     rank, world = multigpu.init_from_env()
@@ -309,14 +310,22 @@ def run_ours(args):
         if world > 1:
             torch.distributed.barrier()
 
+    def phase(what):   # progress on stderr (rank 0): where the wall-clock of a run goes
+        if rank == 0:
+            print('[bench] +{:6.1f}s {}'.format(time.perf_counter() - t_start, what), file=sys.stderr, flush=True)
+
+    phase('rendezvous done ({} rank{})'.format(world, 's' if world > 1 else ''))
     trio = simtrio.simulate_trio(1000000, reads_per_sample=args.reads_per_sample, seed_offset=1000 * rank)
     nk_rank = kmers_per_step(trio)
+    phase('synthetic trio generated')
     runner = GpuTrio(args, trio, world)
+    phase('sketches allocated, inputs staged')
 
     for _ in range(max(3, args.warmup)):
         runner.step(True)
     for _ in range(2):
         runner.step(False)
+    phase('warm-up done')
 
     sampler = ClockSampler(_lib.current_device())
     if rank == 0:
@@ -330,6 +339,7 @@ def run_ours(args):
     hits_value = runner.last_hits.copy()
     ms_e2e = runner.timed(args.steps, False, barrier)
     hits_e2e = runner.last_hits.copy()
+    phase('timed regions done')
     assert len(hits_value) == len(hits_e2e) and (hits_value['offset'] == hits_e2e['offset']).all()
 
     # whole-job numbers: max time over ranks, k-mers summed over ranks
