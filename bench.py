@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--hasher', default='murmur', choices=['murmur', 'twobit'],
                     help='murmur = Counttable (what `kevlar count` builds); twobit = Countgraph')
+    ap.add_argument('--counter-size', type=int, default=8, choices=[8, 4, 1],
+                    help='bits per counter at the same 64 MB per sketch (4 = SmallCount*, 1 = Node*); the headline is 8')
     ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p', 'p2p_host', 'sharded'],
                     help="N>1: how per-GPU work is combined; 'sharded' = plan B, bin-range-sharded sketches")
     ap.add_argument('--reads-per-sample', type=int, default=READS_PER_SAMPLE)
@@ -57,12 +59,21 @@ def parse_args():
     return ap.parse_args()
 
 
+SKETCH_CLASS = {('murmur', 8): 'Counttable', ('murmur', 4): 'SmallCounttable', ('murmur', 1): 'Nodetable',
+                ('twobit', 8): 'Countgraph', ('twobit', 4): 'SmallCountgraph', ('twobit', 1): 'Nodegraph'}
+
+
+def sketch_shape(args):
+    """(khmer class name, buckets per table): kevlar/count.py:33 sizes tables as memory / 4 * buckets per byte."""
+    return SKETCH_CLASS[(args.hasher, args.counter_size)], MEMORY / N_TABLES * (8 // args.counter_size)
+
+
 def workload_name(args):
-    kind = 'Counttable (MurmurHash3 canonical)' if args.hasher == 'murmur' else 'Countgraph (2-bit canonical)'
+    kind = '(MurmurHash3 canonical)' if args.hasher == 'murmur' else '(2-bit canonical)'
     return ('C2: gentrio-style synthetic trio, 1 Mbp genome at 30x = {} reads x {} bp per sample, k={}, '
-            '3 x {:.0f} MB 8-bit {} with {} tables; step = count x3 + novel scan of the proband reads '
-            '(case_min {}, ctrl_max {})').format(args.reads_per_sample, READ_LEN, K, MEMORY / 1e6, kind, N_TABLES,
-                                                  CASE_MIN, CTRL_MAX)
+            '3 x {:.0f} MB {}-bit {} {} with {} tables; step = count x3 + novel scan of the proband reads '
+            '(case_min {}, ctrl_max {})').format(args.reads_per_sample, READ_LEN, K, MEMORY / 1e6, args.counter_size,
+                                                  sketch_shape(args)[0], kind, N_TABLES, CASE_MIN, CTRL_MAX)
 
 
 def kmers_per_step(trio):
@@ -128,12 +139,12 @@ class ClockSampler(object):
 
 # ----------------------------------------------------------------------------- CPU arms
 
-def cpu_step(ko, trio, threads, sketches=None):
+def cpu_step(ko, trio, threads, shape=('Counttable', MEMORY / N_TABLES)):
     """count x3 + novel with the oracle; returns (seconds, n_hits, per-sample k-mer counts)."""
     t0 = time.perf_counter()
     sks, counted = [], []
     for bases, offs in trio:
-        sk = ko.Counttable(K, MEMORY / N_TABLES, N_TABLES)
+        sk = getattr(ko, shape[0])(K, shape[1], N_TABLES)
         counted.append(sk.consume_batch(bases, offs, threads=threads))
         sks.append(sk)
     hits, _ = ko.novel_batch(sks[:1], sks[1:], trio[0][0], trio[0][1], CASE_MIN, CTRL_MAX, threads=threads)
@@ -152,10 +163,10 @@ def run_reference(args):
     trio = simtrio.simulate_trio(1000000, reads_per_sample=n_reads)
     nk = kmers_per_step(trio)
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_step(ko, trio, cores)
+        cpu_step(ko, trio, cores, sketch_shape(args))
     times = []
     for _ in range(args.steps):
-        times.append(cpu_step(ko, trio, cores)[0])
+        times.append(cpu_step(ko, trio, cores, sketch_shape(args))[0])
     total = sum(times)
     value = nk * args.steps / total
     sample = ('{} of {} reads/sample per step; count in {} pthreads pulling read chunks (khmer model), novel scan in C '
@@ -185,12 +196,13 @@ class GpuTrio(object):
         self.torch, self.kv, self.lib, self.khmer, self.multigpu = torch, kevlar_b200, _lib, khmer, multigpu
         self.args, self.world = args, world
         self.device = _lib.current_device()
-        cls = khmer.Counttable if args.hasher == 'murmur' else khmer.Countgraph
+        name, buckets = sketch_shape(args)
+        cls = getattr(khmer, name)
         self.sharded = world > 1 and args.merge == 'sharded'
         if self.sharded:   # plan B: every rank holds 1/world of every table; reads stay sharded
-            self.sketches = [multigpu.ShardedSketch(cls, K, MEMORY / N_TABLES, N_TABLES) for _ in range(3)]
+            self.sketches = [multigpu.ShardedSketch(cls, K, buckets, N_TABLES) for _ in range(3)]
         else:
-            self.sketches = [cls(K, MEMORY / N_TABLES, N_TABLES) for _ in range(3)]
+            self.sketches = [cls(K, buckets, N_TABLES) for _ in range(3)]
         if args.no_unique and not self.sharded:
             for sk in self.sketches:
                 sk.set_unique_tracking(False)
@@ -380,7 +392,8 @@ def run_ours(args):
             entry['algorithmic_GBps'] = alg_bytes[name] / (ms / args.steps / 1e3) / 1e9
         kernels[name] = entry
     dominant = max((k for k in kernels if k in alg_bytes), key=lambda k_: kernels[k_]['share_of_kernel_time'])
-    kname = {'increment': 'kv_increment_kernel<8>', 'hash': 'kv_hash_kernel', 'novel': 'kv_novel_kernel'}[dominant]
+    kname = {'increment': 'kv_increment_kernel<{}>'.format(args.counter_size), 'hash': 'kv_hash_kernel',
+             'novel': 'kv_novel_kernel'}[dominant]
     achieved = kernels[dominant]['algorithmic_GBps']
     roofline = {'kernel': kname, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': load_traffic(kname), 'peak_source': peak_src,
@@ -436,7 +449,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import khmer_oracle as ko
         cores = os.cpu_count() or 1
-        secs, ohits, counted, osk = cpu_step(ko, trio, cores)
+        secs, ohits, counted, osk = cpu_step(ko, trio, cores, sketch_shape(args))
         line['cpu_baseline'] = {
             'value': nk_rank / secs, 'unit': 'k-mers/s', 'cores': cores, 'kind': 'port',
             'sample': 'one full step (3 x {} reads): oracle count in {} pthreads + C novel scan in {} threads, {:.1f} s'
@@ -455,11 +468,14 @@ def run_ours(args):
     if world == 1 and not args.no_variants:
         # the same step with the other hasher / without n_unique tracking, for context
         variants = {}
-        for label, hasher, no_unique in (('countgraph_twobit', 'twobit', False), ('counttable_no_unique', 'murmur', True)):
-            if hasher == args.hasher and no_unique == args.no_unique:
+        for label, hasher, no_unique, bits in (('countgraph_twobit', 'twobit', False, 8),
+                                               ('counttable_no_unique', 'murmur', True, 8),
+                                               ('smallcounttable_4bit', 'murmur', False, 4),
+                                               ('nodetable_1bit', 'murmur', False, 1)):
+            if hasher == args.hasher and no_unique == args.no_unique and bits == args.counter_size:
                 continue
             a2 = argparse.Namespace(**vars(args))
-            a2.hasher, a2.no_unique = hasher, no_unique
+            a2.hasher, a2.no_unique, a2.counter_size = hasher, no_unique, bits
             r2 = GpuTrio(a2, trio, world)
             for _ in range(3):
                 r2.step(True)

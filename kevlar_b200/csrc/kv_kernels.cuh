@@ -511,18 +511,25 @@ __global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_part_apply_kernel(KvV
 //                             clear) and g is the smallest position of the batch touching it.
 // pass A (per table): first[bin] = min(first[bin], g) for every valid g whose bucket is empty;
 // pass B (per table): every position recorded in first[] is flagged;   finally popcount of the flags.
-// first[] is ONE u32 array as long as the largest table, reused for each table in turn, so the
+// first[] is ONE u32 array as long as the largest table (or bucket range, below), reused for each table in turn, so the
 // random atomics of a pass stay inside a (for the benchmark config L2-resident) 4-bytes-per-
 // bucket region instead of spreading over all tables at once.
+// Tables with more buckets than first[] holds (KV_FIRST_RANGE_LOG2, default 2^27 = 512 MB of first[])
+// are handled in bucket ranges [bin_lo, bin_lo + bin_n): one pass A + pass B per range, so the
+// scratch does not grow with the sketch.  (Ranges small enough to keep first[] in L2 were measured
+// and lose: every extra pass re-streams the hashes and redoes the modulo, ~60 us per 21 M k-mers,
+// more than the DRAM-resident atomics cost -- profiles/r01_notes.md.)
 __global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint32_t *__restrict__ first,
                                                            const uint64_t *__restrict__ hashes,
-                                                           const uint32_t *__restrict__ valid, uint64_t total)
+                                                           const uint32_t *__restrict__ valid, uint64_t total,
+                                                           uint64_t bin_lo, uint64_t bin_n)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
         if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
         uint64_t bin;
-        if (kv_bin(v, t, __ldcs(hashes + g), bin) && kv_bucket_empty(v, t, bin)) atomicMin(first + bin, (uint32_t)g);
+        if (kv_bin(v, t, __ldcs(hashes + g), bin) && bin - bin_lo < bin_n && kv_bucket_empty(v, t, bin))
+            atomicMin(first + (bin - bin_lo), (uint32_t)g);
     }
 }
 

@@ -99,6 +99,7 @@ struct KvCtx {
     double prof_ms[KV_PROF_CLASSES] = {0};
     uint64_t prof_n[KV_PROF_CLASSES] = {0};
     int sm_count = 148;
+    uint64_t first_range = 1ull << 27;   // buckets covered by the n_unique first[] scratch: 512 MB (KV_FIRST_RANGE_LOG2)
     size_t l2_persist = 0;     // bytes of L2 set aside for persisting accesses
     size_t l2_window_max = 0;
     uint64_t chunk_bases = 64ull << 20;
@@ -156,6 +157,7 @@ static int kv_ctx_get(int device, KvCtx **out)
         if (const char *env = getenv("KV_PART_MIN_BYTES")) c.part_min_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_MAX_BYTES")) c.part_max_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_REGION_LOG2")) c.part_region_log2 = std::max(4, std::min(30, atoi(env)));
+        if (const char *env = getenv("KV_FIRST_RANGE_LOG2")) c.first_range = 1ull << std::max(8, std::min(32, atoi(env)));
         c.ready = true;
     }
     *out = &c;
@@ -883,11 +885,12 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
 {
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
-    if (maxsize * 4 > ctx->first.cap) {   // (re)allocated: establish the all-ones invariant the passes maintain
-        if (kv_buf_ensure(ctx->first, maxsize * 4) != KV_OK)
-            return kv_fail(KV_ENOMEM, "exact n_unique_kmers tracking needs %llu bytes of scratch HBM (4 per bucket of the "
-                           "largest table); switch it off with kv_sketch_set_unique_tracking(sketch, 0)",
-                           (unsigned long long)(maxsize * 4));
+    // first[] covers at most first_range buckets; larger tables are walked range by range
+    const uint64_t range = std::min(maxsize, ctx->first_range);
+    if (range * 4 > ctx->first.cap) {   // (re)allocated: establish the all-ones invariant the passes maintain
+        if (kv_buf_ensure(ctx->first, range * 4) != KV_OK)
+            return kv_fail(KV_ENOMEM, "exact n_unique_kmers tracking needs %llu bytes of scratch HBM; switch it off with "
+                           "kv_sketch_set_unique_tracking(sketch, 0)", (unsigned long long)(range * 4));
         CU(cudaMemsetAsync(ctx->first.p, 0xff, ctx->first.cap, ctx->compute));
     }
     const uint64_t n_words = (n + 31) / 32;
@@ -900,12 +903,15 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
             if (s->bits == 8) LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<8>, kv_grid_for(ctx, n_words, 16), 256, v, t);
             else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<4>, kv_grid_for(ctx, n_words, 16), 256, v, t);
         }
-    kv_l2_window(ctx, ctx->first.p, maxsize * 4);
-    for (int t = 0; t < s->n_tables; t++) {
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n);
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, kv_grid_for(ctx, s->sizes[t] / 4 + 1), 256,
-                 (uint32_t *)ctx->first.p, s->sizes[t], (uint32_t *)ctx->fresh.p);
-    }
+    kv_l2_window(ctx, ctx->first.p, range * 4);
+    for (int t = 0; t < s->n_tables; t++)
+        for (uint64_t lo = 0; lo < s->sizes[t]; lo += range) {
+            const uint64_t nb = std::min(range, s->sizes[t] - lo);
+            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n,
+                     lo, nb);
+            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, kv_grid_for(ctx, nb / 4 + 1), 256,
+                     (uint32_t *)ctx->first.p, nb, (uint32_t *)ctx->fresh.p);
+        }
     kv_l2_window(ctx, nullptr, 0);
     LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_popcount_kernel, kv_grid_for(ctx, n_words), 256, (const uint32_t *)ctx->fresh.p, n_words,
              s->d_unique);

@@ -737,6 +737,14 @@ def test_multi_chunk_batches_are_exact():
                     KV_CHUNK_BASES='2048')
 
 
+def test_ranged_first_touch_passes_are_exact():
+    """Tables with more buckets than the n_unique scratch covers are processed in bucket ranges.
+    Child process with a 1024-bucket range: every table of the parity tests spans several ranges,
+    and n_unique_kmers / the abundance distribution must not change."""
+    _rerun_in_child('(consume and not saturation) or count_simple or abundance_distribution or dist_passes',
+                    KV_FIRST_RANGE_LOG2='10')
+
+
 def test_khmer_namespace_drop_in(kv, tmp_path):
     """INTEGRATION.md route 1: code written against the `khmer` namespace the way the reference
     uses it -- threads sharing one ReadParser into consume_seqfile, then one get() per k-mer per
