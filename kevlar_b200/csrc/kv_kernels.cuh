@@ -170,8 +170,7 @@ __global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_increment_kernel(KvVi
             for (int t = 0; t < 4; t++) {
                 if (own[t]) {
                     if (hot[t]) {
-                        did[t] = kv_sat_inc_exact<BITS>(w[t], sh[t], ob[t]);
-                        if (did[t]) kv_state_publish<BITS>(v, t, bin[t], ob[t]);
+                        did[t] = kv_sat_inc_exact<BITS>(w[t], sh[t], ob[t]);   // the group is hot already: nothing to publish
                     } else if (ob[t] == maxv)
                         atomicOr(dirty, 1u);
                     else
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_increment_kernel(KvVi
                     unsigned ob;
                     if (EXACT || kv_maybe_hot(v, t, bin)) {
                         did = kv_sat_inc_exact<BITS>(w, sh, ob);
-                        if (did) kv_state_publish<BITS>(v, t, bin, ob);
+                        if (did && EXACT) kv_state_publish<BITS>(v, t, bin, ob);   // (a hot group needs no second mark)
                     } else {
                         ob = (atomicAdd(w, 1u << sh) >> sh) & maxv;
                         did = true;
@@ -487,7 +486,7 @@ __global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_part_apply_kernel(KvV
                     if ((added[i >> 5] >> (i & 31)) & 1u) atomicAdd(w[j], 0u - (1u << sh[j]));
                 } else if (hot[j]) {
                     did[j] = kv_sat_inc_exact<BITS>(w[j], sh[j], ob[j]);
-                    if (did[j]) kv_state_publish<BITS>(v, tt[j], bin[j], ob[j]);
+                    if (did[j] && MODE == 2) kv_state_publish<BITS>(v, tt[j], bin[j], ob[j]);   // MODE 0: the group is hot already
                 } else if (ob[j] == maxv)
                     atomicOr(dirty, 1u);
                 else
