@@ -414,3 +414,48 @@ def test_dist_cli_arguments():
     args = kevlar_b200.cli.parser().parse_args(['dist', '-k', '25', '-M', '4M', '--tsv', 'o.tsv', '--plot-xlim', '0', '50',
                                                 'mask.nt', 'a.fq'])
     assert (args.ksize, args.memory, args.tsv, list(args.plot_xlim)) == (25, 4e6, 'o.tsv', [0, 50])
+
+
+# ------------------------------------------------------------------ simlike host logic (no GPU)
+
+class _OracleQueries(object):
+    """Gives an oracle sketch the batched query method the product's sketches have, so the host
+    side of kevlar_b200.simlike can run on the CPU."""
+
+    def __init__(self, sketch):
+        self.sketch = sketch
+
+    def ksize(self):
+        return self.sketch.ksize()
+
+    def get_kmer_counts_many(self, sequences):
+        k = self.sketch.ksize()
+        return [np.array(self.sketch.get_kmer_counts(s) if len(s) >= k else [], dtype=np.uint8) for s in sequences]
+
+
+def test_simlike_host_logic_against_reference_outputs(oracle):
+    """kevlar/simlike.py:22-96: filtering by reference-genome abundance, outlier dropping, SNV vs
+    indel pairing -- the 52 windows the reference's own function produced over the oracle
+    (tests/golden/gen/simlike_spanning.json), batched and one by one."""
+    import json
+    from conftest import golden_gen
+    from kevlar_b200.simlike import (spanning_kmer_abundances, spanning_kmer_abundances_many, discard_nonunique_kmers,
+                                     discard_outlier_abunds)
+    kid, mom, dad = (oracle.Counttable(31, 1e6, 4) for _ in range(3))
+    ref = oracle.SmallCounttable(31, 125000, 4)
+    for sk, fn in ((kid, 'trio-proband.fq.gz'), (mom, 'trio-mother.fq.gz'), (dad, 'trio-father.fq.gz'), (ref, 'refr.fa.gz')):
+        sk.consume_seqfile(oracle.ReadParser(golden_data('minitrio/' + fn)))
+    kid, mom, dad, ref = (_OracleQueries(s) for s in (kid, mom, dad, ref))
+    cases = json.load(open(golden_gen('simlike_spanning.json')))
+    for drop in (False, True):
+        subset = [c for c in cases if c['dropoutliers'] == drop]
+        got = spanning_kmer_abundances_many([(c['alt'], c['refr']) for c in subset], kid, (mom, dad), ref, dropoutliers=drop)
+        assert [list(g) for g in got] == [[c['abundances'], c['refr_abunds'], c['ndropped']] for c in subset]
+    first = cases[0]
+    assert spanning_kmer_abundances(first['alt'], first['refr'], kid, (mom, dad), ref) == \
+        (first['abundances'], first['refr_abunds'], 3)
+    case_counts, ctrl_counts, alt_in_refr = discard_nonunique_kmers(first['alt'], kid, (mom, dad), ref)
+    assert case_counts == first['abundances'][0] and ctrl_counts == first['abundances'][1:]
+    assert len(alt_in_refr) == 31 and sum(1 for r in alt_in_refr if r) == 3
+    # mean 30.75: 10 is 20.75 away (dropped, the bound is strict), 90 too; mean 10: 40 is dropped
+    assert discard_outlier_abunds([10, 11, 12, 90], [[1, 1, 1, 1], [0, 40, 0, 0]]) == ([11, 12], [[1, 1, 1, 1], [0, 0, 0]])
