@@ -251,7 +251,9 @@ int kv_peer_sync_destroy(kv_peer_sync *ps);
  * pointers refer to reader-owned host memory that stays valid until the next call on the same
  * reader: names / quals are the header lines (without '@' / '>') and quality strings of the
  * batch back to back, with n_reads+1 offsets each; is_fastq[i] tells whether record i has a
- * quality string.  Any of the text outputs may be NULL.  Not thread-safe per reader. */
+ * quality string.  Any of the text outputs may be NULL; with names == NULL and quals == NULL the
+ * header / quality text is not collected at all (the counting path needs sequences only).  File
+ * I/O and inflate run in a read-ahead thread owned by the reader.  Not thread-safe per reader. */
 typedef struct kv_reader kv_reader;
 int kv_reader_open(const char *path, kv_reader **out);
 int kv_reader_next(kv_reader *r, uint64_t max_bases, const uint8_t **bases, const uint64_t **offsets,

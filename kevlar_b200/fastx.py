@@ -7,6 +7,8 @@ take (include/kvsketch.h) -- so the hot loops never touch Python strings.
 """
 import ctypes
 import gzip
+import os
+import queue
 import threading
 
 import numpy as np
@@ -227,9 +229,9 @@ class FastxReader(object):
 
 
 class NativeFastxReader(object):
-    """The same interface on top of the native parser in libkvsketch.so (kv_reader_*, zlib + a
-    memchr line splitter): ~10x the throughput of the pure-Python reader above, which remains as
-    the reference implementation the tests compare it with."""
+    """The same interface on top of the native parser in libkvsketch.so (kv_reader_*: a read-ahead
+    thread doing the file I/O / inflate, memchr record splitting straight into the batch arrays);
+    the pure-Python reader above remains as the implementation the tests compare it with."""
 
     def __init__(self, filename):
         from kevlar_b200 import _lib
@@ -251,9 +253,8 @@ class NativeFastxReader(object):
         c = ctypes
         bases, offs, names, noffs, quals, qoffs, isfq = (c.c_void_p() for _ in range(7))
         n = c.c_uint64()
-        self._lib.check(self._lib.lib().kv_reader_next(self._h, int(max_bases), c.byref(bases), c.byref(offs), c.byref(n),
-                                                       c.byref(names), c.byref(noffs), c.byref(quals), c.byref(qoffs),
-                                                       c.byref(isfq)))
+        text = (c.byref(names), c.byref(noffs), c.byref(quals), c.byref(qoffs), c.byref(isfq)) if keep_text else (None,) * 5
+        self._lib.check(self._lib.lib().kv_reader_next(self._h, int(max_bases), c.byref(bases), c.byref(offs), c.byref(n), *text))
         n = n.value
         if n == 0:
             return None
@@ -269,13 +270,49 @@ class NativeFastxReader(object):
         self.num_reads += n
         return SeqBatch(b, offsets, packed=packed)
 
-    def batches(self, max_bases=64 << 20, keep_text=False):
-        while True:
-            with self._lock:
-                batch = self._next(max_bases, keep_text)
-            if batch is None:
-                return
-            yield batch
+    def batches(self, max_bases=64 << 20, keep_text=False, prefetch=True):
+        """Batches in file order.  With ``prefetch`` a helper thread parses one batch ahead, so the
+        parsing of batch i+1 overlaps whatever the consumer does with batch i (typically waiting
+        for the GPU inside a ctypes call, which releases the GIL).  A generator that is abandoned
+        early gives back nothing it has not yielded except the one batch parsed ahead."""
+        if not prefetch or os.environ.get('KV_NO_PREFETCH'):
+            while True:
+                with self._lock:
+                    batch = self._next(max_bases, keep_text)
+                if batch is None:
+                    return
+                yield batch
+        ahead = queue.Queue(maxsize=1)
+        stop = threading.Event()
+
+        def parse_ahead():
+            try:
+                while not stop.is_set():
+                    with self._lock:
+                        batch = self._next(max_bases, keep_text)
+                    ahead.put(batch)
+                    if batch is None:
+                        return
+            except BaseException as exc:   # handed to the consumer
+                ahead.put(exc)
+
+        worker = threading.Thread(target=parse_ahead, name='kv-fastx-prefetch', daemon=True)
+        worker.start()
+        try:
+            while True:
+                item = ahead.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            while worker.is_alive():   # unblock a pending put, then let the thread see the flag
+                try:
+                    ahead.get(timeout=0.05)
+                except queue.Empty:
+                    pass
 
     def __iter__(self):
         while True:

@@ -226,6 +226,49 @@ def test_native_reader_edge_cases(tmp_path):
         fastx.NativeFastxReader(str(tmp_path / 'missing.fq'))
 
 
+def test_native_reader_large_inputs(tmp_path):
+    """The native reader hands 4 MB blocks from its read-ahead thread to the record splitter:
+    a ~10 MB FASTQ with ragged read lengths puts records across many block boundaries.  Plain,
+    gzip (two concatenated members), sequences-only batches, a truncated last record, and closing
+    a reader that was never drained (the producer thread must stop)."""
+    import gzip
+    rng = np.random.default_rng(99)
+    letters = np.frombuffer(b'ACGTN', dtype=np.uint8)
+    recs, chunks = [], []
+    for i in range(45000):
+        n = int(rng.integers(1, 400))
+        seq = letters[rng.integers(0, 5, size=n)].tobytes()
+        name = b'read%d len=%d' % (i, n)
+        recs.append((name.decode(), seq.decode(), 'I' * n))
+        chunks.append(b'@' + name + b'\n' + seq + b'\n+\n' + b'I' * n + b'\n')
+    text = b''.join(chunks)
+    assert len(text) > 2 * (4 << 20)
+    plain = tmp_path / 'big.fq'
+    plain.write_bytes(text)
+    gz = tmp_path / 'big.fq.gz'
+    half = len(chunks) // 2
+    gz.write_bytes(gzip.compress(b''.join(chunks[:half]), 1) + gzip.compress(b''.join(chunks[half:]), 1))
+    for path in (plain, gz):
+        got = [(r.name, r.sequence, r.quality) for r in fastx.NativeFastxReader(str(path))]
+        assert got == recs, path
+        reader = fastx.NativeFastxReader(str(path))
+        seqs = []
+        for batch in reader.batches(1 << 20):            # sequences only: no header / quality text collected
+            assert batch.name(0) == b'' and batch.qual(0) is None
+            seqs.extend(batch.bases[int(batch.offsets[i]):int(batch.offsets[i + 1])].tobytes().decode()
+                        for i in range(len(batch)))
+        assert seqs == [r[1] for r in recs] and reader.num_reads == len(recs)
+    cut = tmp_path / 'cut.fq'
+    cut.write_bytes(b''.join(chunks[:3]) + b'@last one\nACGTAC\n+')
+    for cls in (fastx.NativeFastxReader, fastx.FastxReader):
+        got = [(r.name, r.sequence, r.quality) for r in cls(str(cut))]
+        assert got == recs[:3] + [('last one', 'ACGTAC', '')], cls
+    for _ in range(3):
+        reader = fastx.NativeFastxReader(str(plain))
+        next(iter(reader.batches(1000)))
+        del reader
+
+
 def test_fastx_reader_shared_by_threads():
     """kevlar/count.py:40-77: several consumers drain one parser; every read exactly once."""
     reader = kv.khmer.ReadParser(golden_data('trio1/case1.fq.gz'))

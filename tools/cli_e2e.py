@@ -34,10 +34,14 @@ def main():
         write_fastq(os.path.join(d, nm + '.fq'), b, o, nm)
     kv.khmer.Counttable(31, 1e4, 4)   # context + library warm-up
     t0 = time.time()
+    per_count = []
     for nm in names:
+        t = time.time()
         args = kv.cli.parser().parse_args(['count', '--memory', '64M', os.path.join(d, nm + '.ct'), os.path.join(d, nm + '.fq')])
         kv.count.main(args)
+        per_count.append(round(time.time() - t, 3))
     t1 = time.time()
+    print('per count call:', per_count)
     args = kv.cli.parser().parse_args(['novel', '--case', os.path.join(d, 'proband.fq'), '--case-counts', os.path.join(d, 'proband.ct'),
                                        '--control-counts', os.path.join(d, 'mother.ct'), os.path.join(d, 'father.ct'),
                                        '-o', os.path.join(d, 'novel.augfastq')])
