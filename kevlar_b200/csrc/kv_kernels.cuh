@@ -532,6 +532,37 @@ __global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint
     }
 }
 
+// Between pass A and pass B of table 0: which positions still matter for the other tables?
+// The minima in first[] only depend on the FIRST occurrence of each distinct hash -- a later
+// occurrence touches the same buckets at a larger position -- and it can never be new itself.  A
+// position whose table-0 bucket was empty at batch start knows that bucket's owner (the smallest
+// position touching it); if the owner is an earlier position with the SAME hash, this one is a
+// repeat and is dropped from the passes over tables 1..T-1.  At sequencing depth that is most of
+// the stream (30x coverage: ~3/4 of the k-mer occurrences).  Everything else stays: owners,
+// positions that merely collide with their owner, positions whose bucket was already occupied or
+// lives on another shard.  todo[] has the layout of valid[].
+__global__ void __launch_bounds__(256) kv_first_classify_kernel(KvView v, const uint32_t *__restrict__ first,
+                                                                const uint64_t *__restrict__ hashes,
+                                                                const uint32_t *__restrict__ valid, uint64_t total,
+                                                                uint32_t *__restrict__ todo)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
+        bool keep = g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
+        if (keep) {
+            const uint64_t h = __ldg(hashes + g);
+            uint64_t bin;
+            if (kv_bin(v, 0, h, bin) && kv_bucket_empty(v, 0, bin)) {
+                const uint32_t owner = __ldcg(first + bin);
+                if (owner < (uint32_t)g && __ldg(hashes + owner) == h) keep = false;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if ((threadIdx.x & 31) == 0) todo[g >> 5] = bal;
+    }
+}
+
 // pass B, bucket-major: stream first[] once; every recorded owner position gets its bit in
 // fresh[] (RED.OR into a bitmap of a few MB) and the entry is reset for the next table / batch.
 __global__ void __launch_bounds__(256) kv_first_resolve_kernel(uint32_t *__restrict__ first, uint64_t n_buckets,

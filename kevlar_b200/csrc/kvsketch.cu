@@ -82,7 +82,7 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small, hist;
+    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small, hist, todo;
     // sketches between these sizes take the region-partitioned update path (measured: 1.2-1.7x over
     // direct random atomics from 256 MB to 4 GB, break-even at 16 GB; profiles/r01_notes.md)
     uint64_t part_min_bytes = 128ull << 20, part_max_bytes = 8ull << 30;
@@ -99,6 +99,7 @@ struct KvCtx {
     double prof_ms[KV_PROF_CLASSES] = {0};
     uint64_t prof_n[KV_PROF_CLASSES] = {0};
     int sm_count = 148;
+    bool unique_classify = true;         // drop repeats after the table-0 pass (KV_NO_CLASSIFY switches it off)
     uint64_t first_range = 1ull << 27;   // buckets covered by the n_unique first[] scratch: 512 MB (KV_FIRST_RANGE_LOG2)
     size_t l2_persist = 0;     // bytes of L2 set aside for persisting accesses
     size_t l2_window_max = 0;
@@ -157,6 +158,7 @@ static int kv_ctx_get(int device, KvCtx **out)
         if (const char *env = getenv("KV_PART_MIN_BYTES")) c.part_min_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_MAX_BYTES")) c.part_max_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_REGION_LOG2")) c.part_region_log2 = std::max(4, std::min(30, atoi(env)));
+        if (getenv("KV_NO_CLASSIFY")) c.unique_classify = false;
         if (const char *env = getenv("KV_FIRST_RANGE_LOG2")) c.first_range = 1ull << std::max(8, std::min(32, atoi(env)));
         c.ready = true;
     }
@@ -904,13 +906,22 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint6
             else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<4>, kv_grid_for(ctx, n_words, 16), 256, v, t);
         }
     kv_l2_window(ctx, ctx->first.p, range * 4);
+    // after table 0, repeats of an earlier hash are dropped from the other tables' passes
+    // (kv_first_classify_kernel); needs table 0 in one range so that every owner is in first[]
+    const bool classify = ctx->unique_classify && s->n_tables > 1 && s->sizes[0] <= range;
+    if (classify) KV_TRY(kv_buf_ensure(ctx->todo, n_words * 4));
+    const uint32_t *pass_valid = d_valid;
     for (int t = 0; t < s->n_tables; t++)
         for (uint64_t lo = 0; lo < s->sizes[t]; lo += range) {
             const uint64_t nb = std::min(range, s->sizes[t] - lo);
-            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, d_valid, n,
+            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, pass_valid, n,
                      lo, nb);
+            if (t == 0 && classify)
+                LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_classify_kernel, grid, 256, v, (const uint32_t *)ctx->first.p, d_hashes,
+                         d_valid, n, (uint32_t *)ctx->todo.p);
             LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, kv_grid_for(ctx, nb / 4 + 1), 256,
                      (uint32_t *)ctx->first.p, nb, (uint32_t *)ctx->fresh.p);
+            if (t == 0 && classify) pass_valid = (const uint32_t *)ctx->todo.p;
         }
     kv_l2_window(ctx, nullptr, 0);
     LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_popcount_kernel, kv_grid_for(ctx, n_words), 256, (const uint32_t *)ctx->fresh.p, n_words,
