@@ -169,6 +169,10 @@ static int is_prime(uint64_t n)
  * down over odd numbers from x-1 (ctor called from kevlar/sketch.py:118). */
 int ko_primes_below(uint64_t x, int n, uint64_t *out)
 {
+    /* khmer special case: one table "near 1" has size 1.  Pinned by the reference fixture
+     * kevlar/tests/data/term-high-abund/reference.sct (28 bytes: one table of size 1) and by
+     * khmer.Nodetable(31, 1, 1) in kevlar/tests/test_simlike.py:69. */
+    if (x == 1 && n == 1) { out[0] = 1; return 0; }
     if (x < 3) return -1;
     uint64_t i = x - 1;
     if (i % 2 == 0) i--;

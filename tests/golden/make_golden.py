@@ -49,7 +49,16 @@ COPY = [
     'example1.augfastq', 'example2.augfastq', 'example2.augfastq.gz',
     'minitrio/mask.nt', 'minitrio/trio-proband-mask-counts.ct', 'minitrio/trio-proband.fq.gz',
     'minitrio/trio-proband-dist.tsv', 'minitrio/trio-mother.fq.gz', 'minitrio/trio-father.fq.gz',
-    'case-low-abund/case.sct', 'ctrl-high-abund/ctrl1.sct',
+    # small sketches of the simlike tests: more OXLI files (k=49 Murmur, 4-bit tables, a size-1 table)
+    'case-low-abund/dad.ct', 'case-low-abund/kid.ct', 'case-low-abund/mom.ct', 'case-low-abund/refr.sct',
+    'ctrl-high-abund/cc57120.dad.sct', 'ctrl-high-abund/cc57120.kid.sct', 'ctrl-high-abund/cc57120.mom.sct',
+    'ctrl-high-abund/cc57120.refr.sct',
+    'term-high-abund/father.ct', 'term-high-abund/mother.ct', 'term-high-abund/proband.ct', 'term-high-abund/reference.sct',
+    'partscore/partscore-father.ct', 'partscore/partscore-mother.ct', 'partscore/partscore-proband.ct',
+    'partscore/partscore-refr.sct',
+    'simlike-fast-mode/cc27.dad.ct', 'simlike-fast-mode/cc27.kid.ct', 'simlike-fast-mode/cc27.mom.ct',
+    'simlike-fast-mode/cc27.refr.sct',
+    'homopolymer/12175-dad.sct', 'homopolymer/12175-kid.sct', 'homopolymer/12175-mom.sct', 'homopolymer/12175-refr.sct',
 ]
 COPY_GZ = ['trio1/case1.fq', 'trio1/ctrl1.fq', 'trio1/ctrl2.fq', 'minitrio/refr.fa']
 
@@ -207,6 +216,36 @@ for alt, refw in windows:
 assert cases[0]['ndropped'] == 3 and cases[0]['abundances'][0][:4] == [7, 6, 6, 6]   # test_simlike.py:88-91
 with open(OUT + 'simlike_spanning.json', 'w') as fh:
     json.dump(cases, fh, indent=0)
+
+# the same function on the sketch + VCF fixtures of kevlar/tests/test_simlike.py:46-80,250-330 (k = 49 and 31,
+# 8-bit case/control sketches, 4-bit reference sketches): windows come from the calls' ALTWINDOW / REFRWINDOW
+fixture_sets = [
+    ('simlike-fast-mode', 'cc27.kid.ct', ('cc27.mom.ct', 'cc27.dad.ct'), 'cc27.refr.sct', 'cc27.calls.vcf'),
+    ('ctrl-high-abund', 'cc57120.kid.sct', ('cc57120.mom.sct', 'cc57120.dad.sct'), 'cc57120.refr.sct', 'cc57120.calls.vcf'),
+    ('case-low-abund', 'kid.ct', ('mom.ct', 'dad.ct'), 'refr.sct', 'calls.vcf.gz'),
+    ('term-high-abund', 'proband.ct', ('mother.ct', 'father.ct'), 'reference.sct', 'calls.vcf'),
+]
+fixture_cases = []
+for folder, kidf, ctrlf, refrf, vcff in fixture_sets:
+    base = D + folder + '/'
+    kidsk = kevlar.sketch.load(base + kidf)
+    ctrlsk = [kevlar.sketch.load(base + f) for f in ctrlf]
+    refsk = kevlar.sketch.load(base + refrf)
+    for call in kevlar.vcf.VCFReader(kevlar.open(base + vcff, 'r')):
+        alt, refw = call.window, call.refrwindow
+        if alt is None or refw is None or len(alt) < kidsk.ksize() or len(refw) < kidsk.ksize():
+            continue
+        for drop in (False, True):
+            try:
+                abunds, refrabunds, ndropped = spanning_kmer_abundances(alt, refw, kidsk, ctrlsk, refsk, dropoutliers=drop)
+            except ZeroDivisionError:   # every k-mer is in the reference: the outlier filter divides by zero
+                continue
+            fixture_cases.append({'set': folder, 'sketches': [kidf] + list(ctrlf) + [refrf], 'alt': alt, 'refr': refw,
+                                  'dropoutliers': drop, 'abundances': abunds, 'refr_abunds': refrabunds,
+                                  'ndropped': ndropped})
+assert len(fixture_cases) > 20 and any(max(c['abundances'][0] + [0]) > 5 for c in fixture_cases)
+with open(OUT + 'simlike_fixture_windows.json', 'w') as fh:
+    json.dump(fixture_cases, fh, indent=0)
 '''
 
 
@@ -218,8 +257,10 @@ def generate(env, root):
     with open(drv, 'w') as fh:
         fh.write(DRIVER)
     subprocess.check_call([sys.executable, drv, REFDATA, gen], env=env, cwd=root)
+    # test_simlike.py pins get_kmer_counts (k = 31 and 49, 8- and 4-bit tables) through the reference's
+    # own likelihood scores and filter calls
     tests = ['test_count.py', 'test_sketch.py', 'test_novel.py', 'test_filter.py', 'test_seqio.py',
-             'test_unband.py']
+             'test_unband.py', 'test_simlike.py']
     # test_dist.py: the tests that go through compute_dist() need DataFrame.append, which the pandas
     # in this image (3.x) no longer has, and test_calc_mu_sigma asserts on a bare pytest.approx(),
     # which pytest 9 rejects -- the reference itself cannot run those here

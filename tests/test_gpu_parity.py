@@ -972,3 +972,42 @@ def test_mask_from_windows(kv, oracle, tmp_path):
     assert 'WARNING: mask FPR is' in log.getvalue() and 'exceeds user-specified limit of 0.0010' in log.getvalue()
     with pytest.raises(ValueError):
         mask_from_windows(['ACGTN' * 10], 31, 2000)
+
+
+def test_simlike_reference_fixture_windows(kv):
+    """The sketch + VCF fixtures of kevlar/tests/test_simlike.py (k = 49 and 31, 8-bit case/control
+    and 4-bit reference sketches, one of them a one-bucket table): sketches loaded on the GPU, all
+    windows of a fixture set in one batched query, equal to the reference's own
+    spanning_kmer_abundances over the oracle (gen/simlike_fixture_windows.json)."""
+    import json
+    from kevlar_b200.simlike import spanning_kmer_abundances_many
+    cases = json.load(open(golden_gen('simlike_fixture_windows.json')))
+    assert len(cases) == 105
+    groups = {}
+    for c in cases:
+        groups.setdefault((c['set'], tuple(c['sketches']), c['dropoutliers']), []).append(c)
+    for (folder, files, drop), members in groups.items():
+        sk = [kv.sketch.load(golden_data(folder + '/' + f)) for f in files]
+        got = spanning_kmer_abundances_many([(c['alt'], c['refr']) for c in members], sk[0], sk[1:-1], sk[-1],
+                                            dropoutliers=drop)
+        for c, g in zip(members, got):
+            assert g == (c['abundances'], c['refr_abunds'], c['ndropped']), (folder, c['alt'])
+
+
+def test_single_bucket_table(kv, oracle, tmp_path):
+    """khmer.Nodetable(31, 1, 1) (kevlar/tests/test_simlike.py:69) and the shipped one-bucket
+    SmallCounttable term-high-abund/reference.sct."""
+    assert kv._lib.primes_below(1, 1) == [1]
+    shipped = kv.khmer.SmallCounttable.load(golden_data('term-high-abund/reference.sct'))
+    assert shipped.hashsizes() == [1] and shipped.n_occupied() == 0
+    out = str(tmp_path / 'one.sct')
+    shipped.save(out)
+    assert filecmp.cmp(out, golden_data('term-high-abund/reference.sct'), shallow=False)
+    for name in ('Nodetable', 'SmallCounttable', 'Counttable'):
+        g, c = getattr(kv.khmer, name)(31, 1, 1), getattr(oracle, name)(31, 1, 1)
+        assert g.hashsizes() == [1]
+        for seq in ('ACGT' * 10, 'GATTACA' * 9):
+            g.consume(seq)
+            c.consume(seq)
+        assert_same_sketch(g, c)
+        assert g.get('TTTT' * 7 + 'TTT') == c.get('TTTT' * 7 + 'TTT') > 0

@@ -500,5 +500,16 @@ def test_simlike_host_logic_against_reference_outputs(oracle):
     case_counts, ctrl_counts, alt_in_refr = discard_nonunique_kmers(first['alt'], kid, (mom, dad), ref)
     assert case_counts == first['abundances'][0] and ctrl_counts == first['abundances'][1:]
     assert len(alt_in_refr) == 31 and sum(1 for r in alt_in_refr if r) == 3
-    # mean 30.75: 10 is 20.75 away (dropped, the bound is strict), 90 too; mean 10: 40 is dropped
+    # the reference's sketch + VCF fixtures (k = 49 and 31; 4-bit reference sketches; a one-bucket table)
+    fixture = json.load(open(golden_gen('simlike_fixture_windows.json')))
+    assert len(fixture) == 105
+    loaded = {}
+    for c in fixture:
+        key = (c['set'],) + tuple(c['sketches'])
+        if key not in loaded:
+            loaded[key] = [_OracleQueries((oracle.SmallCounttable if f.endswith('.sct') else oracle.Counttable)
+                                          .load(golden_data(c['set'] + '/' + f))) for f in c['sketches']]
+        sk = loaded[key]
+        got = spanning_kmer_abundances(c['alt'], c['refr'], sk[0], sk[1:-1], sk[-1], dropoutliers=c['dropoutliers'])
+        assert got == (c['abundances'], c['refr_abunds'], c['ndropped'])
     assert discard_outlier_abunds([10, 11, 12, 90], [[1, 1, 1, 1], [0, 40, 0, 0]]) == ([11, 12], [[1, 1, 1, 1], [0, 0, 0]])
