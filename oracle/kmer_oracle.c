@@ -15,7 +15,12 @@
  *     (kevlar/tests/test_count.py:45-68)
  *   - test.{counttable,countgraph,smallcounttable,smallcountgraph,nodetable,nodegraph}
  *     queries (kevlar/tests/test_sketch.py:17-29)
- *   - the numeric pins of test_novel.py:179-194, test_filter.py:27-87, test_count.py:153-166.
+ *   - the numeric pins of test_novel.py:179-194, test_filter.py:27-87, test_count.py:153-166,
+ *     test_dist.py:25-43 (+ the shipped minitrio/trio-proband-dist.tsv);
+ *   - the reference's own, unmodified test files for the path run on top of this oracle
+ *     (tests/golden/reference_tests_over_oracle.log: 130 passed, incl. all of test_simlike.py,
+ *     whose likelihood scores pin get_kmer_counts for k = 31 and 49 on 8- and 4-bit tables);
+ *   - 24 more shipped sketch files load with consistent headers and re-save byte-identically.
  *
  * Call sites in the reference that each function stands in for are cited inline
  * as kevlar/<file>:<line>.
