@@ -9,9 +9,13 @@ increments), [N>1: merge the per-GPU partial sketches], then scan the proband re
 all three sketches (kevlar novel).  k-mers per step = sum over the 3 samples of counted
 k-mer positions + scanned k-mer positions.
 
-Workload at N=1 = BASELINE.json configs[1]: 1 Mbp genome, 30x => 300,000 reads x 100 bp per
-sample, k=31, 64 MB / 4-table 8-bit sketches.  Under torchrun every rank gets its own
-300k-read shard per sample (weak scaling; reads sharded, sketches merged).
+`value` / `e2e` workload = BASELINE.json configs[1] (C2): 1 Mbp genome, 30x => 300,000 reads x 100 bp
+per sample, k=31, 64 MB / 4-table 8-bit sketches.  Under torchrun every rank gets its own 300k-read
+shard per sample (weak scaling; reads sharded, sketches merged, novel shard-local).
+
+`c3` = BASELINE.json configs[2] in the same line: 100 Mbp genome at 30x => 30 M reads per sample,
+3 x 4 GB sketches (HBM-resident), reads generated on the device and sharded over the ranks (STRONG
+scaling: the same 90 M reads at every N), partial sketches merged over NVLink, novel shard-local.
 
 `value`  inputs already resident in HBM when the timed region starts.
 `e2e`    the same step through the public host-buffer API (pinned host batches, H2D copies and
@@ -39,6 +43,10 @@ READ_LEN = 100
 CASE_MIN, CTRL_MAX = 6, 1
 N_TABLES = 4
 
+C3_GENOME = 100000000
+C3_READS = 30000000
+C3_MEMORY = 4e9
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -56,6 +64,12 @@ def parse_args():
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-variants', action='store_true')
+    ap.add_argument('--no-c3', action='store_true', help='skip the config-3 (100 Mbp, 3 x 4 GB sketches) part')
+    ap.add_argument('--c3-reads', type=int, default=C3_READS, help='reads per sample of the config-3 part')
+    ap.add_argument('--c3-genome', type=int, default=C3_GENOME)
+    ap.add_argument('--c3-memory', type=float, default=C3_MEMORY)
+    ap.add_argument('--c3-steps', type=int, default=2)
+    ap.add_argument('--c3-no-parity', action='store_true')
     return ap.parse_args()
 
 
@@ -74,6 +88,17 @@ def workload_name(args):
             '3 x {:.0f} MB {}-bit {} {} with {} tables; step = count x3 + novel scan of the proband reads '
             '(case_min {}, ctrl_max {})').format(args.reads_per_sample, READ_LEN, K, MEMORY / 1e6, args.counter_size,
                                                   sketch_shape(args)[0], kind, N_TABLES, CASE_MIN, CTRL_MAX)
+
+
+def config_of(args, world):
+    """The workload description; BOTH arms print exactly this dict."""
+    return {
+        'workload': workload_name(args),
+        'reads_sharded': world > 1,
+        'exact_n_unique_tracking': not args.no_unique,
+        'l2': 'inputs larger than L2: per step 120 MB of reads + 192 MB of sketches + 240 MB of hash scratch '
+              'stream through a 126 MB L2; no explicit flush',
+    }
 
 
 def kmers_per_step(trio):
@@ -151,6 +176,32 @@ def cpu_step(ko, trio, threads, shape=('Counttable', MEMORY / N_TABLES)):
     return time.perf_counter() - t0, hits, counted, sks
 
 
+def reference_python_novel(ko, trio, max_reads=1500):
+    """The reference's REAL novel loop shape (kevlar/novel.py:123-169: a Python loop over reads and over
+    k-mers with one `get` per sample and k-mer, single-threaded) over the oracle's khmer-shaped
+    objects, on the first `max_reads` proband reads.  Returns (k-mers/s, reads used)."""
+    sks = []
+    for bases, offs in trio:
+        sk = ko.Counttable(K, MEMORY / N_TABLES, N_TABLES)
+        sk.consume_batch(bases, offs, threads=os.cpu_count() or 1)
+        sks.append(sk)
+    bases, offs = trio[0]
+    n = min(max_reads, len(offs) - 1)
+    seqs = [bases[int(offs[i]):int(offs[i + 1])].tobytes().decode() for i in range(n)]
+    case, ctrls = sks[0], sks[1:]
+    t0 = time.perf_counter()
+    nk = 0
+    for seq in seqs:
+        for kmer in case.get_kmers(seq):
+            nk += 1
+            if case.get(kmer) < CASE_MIN:
+                continue
+            for ct in ctrls:
+                if ct.get(kmer) > CTRL_MAX:
+                    break
+    return nk / (time.perf_counter() - t0), n
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host threads."""
     rank = int(os.environ.get('RANK', '0'))
@@ -172,12 +223,18 @@ def run_reference(args):
     sample = ('{} of {} reads/sample per step; count in {} pthreads pulling read chunks (khmer model), novel scan in C '
               'with {} threads (the reference runs it single-threaded in Python)').format(
                   n_reads, args.reads_per_sample, cores, cores)
+    py_rate, py_reads = reference_python_novel(ko, trio)
     line = {
         'impl': 'reference', 'metric': 'kmers_per_sec_count_plus_novel', 'value': value, 'unit': 'k-mers/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * total / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': workload_name(args), 'arm': 'CPU oracle port of the khmer path (khmer is not vendored)'},
+        'config': config_of(args, max(1, int(os.environ.get('WORLD_SIZE', '1')))),
+        'arm': 'CPU oracle port of the khmer path (khmer is not vendored)',
         'cpu_baseline': {'value': value, 'unit': 'k-mers/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'reference_python_novel_loop': {
+            'value': py_rate, 'unit': 'k-mers/s', 'cores': 1,
+            'sample': 'kevlar/novel.py:123-169 as the reference runs it: a single-threaded Python loop with one get() per '
+                      'sample and k-mer over the oracle sketches, first {} proband reads'.format(py_reads)},
         'e2e': {'value': value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -215,9 +272,11 @@ class GpuTrio(object):
         self.stream = torch.cuda.ExternalStream(_lib.stream_ptr(self.device), device=dev)
         self.last_hits = None
 
+    def plain_sketches(self):
+        return [] if self.sharded else list(self.sketches)
+
     def step_sharded(self):
-        # host buffers in both arms: hash locally, all-gather the hash stream, apply to the local bin
-        # ranges; novel from MIN-all-reduced partial abundances
+        # host buffers in both arms: hash locally, exchange, apply to the local bin ranges
         for sk in self.sketches:
             sk.local.clear()
         for i, sk in enumerate(self.sketches):
@@ -307,6 +366,269 @@ def load_atomic_peak(table_mb=64):
     return peaks
 
 
+def sketch_checksum(torch, sketch):
+    """64-bit checksum of a sketch's table storage, computed on the device."""
+    from kevlar_b200 import multigpu
+    flat = multigpu.GpuSketchAdapter(sketch).flat_tensor()
+    n8 = flat.numel() // 8 * 8
+    words = flat[:n8].view(torch.int64)
+    weights = torch.arange(1, 1025, dtype=torch.int64, device=flat.device)
+    pad = (-words.numel()) % 1024
+    if pad:
+        words = torch.cat([words, torch.zeros(pad, dtype=torch.int64, device=flat.device)])
+    return int((words.view(-1, 1024) * weights).sum().item()) ^ int(flat[n8:].sum().item())
+
+
+def multi_rank_parity(args, runner, rank, world, torch, multigpu, phase):
+    """N>1: what did the merge produce?  (a) every rank holds byte-identical merged sketches (device
+    checksums compared over the ranks); (b) rank 0 counts ALL ranks' shards with the multi-threaded oracle
+    and compares its table bytes with rank 0's merged GPU sketches, and the oracle's novel hits with
+    the hits gathered from all ranks.  Collective: every rank calls it."""
+    td = torch.distributed
+    sums = torch.tensor([sketch_checksum(torch, sk) for sk in runner.sketches], dtype=torch.int64, device='cuda')
+    allsums = [torch.empty_like(sums) for _ in range(world)]
+    td.all_gather(allsums, sums)
+    identical = all(bool((s == allsums[0]).all()) for s in allsums)
+    hits = multigpu.gather_hits(runner.last_hits, rank * args.reads_per_sample)
+    if rank != 0:
+        return None
+    from oracle import khmer_oracle as ko
+    from kevlar_b200 import simtrio
+    cores = os.cpu_count() or 1
+    name, buckets = sketch_shape(args)
+    osk = [getattr(ko, name)(K, buckets, N_TABLES) for _ in range(3)]
+    case_b, case_o = [], []
+    for r in range(world):
+        trio = simtrio.simulate_trio(1000000, reads_per_sample=args.reads_per_sample, seed_offset=1000 * r)
+        for sk, (b, o) in zip(osk, trio):
+            sk.consume_batch(b, o, threads=cores)
+        case_b.append(trio[0][0])
+        case_o.append(trio[0][1][:-1] + np.uint64(r * args.reads_per_sample * READ_LEN))
+    case_o.append(np.array([world * args.reads_per_sample * READ_LEN], dtype=np.uint64))
+    ohits, _ = ko.novel_batch(osk[:1], osk[1:], np.concatenate(case_b), np.concatenate(case_o), CASE_MIN, CTRL_MAX,
+                              threads=cores)
+    phase('oracle counted all {} shards'.format(world))
+    same_tables = all(g.table_bytes(t) == c.table_bytes(t) for g, c in zip(runner.sketches, osk) for t in range(N_TABLES))
+    hits = hits[np.lexsort((hits['offset'], hits['read']))]
+    same_hits = len(hits) == len(ohits) and bool((hits['read'] == ohits['read']).all()) and \
+        bool((hits['offset'] == ohits['offset']).all()) and bool((hits['abund'][:, :3] == ohits['abund'][:, :3]).all())
+    ok = identical and same_tables and same_hits
+    text = ('bit-exact at N={}: merged sketches identical on all ranks (device checksums), rank 0 tables == oracle over all '
+            '{} shards, {} gathered hits == oracle').format(world, world, len(ohits)) if ok else \
+        'MISMATCH (ranks identical: {}, tables: {}, hits: {} [{} vs {}])'.format(identical, same_tables, same_hits,
+                                                                                 len(hits), len(ohits))
+    return ok, text
+
+
+# ----------------------------------------------------------------------------- config 3
+
+def run_c3(args, rank, world, barrier, phase):
+    """BASELINE config 3: 100 Mbp trio at 30x, 3 x 4 GB 8-bit Counttables (HBM-resident), reads drawn on
+    the device and sharded over the ranks -- the same 90 M reads at every N (strong scaling).  Returns
+    this rank's measurements; collective (every rank calls it)."""
+    import torch
+    from kevlar_b200 import _lib, khmer, multigpu, simtrio
+    td = torch.distributed
+    device = _lib.current_device()
+    dev = torch.device('cuda', device)
+    n_total = args.c3_reads
+    lo, hi = multigpu.shard_bounds(n_total, rank, world)
+    dtrio = simtrio.device_trio(args.c3_genome, n_total, rank, world, read_len=READ_LEN)
+    phase('c3: {} reads x 3 samples drawn on the device'.format(hi - lo))
+    buckets = args.c3_memory / N_TABLES
+    sketches = [khmer.Counttable(K, buckets, N_TABLES) for _ in range(3)]
+    for sk in sketches:
+        sk.set_unique_tracking(False)
+    stream = torch.cuda.ExternalStream(_lib.stream_ptr(device), device=dev)
+    nk_sample = (hi - lo) * (READ_LEN - K + 1)
+    state = {}
+
+    def count(trio_slice, tracked=False):
+        for sk, (b, o) in zip(sketches, trio_slice):
+            sk.clear()
+            sk.set_unique_tracking(tracked)
+            sk.consume_batch(b.data_ptr(), (o.data_ptr(), o.numel() - 1), where=khmer.MEM_DEVICE, wait=False)
+        if world > 1:
+            multigpu.merge_sketches(sketches, how='p2p')
+
+    def scan(trio_slice):
+        b, o = trio_slice[0]
+        state['hits'] = khmer.novel_batch(sketches[:1], sketches[1:], b.data_ptr(), (o.data_ptr(), o.numel() - 1, b.numel()),
+                                          CASE_MIN, CTRL_MAX, where=khmer.MEM_DEVICE)[0]
+
+    def step():
+        count(dtrio)
+        scan(dtrio)
+
+    def timed(fn, n):
+        barrier()
+        torch.cuda.synchronize()
+        _lib.sync(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        _lib.sync(device)
+        torch.cuda.synchronize()
+        barrier()
+        return e0.elapsed_time(e1) / n
+
+    step()   # warm-up (allocates the scratch, maps the peers)
+    ms_step = timed(step, args.c3_steps)
+    phase('c3: timed steps done')
+    _lib.profile(1)
+    ms_count = timed(lambda: count(dtrio), 1)
+    prof_count = _lib.profile(1)
+    ms_scan = timed(lambda: scan(dtrio), 1)
+    prof_scan = _lib.profile(0)
+    ms_count_tracked = timed(lambda: count(dtrio, tracked=True), 1)
+    for sk in sketches:
+        sk.set_unique_tracking(False)
+    count(dtrio)
+    scan(dtrio)
+    _lib.sync(device)
+    n_hits = len(state['hits'])
+    # size-independent properties at full size: no counter saturated => every table sums to the number of
+    # k-mers counted by ALL ranks; all ranks hold the same merged sketch
+    props = {}
+    sums_ok, sat = True, False
+    for sk in sketches:
+        sat = sat or int(multigpu.GpuSketchAdapter(sk).flat_tensor().max().item()) == 255
+    if not sat:
+        for sk in sketches:
+            total = int(multigpu.GpuSketchAdapter(sk).flat_tensor().sum(dtype=torch.int64).item())
+            sums_ok = sums_ok and total == N_TABLES * n_total * (READ_LEN - K + 1)
+    props['table_sums_equal_kmers_counted'] = (sums_ok if not sat else 'not applicable: a counter saturated')
+    sums = torch.tensor([sketch_checksum(torch, sk) for sk in sketches], dtype=torch.int64, device=dev)
+    if world > 1:
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        td.all_gather(allsums, sums)
+        props['merged_sketches_identical_on_all_ranks'] = all(bool((s == allsums[0]).all()) for s in allsums)
+    props['sketch_checksums'] = [int(x) for x in sums.tolist()]
+    hits_total = torch.tensor([n_hits], dtype=torch.int64, device=dev)
+    if world > 1:
+        td.all_reduce(hits_total)
+    props['novel_hits_all_ranks'] = int(hits_total.item())
+    phase('c3: profiles and full-size properties done')
+
+    # parity on a bounded sample: the first 1/32 of every rank's shard, counted into the same (cleared)
+    # 4 GB sketches, merged, scanned; rank 0 redraws every rank's sample on its own device, copies it to the
+    # host and runs the oracle on the union
+    parity = None
+    if not args.c3_no_parity:
+        sub = max(1000, (hi - lo) // 32)
+        sub_trio = [(b[:sub * READ_LEN], o[:sub + 1]) for b, o in dtrio]
+        count(sub_trio, tracked=False)
+        scan(sub_trio)
+        _lib.sync(device)
+        hits = multigpu.gather_hits(state['hits'], 0)   # read indices stay rank-local; the rank is added below
+        sub_hits = state['hits']
+        counts = torch.tensor([len(sub_hits)], dtype=torch.int64, device=dev)
+        all_counts = [torch.empty_like(counts) for _ in range(world)]
+        if world > 1:
+            td.all_gather(all_counts, counts)
+        else:
+            all_counts = [counts]
+        if rank == 0:
+            from oracle import khmer_oracle as ko
+            cores = os.cpu_count() or 1
+            osk = [ko.Counttable(K, buckets, N_TABLES) for _ in range(3)]
+            case_parts = []
+            haps = simtrio.trio_haplotypes(args.c3_genome)
+            import ctypes
+            for r in range(world):
+                rlo, rhi = multigpu.shard_bounds(n_total, r, world)
+                rsub = max(1000, (rhi - rlo) // 32)
+                for si, (hp, seed) in enumerate(zip(haps, simtrio.READ_SEEDS)):
+                    dh = [torch.from_numpy(np.ascontiguousarray(h)).to(dev) for h in hp]
+                    ptrs = (ctypes.c_void_p * len(dh))(*[t.data_ptr() for t in dh])
+                    lens = (ctypes.c_uint64 * len(dh))(*[t.numel() for t in dh])
+                    bases = torch.empty(rsub * READ_LEN, dtype=torch.uint8, device=dev)
+                    torch.cuda.synchronize(dev)
+                    _lib.check(_lib.lib().kv_synth_reads(device, ptrs, lens, len(dh), rsub, rlo, READ_LEN, 0.005, int(seed),
+                                                         bases.data_ptr(), None))
+                    hb = bases.cpu().numpy()
+                    ho = np.arange(rsub + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+                    osk[si].consume_batch(hb, ho, threads=cores)
+                    if si == 0:
+                        case_parts.append((hb, ho))
+                    del dh, bases
+            same_tables = all(g.table_bytes(t) == c.table_bytes(t) for g, c in zip(sketches, osk) for t in range(N_TABLES))
+            o_total, same_hits, pos = 0, True, 0
+            for r, (hb, ho) in enumerate(case_parts):
+                ohits, _ = ko.novel_batch(osk[:1], osk[1:], hb, ho, CASE_MIN, CTRL_MAX, threads=cores)
+                n_r = int(all_counts[r].item())
+                mine = hits[pos:pos + n_r]
+                pos += n_r
+                mine = mine[np.lexsort((mine['offset'], mine['read']))]
+                same_hits = same_hits and len(mine) == len(ohits) and bool((mine['read'] == ohits['read']).all()) and \
+                    bool((mine['offset'] == ohits['offset']).all()) and \
+                    bool((mine['abund'][:, :3] == ohits['abund'][:, :3]).all())
+                o_total += len(ohits)
+            ok = same_tables and same_hits
+            parity = {'ok': ok, 'sample': 'first 1/32 of every rank\'s shard ({} reads per sample in all) counted into 3 x {:.0f} GB '
+                                          'sketches, merged over {} rank(s), scanned'.format(
+                                              sum(max(1000, (multigpu.shard_bounds(n_total, r, world)[1] -
+                                                             multigpu.shard_bounds(n_total, r, world)[0]) // 32)
+                                                  for r in range(world)), args.c3_memory / 1e9, world),
+                      'result': 'bit-exact: 12 tables of rank 0 == oracle, {} hits == oracle'.format(o_total) if ok else
+                                'MISMATCH (tables {}, hits {})'.format(same_tables, same_hits)}
+            del osk
+            phase('c3: parity sample checked against the oracle')
+        barrier()
+
+    # whole-job numbers: max over ranks
+    t = torch.tensor([ms_step, ms_count, ms_scan, ms_count_tracked, prof_count['merge'][0]], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_step, ms_count, ms_scan, ms_count_tracked, ms_merge = t.tolist()
+    flat_bytes = sketches[0].flat_device_buffer()[1]
+    out = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        nk_all = n_total * (READ_LEN - K + 1)
+        lfrac = READ_LEN / float(READ_LEN - K + 1)
+        kern_count = {k: round(v[0], 3) for k, v in prof_count.items() if v[1]}
+        kern_scan = {k: round(v[0], 3) for k, v in prof_scan.items() if v[1]}
+        upd_ms = prof_count['increment'][0] or 1e-9      # rank 0, all three samples
+        nov_ms = prof_scan['novel'][0] or 1e-9
+        out = {
+            'workload': 'C3: synthetic 100 Mbp trio at 30x = {} reads x {} bp per sample (drawn on the device), k={}, 3 x {:.0f} GB '
+                        '8-bit Counttable with {} tables (HBM-resident); reads sharded over {} rank(s) (strong scaling), partial '
+                        'sketches merged by the one-pass p2p all-reduce, novel scan shard-local'.format(
+                            n_total, READ_LEN, K, args.c3_memory / 1e9, N_TABLES, world),
+            'scaling': 'strong', 'steps': args.c3_steps, 'kmers_per_step': 4 * nk_all,
+            'value': 4 * nk_all / (ms_step / 1e3), 'unit': 'k-mers/s', 'ms_per_step': ms_step,
+            'count': {'ms': ms_count, 'kmers_per_s': 3 * nk_all / (ms_count / 1e3),
+                      'frac_of_hbm_model': 3 * nk_all / (ms_count / 1e3) * (64.0 * N_TABLES + lfrac) / (peak * 1e9),
+                      'ms_with_exact_n_unique': ms_count_tracked,
+                      'kmers_per_s_with_exact_n_unique': 3 * nk_all / (ms_count_tracked / 1e3),
+                      'kernel_ms_rank0': kern_count},
+            'novel': {'ms': ms_scan, 'kmers_per_s': nk_all / (ms_scan / 1e3),
+                      'frac_of_hbm_model': nk_all / (ms_scan / 1e3) * (32.0 * 3 * N_TABLES + lfrac) / (peak * 1e9),
+                      'kernel_ms_rank0': kern_scan},
+            'roofline_update': {
+                'kernel': 'kv_part_apply_kernel<8> (+ partition) / kv_increment_kernel<8>', 'bound': 'hbm',
+                'achieved': 64.0 * N_TABLES * 3 * nk_sample / ((upd_ms + prof_count['partition'][0]) / 1e3) / 1e9,
+                'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
+                'note': 'algorithmic 64 B x 4 tables per k-mer over the update kernels of rank 0 (partition + apply)'},
+            'roofline_novel': {
+                'kernel': 'kv_novel_kernel', 'bound': 'hbm',
+                'achieved': (32.0 * 3 * N_TABLES + lfrac) * nk_sample / (nov_ms / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                'peak_source': peak_src},
+            'merge': {'ms_per_step': ms_merge, 'share_of_count': ms_merge / ms_count if ms_count else None,
+                      'bytes_in_plus_out_per_rank': 2 * 3 * flat_bytes * (world - 1) / world,
+                      'nvlink_GBps_per_rank': (2 * 3 * flat_bytes * (world - 1) / world) / (ms_merge / 1e3) / 1e9 if ms_merge else None},
+            'properties_at_full_size': props,
+            'parity_vs_oracle': parity,
+        }
+        for key in ('roofline_update', 'roofline_novel'):
+            out[key]['frac'] = out[key]['achieved'] / peak
+    barrier()
+    return out, sketches
+
+
 def run_ours(args):
     t_start = time.perf_counter()
     import torch
@@ -317,6 +639,7 @@ def run_ours(args):
     if _lib.device_count() < 1:
         raise SystemExit('bench.py: no CUDA device; the GPU arm has no CPU fallback')
     torch.cuda.set_device(_lib.current_device())
+    live = []   # every sketch a merge may have exported: released collectively in the teardown
 
     def barrier():
         if world > 1:
@@ -326,11 +649,26 @@ def run_ours(args):
         if rank == 0:
             print('[bench] +{:6.1f}s {}'.format(time.perf_counter() - t_start, what), file=sys.stderr, flush=True)
 
+    try:
+        line = measure(args, rank, world, barrier, phase, live)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    finally:
+        # collective teardown on EVERY rank: unmap peers, meet, free, leave the group
+        if world > 1:
+            multigpu.shutdown(live)
+        live.clear()
+
+
+def measure(args, rank, world, barrier, phase, live):
+    import torch
+    from kevlar_b200 import _lib, multigpu, simtrio
     phase('rendezvous done ({} rank{})'.format(world, 's' if world > 1 else ''))
     trio = simtrio.simulate_trio(1000000, reads_per_sample=args.reads_per_sample, seed_offset=1000 * rank)
     nk_rank = kmers_per_step(trio)
     phase('synthetic trio generated')
     runner = GpuTrio(args, trio, world)
+    live.extend(runner.plain_sketches())
     phase('sketches allocated, inputs staged')
 
     for _ in range(max(3, args.warmup)):
@@ -339,18 +677,22 @@ def run_ours(args):
         runner.step(False)
     phase('warm-up done')
 
+    # headline: per-launch profiling OFF; clocks sampled during the timed region
     sampler = ClockSampler(_lib.current_device())
     if rank == 0:
         sampler.start()
-    _lib.profile(1)
     launches0 = _lib.launch_count()
     ms_value = runner.timed(args.steps, True, barrier)
     launches = _lib.launch_count() - launches0
-    prof = _lib.profile(0)
     clocks = sampler.stop() if rank == 0 else None
     hits_value = runner.last_hits.copy()
     ms_e2e = runner.timed(args.steps, False, barrier)
     hits_e2e = runner.last_hits.copy()
+    # separate pass for the per-kernel-class split (event pair around every launch)
+    prof_steps = min(args.steps, 5)
+    _lib.profile(1)
+    ms_profiled = runner.timed(prof_steps, True, barrier)
+    prof = _lib.profile(0)
     phase('timed regions done')
     assert len(hits_value) == len(hits_e2e) and (hits_value['offset'] == hits_e2e['offset']).all()
 
@@ -362,15 +704,32 @@ def run_ours(args):
         torch.distributed.all_reduce(n, op=torch.distributed.ReduceOp.SUM)
     ms_value, ms_e2e = t.tolist()
     nk = n.item()
+
+    parity_n = None
+    if world > 1 and not runner.sharded and not args.no_cpu_baseline:
+        parity_n = multi_rank_parity(args, runner, rank, world, torch, multigpu, phase)
+
+    c3 = None
+    if not args.no_c3 and not runner.sharded:
+        c3, c3_sketches = run_c3(args, rank, world, barrier, phase)
+        live.extend(c3_sketches)
+        if world > 1:   # free 12 GB per rank before anything else is allocated
+            multigpu.release_p2p(c3_sketches)
+        for sk in c3_sketches:
+            live.remove(sk)
+        del c3_sketches
+
+    if world > 1 and args.merge == 'p2p':
+        multigpu.peer_sync_status()   # raises if a device-side barrier ever timed out
     if rank != 0:
-        return
+        return None
 
     value = nk * args.steps / (ms_value / 1e3)
     e2e = nk * args.steps / (ms_e2e / 1e3)
     h2d = sum(b.nbytes + o.nbytes for b, o in trio) + trio[0][0].nbytes + trio[0][1].nbytes
     d2h = len(hits_e2e) * 24 + len(trio[0][1]) * 4 + 64
 
-    # per-kernel-class breakdown of the timed (resident) region, device time from CUDA events
+    # per-kernel-class breakdown (profiled pass), device time from CUDA events
     kmers_count = (nk_rank - int(np.maximum(np.diff(trio[0][1].astype(np.int64)) - K + 1, 0).sum())) // 3
     kmers_scan = nk_rank - 3 * kmers_count
     lfrac = READ_LEN / float(READ_LEN - K + 1)
@@ -385,12 +744,13 @@ def run_ours(args):
     for name, (ms, count) in prof.items():
         if not count:
             continue
-        entry = {'launches_per_step': count / args.steps, 'ms_per_launch': ms / count,
+        entry = {'launches_per_step': count / prof_steps, 'ms_per_launch': ms / count,
                  'share_of_kernel_time': ms / total_kernel_ms}
-        entry['ms_per_step'] = ms / args.steps
+        entry['ms_per_step'] = ms / prof_steps
         if name in alg_bytes:
-            entry['algorithmic_GBps'] = alg_bytes[name] / (ms / args.steps / 1e3) / 1e9
+            entry['algorithmic_GBps'] = alg_bytes[name] / (ms / prof_steps / 1e3) / 1e9
         kernels[name] = entry
+    dominant_any = max(kernels, key=lambda k_: kernels[k_]['share_of_kernel_time'])
     dominant = max((k for k in kernels if k in alg_bytes), key=lambda k_: kernels[k_]['share_of_kernel_time'])
     kname = {'increment': 'kv_increment_kernel<{}>'.format(args.counter_size), 'hash': 'kv_hash_kernel',
              'novel': 'kv_novel_kernel'}[dominant]
@@ -399,22 +759,29 @@ def run_ours(args):
                 'frac': achieved / peak, 'traffic': load_traffic(kname), 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes[dominant] / kernels[dominant]['launches_per_step'],
                 'launches_per_step': kernels[dominant]['launches_per_step'],
-                'avg_launch_ms': kernels[dominant]['ms_per_launch']}
+                'avg_launch_ms': kernels[dominant]['ms_per_launch'],
+                'largest_kernel_class': dominant_any}
+    if dominant_any != dominant:
+        roofline['note_class'] = ('the largest class by device time is `{}` ({:.0%}), bookkeeping with no algorithmic bytes in '
+                                  'SURVEY 8(d); the roofline is quoted for the largest kernel that has them').format(
+                                      dominant_any, kernels[dominant_any]['share_of_kernel_time'])
     if roofline['frac'] > 1.0:
         roofline['note'] = ('frac > 1: the 64 MB sketch is L2-resident, so most of the algorithmic sector traffic (64 B per '
                             'table touch) never reaches HBM -- `traffic` is the measured DRAM bytes per launch; the bound '
-                            'that applies is roofline_l2 (L2 atomic throughput)')
+                            'that applies is roofline_l2 (L2 atomic throughput); the HBM-resident regime is in `c3`')
     # L2-resident case: update rate against the microbenchmarked L2 atomic peak for a 64 MB table
     atomic = load_atomic_peak(64)
-    updates_per_s = N_TABLES * kmers_count * 3 / (prof['increment'][0] / args.steps / 1e3)
-    roofline_l2 = {'kernel': 'kv_increment_kernel<8>', 'bound': 'l2_atomic', 'achieved': updates_per_s / 1e9,
-                   'unit': 'G updates/s', 'peak': atomic.get('atom_add'), 'peak_red_add': atomic.get('red_add'),
-                   'frac': updates_per_s / 1e9 / atomic['atom_add'] if atomic.get('atom_add') else None,
-                   'peak_source': 'tools/atomic_microbench.cu on this pool (profiles/r01_atomic_microbench.csv): random '
-                                  'ATOM.ADD / RED.ADD over a 64 MB table'}
+    roofline_l2 = None
+    if prof['increment'][1]:
+        updates_per_s = N_TABLES * kmers_count * 3 / (prof['increment'][0] / prof_steps / 1e3)
+        roofline_l2 = {'kernel': 'kv_increment_kernel<8>', 'bound': 'l2_atomic', 'achieved': updates_per_s / 1e9,
+                       'unit': 'G updates/s', 'peak': atomic.get('atom_add'), 'peak_red_add': atomic.get('red_add'),
+                       'frac': updates_per_s / 1e9 / atomic['atom_add'] if atomic.get('atom_add') else None,
+                       'peak_source': 'tools/atomic_microbench.cu on this pool (profiles/r01_atomic_microbench.csv): random '
+                                      'ATOM.ADD / RED.ADD over a 64 MB table'}
     # the count path (hash + unique + increment per sample) and the novel path against 8d's figures
-    count_ms = sum(prof[c][0] for c in ('hash', 'unique', 'increment', 'fixup')) / (3.0 * args.steps)
-    novel_ms = prof['novel'][0] / args.steps
+    count_ms = sum(prof[c][0] for c in ('hash', 'unique', 'increment', 'fixup', 'partition')) / (3.0 * prof_steps)
+    novel_ms = prof['novel'][0] / prof_steps
     paths = {
         'count': {'ms_per_sample': count_ms, 'kmers_per_s': kmers_count / (count_ms / 1e3),
                   'algorithmic_GBps': (64.0 * N_TABLES + lfrac) * kmers_count / (count_ms / 1e3) / 1e9},
@@ -428,13 +795,8 @@ def run_ours(args):
         'metric': 'kmers_per_sec_count_plus_novel', 'value': value, 'unit': 'k-mers/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_value / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {
-            'workload': workload_name(args),
-            'kmers_per_step': nk, 'reads_sharded': world > 1, 'merge': args.merge if world > 1 else None,
-            'exact_n_unique_tracking': not args.no_unique,
-            'l2': 'inputs larger than L2: per step 120 MB of reads + 192 MB of sketches + 240 MB of hash scratch '
-                  'stream through a 126 MB L2; no explicit flush',
-        },
+        'config': config_of(args, world),
+        'kmers_per_step': nk, 'merge': args.merge if world > 1 else None,
         'e2e': {'value': e2e, 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
@@ -442,9 +804,13 @@ def run_ours(args):
         'roofline': roofline,
         'roofline_l2': roofline_l2,
         'kernels': kernels,
+        'kernels_note': 'per-class split from a separate pass of {} steps with an event pair around every launch ({:.3f} ms/step); '
+                        'the headline is timed with that switched off'.format(prof_steps, ms_profiled / prof_steps),
         'paths': paths,
         'novel_hits_per_step': int(len(hits_value)),
     }
+    if c3 is not None:
+        line['c3'] = c3
 
     if world == 1 and not args.no_cpu_baseline:
         from oracle import khmer_oracle as ko
@@ -464,6 +830,11 @@ def run_ours(args):
         line['parity_vs_oracle'] = 'bit-exact (3 sketches, {} hits)'.format(len(ohits)) if same else 'MISMATCH'
         if not same:
             raise SystemExit('bench.py: GPU results differ from the oracle')
+    if parity_n is not None:
+        line['parity_vs_oracle'] = parity_n[1]
+        if not parity_n[0]:
+            print(json.dumps(line), flush=True)
+            raise SystemExit('bench.py: merged GPU results differ from the oracle')
 
     if world == 1 and not args.no_variants:
         # the same step with the other hasher / without n_unique tracking, for context
@@ -483,13 +854,7 @@ def run_ours(args):
             variants[label] = {'value': nk * args.steps / (ms2 / 1e3), 'ms_per_step': ms2 / args.steps}
             del r2
         line['variants'] = variants
-    if world > 1 and args.merge == 'p2p':
-        runner.multigpu.peer_sync_status()   # raises if a device-side barrier ever timed out
-    print(json.dumps(line))
-    if world > 1:
-        if args.merge == 'p2p':
-            runner.multigpu.release_peer_sync()
-        torch.distributed.destroy_process_group()
+    return line
 
 
 def main():

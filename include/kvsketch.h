@@ -42,7 +42,7 @@ extern "C" {
 #define KV_MEM_HOST 0
 #define KV_MEM_DEVICE 1
 
-#define KV_MAX_TABLES 16
+#define KV_MAX_TABLES 8   /* tables per sketch (kevlar always builds 4: kevlar/count.py:29) */
 #define KV_MAX_SAMPLES 16 /* case + control sketches in one novel scan */
 #define KV_MAX_KSIZE_MURMUR 64
 #define KV_MAX_KSIZE_TWOBIT 32
@@ -261,6 +261,16 @@ int kv_reader_next(kv_reader *r, uint64_t max_bases, const uint8_t **bases, cons
                    const uint64_t **qual_offsets, const uint8_t **is_fastq);
 int kv_reader_num_reads(const kv_reader *r, uint64_t *n);
 int kv_reader_close(kv_reader *r);
+
+/* Measurement fixture, no reference counterpart in the product path: wgsim-style synthetic reads
+ * drawn on the device (the recipe of kevlar/tests/data/minitrio/README: fixed-length reads from a
+ * random haplotype / position / strand, iid substitution errors), so that inputs of BASELINE
+ * configs 3-4 size never cross PCIe.  Read r (global index first_read + r) is a pure function of
+ * (seed, r): ranks can generate disjoint slices of one sample.  dev_haplotypes: n_haps device
+ * pointers to upper-case ACGT bytes.  dev_offsets (n_reads + 1 u64, device) may be NULL. */
+int kv_synth_reads(int device, const uint8_t *const *dev_haplotypes, const uint64_t *hap_lens, int n_haps,
+                   uint64_t n_reads, uint64_t first_read, uint32_t read_len, double error_rate, uint64_t seed,
+                   uint8_t *dev_bases, uint64_t *dev_offsets);
 
 /* Stream plumbing: the cudaStream_t all work for `device` is enqueued on, so a host
  * framework can record events on it; kv_sync waits for it. */

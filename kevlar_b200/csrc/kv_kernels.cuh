@@ -43,6 +43,73 @@ __global__ void kv_tile_index_kernel(const uint64_t *__restrict__ offsets, uint6
 
 // -------------------------------------------------------------------- K1/K2
 
+// K3c bookkeeping shared by the hash kernel (producer) and kv_tile_apply_kernel (consumer): table t is
+// cut into regions of 2^rb buckets; run = run_base[t] + (bin >> rb) owns slab[run * cap .. + cap) and
+// the cursor that hands out its slots.
+struct KvTileInfo {
+    int rb;                              // log2(buckets per region), <= 16 so offsets fit 16 bits
+    uint32_t run_base[KV_TABLES_DEV + 1];   // first run of table t; [n_tables] = number of runs
+    uint32_t cap;                        // slots per run in this chunk (a multiple of the block size)
+    uint32_t *cursor;                    // [runs] slots requested so far (may exceed cap)
+    uint16_t *slab;                      // runs * cap offsets, laid out by kv_slab_index
+    int blk_log2;                        // >= 0: block-interleaved slabs, 2^blk_log2 slots per block; < 0: run-major
+    // overflow (a run asked for more than cap slots: skewed input).  Untracked sketches are updated in
+    // place by the producer; with exact n_unique tracking the tables must stay untouched until the
+    // first-touch passes have run, so the producer only marks (position, table) here and
+    // kv_tile_overflow_kernel applies the marks afterwards.
+    uint32_t *ovf;                       // NULL: update in place; else [n_tables][ovf_stride] bitmaps over chunk positions
+    uint64_t ovf_stride;
+    unsigned *ovf_any;
+};
+
+// Where slot `slot` of run `run` lives.  Hashing spreads the updates evenly, so all runs fill at the same
+// pace: with block-interleaved slabs ([block][run][2^blk_log2 slots]) the write frontier of ALL runs is
+// one contiguous stretch of runs * 2^blk_log2 * 2 bytes that moves through the array, instead of one
+// open sector per run spread over the whole allocation (gigabytes, thousands of pages).
+__device__ __forceinline__ size_t kv_slab_index(const KvTileInfo &ti, uint32_t run, uint32_t slot)
+{
+    if (ti.blk_log2 < 0) return (size_t)run * ti.cap + slot;
+    const uint32_t n_runs = ti.run_base[KV_TABLES_DEV];   // mirrored there by the host: total number of runs
+    return ((((size_t)(slot >> ti.blk_log2) * n_runs + run) << ti.blk_log2) | (slot & ((1u << ti.blk_log2) - 1u)));
+}
+
+// exact saturating update of one bucket in global memory, counter width chosen at run time (the
+// overflow path of K3c and its sparse regions: rare, so no template instance per width)
+__device__ __forceinline__ void kv_bucket_inc_exact(const KvView &v, int t, uint64_t bin)
+{
+    unsigned *w, sh, seen;
+    if (v.bits == 8) { kv_word_addr<8>(v, t, bin, w, sh); kv_sat_inc_exact<8>(w, sh, seen); }
+    else if (v.bits == 4) { kv_word_addr<4>(v, t, bin, w, sh); kv_sat_inc_exact<4>(w, sh, seen); }
+    else { kv_word_addr<1>(v, t, bin, w, sh); atomicOr(w, 1u << sh); }
+}
+
+// file the updates of hash h for tables t0 .. t0+3 (K3c producer)
+__device__ __forceinline__ void kv_scatter4(const KvTileInfo &ti, const KvView &sk, int t0, uint64_t h, uint64_t pos)
+{
+    uint64_t bin[4];
+    uint32_t run[4], slot[4];
+    bool own[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        own[j] = t0 + j < sk.n_tables && kv_bin(sk, t0 + j, h, bin[j]);
+        if (own[j]) run[j] = ti.run_base[t0 + j] + (uint32_t)(bin[j] >> ti.rb);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (own[j]) slot[j] = atomicAdd(ti.cursor + run[j], 1u);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (own[j]) {
+            if (slot[j] < ti.cap)
+                ti.slab[kv_slab_index(ti, run[j], slot[j])] = (uint16_t)(bin[j] & ((1u << ti.rb) - 1u));
+            else if (ti.ovf) {   // slab full (skewed input), tables frozen until the n_unique passes are done
+                atomicOr(ti.ovf + (size_t)(t0 + j) * ti.ovf_stride + (pos >> 5), 1u << (pos & 31));
+                *ti.ovf_any = 1u;
+            } else
+                kv_bucket_inc_exact(sk, t0 + j, bin[j]);   // slab full: update in place, exactly
+        }
+}
+
 struct KvHashParams {
     const uint8_t *bases;
     const uint64_t *offsets;
@@ -59,10 +126,15 @@ struct KvHashParams {
     uint64_t *hashes;      // [chunk positions] (may be NULL)
     uint32_t *valid;       // [chunk positions / 32] bit: position starts a k-mer that passed the filters
     unsigned long long *n_valid;   // running count of valid k-mers (khmer n_consumed)
+    // K3c (tiled update path): the kernel also files every update of the sketch `sk` under its
+    // (table, region) run, as a 16-bit bucket offset inside the region
+    int scatter;
+    KvTileInfo ti;
+    KvView sk;
 };
 
-template <int HASHER, int KW>
-__global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
+template <int HASHER, int KW, bool SCATTER>
+__global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(const __grid_constant__ KvHashParams p)
 {
     __shared__ KvTileSmem sm;
     __shared__ KvTileList ls;
@@ -98,6 +170,12 @@ __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(KvHashParams p)
         if (p.hashes) p.hashes[tile_start + l - pos0] = h;
         if (ok) atomicOr(&s_valid[l >> 5], 1u << (l & 31));
         n_ok += ok;
+        if (SCATTER && ok) {
+            // K3c: one cursor atomic + one 2-byte store per table (kevlar always builds 4 tables; more are
+            // handled four at a time)
+            const uint64_t pos = tile_start + l - pos0;
+            for (int t0 = 0; t0 < p.sk.n_tables; t0 += 4) kv_scatter4(p.ti, p.sk, t0, h, pos);
+        }
     }
     __syncthreads();
     if (threadIdx.x < KV_TILE / 32 && tile_start + threadIdx.x * 32 < p.total)
@@ -500,6 +578,149 @@ __global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_part_apply_kernel(KvV
     }
 }
 
+// ------------------------------------------------------------- K3c: tiled updates in shared memory
+//
+// For sketches that do not fit L2, a counter update in place is a random DRAM sector read-modify-write
+// (~22 G/s on B200, row-activation bound, whatever the instruction).  K3c never does that: the hash
+// kernel files each update under its (table, region) run -- region = 2^rb <= 65536 adjacent buckets --
+// as a 16-bit offset, and here ONE CTA per run
+//   streams its region from HBM into shared memory, widened to 16 bits per counter,
+//   applies the run's offsets with shared-memory adds (two counters per 32-bit word; a lane cannot
+//     overflow before the clamp because at most KV_TILE_BATCH offsets are applied between clamps),
+//   clamps to the counter maximum and streams the region back.
+// All HBM traffic is coalesced: the region (read + write) and 2 bytes per update.  Exact by
+// construction -- the CTA owns the region, so there is no speculation, rollback or hot bitmap.
+// Regions that received only a few offsets are cheaper to update in place (cnt * 64 B of sector
+// traffic against 2 x region bytes): those go through the exact global path.  Bit tables (Bloom
+// filters) keep their bytes and use shared-memory ORs.
+// the producer's overflow marks (tracked sketches), applied in place once the n_unique passes are done
+__global__ void __launch_bounds__(256) kv_tile_overflow_kernel(const __grid_constant__ KvView v, const __grid_constant__ KvTileInfo ti,
+                                                               const uint64_t *__restrict__ hashes, uint64_t n_pos)
+{
+    if (*ti.ovf_any == 0) return;
+    const uint64_t n_words = (n_pos + 31) / 32;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int t = 0; t < v.n_tables; t++)
+        for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+            uint32_t m = ti.ovf[(size_t)t * ti.ovf_stride + w];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                uint64_t bin;
+                if (kv_bin(v, t, hashes[w * 32 + b], bin)) kv_bucket_inc_exact(v, t, bin);
+            }
+        }
+}
+
+#define KV_TILE_THREADS 512
+#define KV_TILE_BATCH 60000u     // offsets applied between two clamps: 255 + 60000 < 65536
+
+template <int BITS>
+__global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __grid_constant__ KvView v, const __grid_constant__ KvTileInfo ti,
+                                                                        uint32_t direct_below)
+{
+    extern __shared__ uint32_t sm_tile[];   // BITS 8/4: (1 << rb) / 2 words of two 16-bit counters; BITS 1: (1 << rb) / 32 words
+    const uint32_t run = blockIdx.x;
+    const uint32_t want = ti.cursor[run];
+    const uint32_t cnt = want < ti.cap ? want : ti.cap;
+    if (cnt == 0) return;
+    int t = 0;
+    while (t + 1 < v.n_tables && run >= ti.run_base[t + 1]) t++;
+    const uint64_t bucket0 = (uint64_t)(run - ti.run_base[t]) << ti.rb;
+    const uint32_t nb = (uint32_t)((v.size[t] - bucket0) < (1ull << ti.rb) ? (v.size[t] - bucket0) : (1ull << ti.rb));
+    if (cnt < direct_below) {   // sparse region: in place
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) kv_bucket_inc_exact(v, t, bucket0 + ti.slab[kv_slab_index(ti, run, i)]);
+        return;
+    }
+    if (BITS == 1) {
+        uint8_t *g = v.tab[t] + (bucket0 >> 3);
+        const uint32_t nbytes = (nb + 7) >> 3, nwords = (nbytes + 3) >> 2;
+        for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) sm_tile[w] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t o = ti.slab[kv_slab_index(ti, run, i)];
+            atomicOr(&sm_tile[o >> 5], 1u << (o & 31));
+        }
+        __syncthreads();
+        // OR the collected bits into the table (bytes of a region are not shared with other regions:
+        // bucket0 is a multiple of 2^rb >= 8)
+        for (uint32_t b = threadIdx.x; b < nbytes; b += blockDim.x) {
+            const uint8_t add = (uint8_t)(sm_tile[b >> 2] >> (8 * (b & 3)));
+            if (add) g[b] |= add;
+        }
+        return;
+    }
+    const unsigned maxv = BITS == 8 ? 255u : 15u;
+    // ---- load + widen: 16 counters per thread and iteration
+    if (BITS == 8) {
+        const uint8_t *g = v.tab[t] + bucket0;          // 2^rb-aligned inside a 256-byte aligned table
+        const uint32_t nvec = nb >> 4;
+        const uint4 *gv = (const uint4 *)g;
+        uint4 *sv = (uint4 *)sm_tile;
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const uint4 x = __ldcs(gv + i);
+            uint4 lo, hi;
+            lo.x = __byte_perm(x.x, 0, 0x4140); lo.y = __byte_perm(x.x, 0, 0x4342);
+            lo.z = __byte_perm(x.y, 0, 0x4140); lo.w = __byte_perm(x.y, 0, 0x4342);
+            hi.x = __byte_perm(x.z, 0, 0x4140); hi.y = __byte_perm(x.z, 0, 0x4342);
+            hi.z = __byte_perm(x.w, 0, 0x4140); hi.w = __byte_perm(x.w, 0, 0x4342);
+            sv[2 * i] = lo;
+            sv[2 * i + 1] = hi;
+        }
+        for (uint32_t b = (nvec << 4) + threadIdx.x; b < nb + (nb & 1); b += blockDim.x)   // ragged end of the table
+            ((uint16_t *)sm_tile)[b] = b < nb ? g[b] : 0;
+    } else {
+        const uint8_t *g = v.tab[t] + (bucket0 >> 1);   // even bucket = high nibble
+        const uint32_t nbytes = (nb + 1) >> 1;
+        for (uint32_t y = threadIdx.x; y < nbytes; y += blockDim.x) {
+            const unsigned byte = g[y];
+            sm_tile[y] = (byte >> 4) | ((byte & 15u) << 16);
+        }
+    }
+    __syncthreads();
+    // ---- apply, at most KV_TILE_BATCH offsets between clamps
+    const uint32_t nwords = (nb + 1) >> 1;
+    for (uint32_t base = 0; base < cnt; base += KV_TILE_BATCH) {
+        const uint32_t end = base + KV_TILE_BATCH < cnt ? base + KV_TILE_BATCH : cnt;
+        for (uint32_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+            const uint32_t o = __ldcs(ti.slab + kv_slab_index(ti, run, i));
+            atomicAdd(&sm_tile[o >> 1], 1u << (16 * (o & 1)));
+        }
+        __syncthreads();
+        if (end < cnt) {
+            for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) sm_tile[w] = __vminu2(sm_tile[w], maxv | (maxv << 16));
+            __syncthreads();
+        }
+    }
+    // ---- clamp + narrow + store
+    if (BITS == 8) {
+        uint8_t *g = v.tab[t] + bucket0;
+        const uint32_t nvec = nb >> 4;
+        uint4 *gv = (uint4 *)g;
+        const uint4 *sv = (const uint4 *)sm_tile;
+        const uint32_t lim = 0x00ff00ffu;
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            uint4 lo = sv[2 * i], hi = sv[2 * i + 1], x;
+            x.x = __byte_perm(__vminu2(lo.x, lim), __vminu2(lo.y, lim), 0x6420);
+            x.y = __byte_perm(__vminu2(lo.z, lim), __vminu2(lo.w, lim), 0x6420);
+            x.z = __byte_perm(__vminu2(hi.x, lim), __vminu2(hi.y, lim), 0x6420);
+            x.w = __byte_perm(__vminu2(hi.z, lim), __vminu2(hi.w, lim), 0x6420);
+            gv[i] = x;
+        }
+        for (uint32_t b = (nvec << 4) + threadIdx.x; b < nb; b += blockDim.x) {
+            const unsigned c = ((const uint16_t *)sm_tile)[b];
+            g[b] = (uint8_t)(c > 255u ? 255u : c);
+        }
+    } else {
+        uint8_t *g = v.tab[t] + (bucket0 >> 1);
+        const uint32_t nbytes = (nb + 1) >> 1;
+        for (uint32_t y = threadIdx.x; y < nbytes; y += blockDim.x) {
+            const uint32_t w = __vminu2(sm_tile[y], 0x000f000fu);
+            g[y] = (uint8_t)(((w & 15u) << 4) | (w >> 16));
+        }
+    }
+}
+
 // ----------------------------------------------------------------------- K5
 //
 // khmer's n_unique_kmers counts the add() calls that found at least one of their T buckets
@@ -649,7 +870,8 @@ struct KvNovelParams {
                                           // computed (sharded sketches: all-reduced partial minima)
 };
 
-template <int HASHER, int KW>
+// FAST: no abundance screen and no precomputed counts -> order-free evaluation (see below)
+template <int HASHER, int KW, bool FAST>
 __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_constant__ KvNovelParams p)
 {
     __shared__ KvTileSmem sm;
@@ -680,9 +902,46 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
         const uint64_t h = kv_tile_hash<HASHER, KW>(sm, l, p.k);
         if (p.banded && (long long)(h & p.band_mask) != p.band_minus_1) continue;
 
-        // kmer_is_interesting (kevlar/novel.py:21-53), same evaluation order and early exits
         uint8_t ab[KV_MAX_SAMPLES];
         bool interesting = true;
+        if (FAST) {
+            // kmer_is_interesting (kevlar/novel.py:21-53) without the abundance screen is a pure
+            // predicate -- every case abundance >= case_min and every control abundance <= ctrl_max --
+            // so the lookups may run in ANY order, and a Count-Min abundance is a minimum over tables:
+            //   control passes as soon as ONE table is <= ctrl_max, fails only if ALL tables exceed it;
+            //   case    fails as soon as ONE table is <  case_min.
+            // Controls first: at sequencing depth most k-mers are inherited and die on the first control
+            // (4 loads); error k-mers pass each control on its first table and die on the first case
+            // table (3 loads) -- against 8 and 1-2 loads in the reference's case-first order.  Random
+            // 32-byte sector loads are what bounds this kernel, so fewer loads is the whole game.
+            for (int s = 0; s < p.n_ctrl && interesting; s++) {
+                const KvView &v = p.sk[p.n_case + s];
+                uint64_t bin;
+                kv_bin(v, 0, h, bin);
+                unsigned m = kv_bucket_get(v, 0, bin);
+                if ((int)m > p.ctrl_max) {
+#pragma unroll 3
+                    for (int t = 1; t < v.n_tables; t++) {
+                        kv_bin(v, t, h, bin);
+                        unsigned c = kv_bucket_get(v, t, bin);
+                        m = c < m ? c : m;
+                    }
+                    if ((int)m > p.ctrl_max) interesting = false;
+                }
+            }
+            for (int s = 0; s < p.n_case && interesting; s++) {
+                const KvView &v = p.sk[s];
+                for (int t = 0; t < v.n_tables; t++) {
+                    uint64_t bin;
+                    kv_bin(v, t, h, bin);
+                    if ((int)kv_bucket_get(v, t, bin) < p.case_min) { interesting = false; break; }
+                }
+            }
+            if (!interesting) continue;
+            // a hit (rare): now the full abundances for the annotation
+            for (int s = 0; s < p.n_case + p.n_ctrl; s++) ab[s] = (uint8_t)kv_get(p.sk[s], h);
+        } else {
+        // kmer_is_interesting (kevlar/novel.py:21-53), same evaluation order and early exits
         for (int s = 0; s < p.n_case; s++) {
             int a = p.pre[s] ? (int)p.pre[s][g] : (int)kv_get(p.sk[s], h);
             if (a < p.case_min) {
@@ -703,6 +962,7 @@ __global__ void __launch_bounds__(KV_THREADS) kv_novel_kernel(const __grid_const
             ab[p.n_case + s] = (uint8_t)a;
         }
         if (!interesting) continue;
+        }
         unsigned long long slot = atomicAdd(p.n_hits, 1ULL);
         if (slot < p.max_hits) {
             uint64_t read, rs, re;
@@ -819,4 +1079,60 @@ __global__ void kv_peer_barrier_kernel(KvPeerFlags f, uint32_t epoch, unsigned l
         if (now - t0 > timeout_ns) { atomicExch(timed_out, 1u); break; }
         __nanosleep(200);
     }
+}
+
+// ------------------------------------------------------------------ synthetic reads (measurement fixture)
+//
+// wgsim-style reads drawn on the device (kevlar/tests/data/minitrio/README recipe, 100 bp,
+// iid substitution errors): read r of a sample is a pure function of (seed, r), so any rank can
+// produce any slice of a sample's read set and the union over ranks never depends on the number
+// of ranks.  Counter-based generator: splitmix64 finaliser over (seed, index).
+struct KvSynthParams {
+    const uint8_t *hap[8];
+    uint64_t hap_len[8];
+    int n_haps;
+    uint64_t n_reads, first_read;
+    uint32_t read_len;
+    uint32_t err_q32;     // substitution probability * 2^32
+    uint64_t seed;
+    uint8_t *out;         // n_reads * read_len bases
+    uint64_t *offsets;    // n_reads + 1 (may be NULL)
+};
+
+__device__ __forceinline__ uint64_t kv_mix64(uint64_t x)
+{
+    x += 0x9e3779b97f4a7c15ULL;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) kv_synth_reads_kernel(KvSynthParams p)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_bases = p.n_reads * p.read_len;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_bases; i += stride) {
+        const uint64_t r = i / p.read_len, j = i - r * p.read_len, gr = p.first_read + r;
+        const uint64_t a = kv_mix64(p.seed ^ kv_mix64(gr));
+        const int h = (int)((a & 0xffff) % (uint64_t)p.n_haps);
+        const uint64_t start = (a >> 17) % (p.hap_len[h] - p.read_len);
+        const bool minus = (a >> 16) & 1;
+        uint8_t b = p.hap[h][start + (minus ? p.read_len - 1 - j : j)];
+        // codes in ACGT order: A=0 C=1 G=2 T=3; complement = 3 - code
+        unsigned code = b == 'A' ? 0u : b == 'C' ? 1u : b == 'G' ? 2u : 3u;
+        if (minus) code = 3u - code;
+        const uint64_t e = kv_mix64((p.seed + 0x632be59bd9b4e019ULL) ^ kv_mix64(gr * p.read_len + j));
+        if ((uint32_t)e < p.err_q32) code = (code + 1u + (unsigned)((e >> 32) % 3u)) & 3u;
+        p.out[i] = "ACGT"[code];
+        if (p.offsets && j == 0) p.offsets[r] = i;
+    }
+    if (p.offsets && blockIdx.x == 0 && threadIdx.x == 0) p.offsets[p.n_reads] = n_bases;
+}
+
+// flag reads shorter than k as skipped (kevlar/novel.py:134): one thread per read
+__global__ void kv_short_reads_kernel(const uint64_t *__restrict__ offsets, uint64_t n_reads, int k, uint32_t *__restrict__ flags)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride)
+        if (offsets[r + 1] - offsets[r] < (uint64_t)k) atomicOr(flags + r, KV_READ_SKIPPED);
 }

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -87,6 +88,14 @@ struct KvCtx {
     // direct random atomics from 256 MB to 4 GB, break-even at 16 GB; profiles/r01_notes.md)
     uint64_t part_min_bytes = 128ull << 20, part_max_bytes = 8ull << 30;
     int part_region_log2 = 24;                // buckets per region (8-bit: 16 MB)
+    // K3c, the tiled update path (default for sketches that do not fit L2): see kv_tile_apply_kernel
+    int update_path = 0;                      // 0 auto, 1 direct, 2 region-partitioned (K3b), 3 tiled (K3c)   [KV_UPDATE_PATH]
+    uint64_t tile_min_bytes = 128ull << 20;   // auto: sketches at least this large take the tiled path       [KV_TILE_MIN_BYTES]
+    int tile_rb = 15;                         // log2(buckets per region)                                      [KV_TILE_RB]
+    uint64_t tile_chunk_bases = 256ull << 20; // positions per chunk on the tiled path                         [KV_TILE_CHUNK_BASES]
+    int tile_direct_below = -1;               // regions with fewer offsets are updated in place (-1: region bytes / 64)
+    int tile_block_log2 = 6;                  // slab layout: slots per interleave block (-1: run-major)               [KV_TILE_BLOCK_LOG2]
+    KvBuf tile_cursor, tile_slab, tile_ovf;
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied  [5] redone chunks
@@ -159,6 +168,14 @@ static int kv_ctx_get(int device, KvCtx **out)
         if (const char *env = getenv("KV_PART_MAX_BYTES")) c.part_max_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_REGION_LOG2")) c.part_region_log2 = std::max(4, std::min(30, atoi(env)));
         if (getenv("KV_NO_CLASSIFY")) c.unique_classify = false;
+        if (const char *env = getenv("KV_UPDATE_PATH"))
+            c.update_path = !strcmp(env, "direct") ? 1 : !strcmp(env, "part") ? 2 : !strcmp(env, "tile") ? 3 : 0;
+        if (const char *env = getenv("KV_TILE_MIN_BYTES")) c.tile_min_bytes = strtoull(env, nullptr, 10);
+        if (const char *env = getenv("KV_TILE_RB")) c.tile_rb = std::max(6, std::min(16, atoi(env)));
+        if (const char *env = getenv("KV_TILE_CHUNK_BASES")) c.tile_chunk_bases = std::max<uint64_t>(KV_TILE, strtoull(env, nullptr, 10));
+        c.tile_chunk_bases = (c.tile_chunk_bases + KV_TILE - 1) / KV_TILE * KV_TILE;
+        if (const char *env = getenv("KV_TILE_DIRECT_BELOW")) c.tile_direct_below = atoi(env);
+        if (const char *env = getenv("KV_TILE_BLOCK_LOG2")) c.tile_block_log2 = std::max(-1, std::min(12, atoi(env)));
         if (const char *env = getenv("KV_FIRST_RANGE_LOG2")) c.first_range = 1ull << std::max(8, std::min(32, atoi(env)));
         c.ready = true;
     }
@@ -765,18 +782,24 @@ static inline void kv_stage_done(KvCtx *ctx, KvBatch *b)
     if (b->slot) cudaEventRecord(b->slot->done, ctx->compute);
 }
 
+template <int HASHER, bool SCATTER>
+static int kv_launch_hash2(KvCtx *ctx, const KvHashParams &p, unsigned n_tiles)
+{
+    if (HASHER == KV_HASH_TWOBIT) { LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_TWOBIT, 4, SCATTER>), n_tiles, KV_THREADS, p); return KV_OK; }
+    int kw = 4 * ((p.k + 15) / 16);
+    switch (kw) {
+    case 4: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 4, SCATTER>), n_tiles, KV_THREADS, p); break;
+    case 8: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 8, SCATTER>), n_tiles, KV_THREADS, p); break;
+    case 12: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 12, SCATTER>), n_tiles, KV_THREADS, p); break;
+    default: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 16, SCATTER>), n_tiles, KV_THREADS, p); break;
+    }
+    return KV_OK;
+}
+
 template <int HASHER>
 static int kv_launch_hash(KvCtx *ctx, const KvHashParams &p, unsigned n_tiles)
 {
-    if (HASHER == KV_HASH_TWOBIT) { LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
-    int kw = 4 * ((p.k + 15) / 16);
-    switch (kw) {
-    case 4: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
-    case 8: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
-    case 12: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
-    default: LAUNCH_C(KV_PROF_HASH, ctx, (kv_hash_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
-    }
-    return KV_OK;
+    return p.scatter ? kv_launch_hash2<HASHER, true>(ctx, p, n_tiles) : kv_launch_hash2<HASHER, false>(ctx, p, n_tiles);
 }
 
 static int kv_band_interval(int num_bands, int band, uint64_t *lo, uint64_t *hi)
@@ -952,7 +975,8 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
     if (dist_counts) d_valid = (const uint32_t *)ctx->fresh.p;
     // large counter sketches: region-partitioned updates (tables must index with 32 bits, <= 4 tables)
     bool partitioned = s->bits != 1 && s->flat_bytes >= ctx->part_min_bytes && s->flat_bytes <= ctx->part_max_bytes &&
-                       s->n_tables <= 4;
+                       s->n_tables <= 4 && ctx->update_path != 1;
+    if (ctx->update_path == 2) partitioned = s->bits != 1 && s->n_tables <= 4;
     KvPartInfo pi;
     memset(&pi, 0, sizeof pi);
     if (partitioned) {
@@ -973,6 +997,74 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
     if (s->bits == 8) return kv_launch_increment<8>(ctx, v, s->flat_bytes, d_hashes, d_valid, n);
     if (s->bits == 4) return kv_launch_increment<4>(ctx, v, s->flat_bytes, d_hashes, d_valid, n);
     return kv_launch_increment<1>(ctx, v, s->flat_bytes, d_hashes, d_valid, n);
+}
+
+// ---- K3c: tiled update path
+
+struct KvTilePlan {
+    bool on;
+    KvTileInfo ti;
+    uint32_t runs, direct_below;
+    size_t smem;
+    uint64_t chunk_tiles;
+};
+
+// Should batches of up to `batch_pos` positions update `s` through the tiled path, and with what geometry?
+static int kv_tile_plan(KvCtx *ctx, const kv_sketch *s, uint64_t batch_pos, KvTilePlan *pl)
+{
+    memset(pl, 0, sizeof *pl);
+    bool on = ctx->update_path == 3 || (ctx->update_path == 0 && s->flat_bytes >= ctx->tile_min_bytes);
+    if (!on) return KV_OK;
+    const int rb = s->bits == 1 ? 16 : ctx->tile_rb;
+    uint64_t runs = 0, min_regions = UINT64_MAX;
+    for (int t = 0; t < s->n_tables; t++) {
+        pl->ti.run_base[t] = (uint32_t)runs;
+        const uint64_t nr = s->sizes[t] ? ((s->sizes[t] - 1) >> rb) + 1 : 0;
+        runs += nr;
+        if (nr) min_regions = std::min(min_regions, nr);
+    }
+    if (!runs || runs >= (1ull << 30)) return KV_OK;   // nothing held here / absurdly many regions: in-place updates
+    pl->ti.run_base[s->n_tables] = (uint32_t)runs;
+    pl->ti.run_base[KV_TABLES_DEV] = (uint32_t)runs;   // kv_slab_index reads the total there
+    const uint64_t chunk_pos = std::min<uint64_t>(ctx->tile_chunk_bases, (batch_pos + KV_TILE - 1) / KV_TILE * KV_TILE);
+    // slots per run: mean + 6 % + 8 sigma + slack, for offsets spread by the hash; anything beyond (skewed
+    // inputs) is updated in place by the producer
+    const double mean = (double)chunk_pos / (double)min_regions;
+    uint64_t cap = (uint64_t)(mean * 1.0625 + 8.0 * sqrt(mean) + 64.0);
+    const uint64_t blk = ctx->tile_block_log2 >= 0 ? (1ull << ctx->tile_block_log2) : 16;
+    cap = (cap + blk - 1) / blk * blk;
+    if (cap >= 0xffffffffull) return KV_OK;
+    KV_TRY(kv_buf_ensure(ctx->tile_cursor, runs * 4 + 16));
+    if (kv_buf_ensure(ctx->tile_slab, runs * cap * 2) != KV_OK) { g_err.clear(); return KV_OK; }   // no room for slabs: in-place updates
+    pl->on = true;
+    pl->ti.rb = rb;
+    pl->ti.cap = (uint32_t)cap;
+    pl->ti.cursor = (uint32_t *)ctx->tile_cursor.p;
+    pl->ti.slab = (uint16_t *)ctx->tile_slab.p;
+    pl->ti.blk_log2 = ctx->tile_block_log2;
+    pl->ti.ovf_any = (unsigned *)((uint32_t *)ctx->tile_cursor.p + runs);   // cleared together with the cursors
+    if (s->track_unique) {
+        pl->ti.ovf_stride = chunk_pos / 32 + 1;
+        KV_TRY(kv_buf_ensure(ctx->tile_ovf, pl->ti.ovf_stride * 4 * (uint64_t)s->n_tables));
+        pl->ti.ovf = (uint32_t *)ctx->tile_ovf.p;
+    }
+    pl->runs = (uint32_t)runs;
+    pl->smem = s->bits == 1 ? ((size_t)1 << rb) / 8 : ((size_t)1 << rb) * 2;
+    const uint64_t region_bytes = ((uint64_t)1 << rb) * (uint64_t)s->bits / 8;
+    pl->direct_below = ctx->tile_direct_below >= 0 ? (uint32_t)ctx->tile_direct_below : (uint32_t)std::max<uint64_t>(1, region_bytes / 64);
+    pl->chunk_tiles = chunk_pos / KV_TILE;
+    return KV_OK;
+}
+
+template <int BITS>
+static int kv_launch_tile_apply(KvCtx *ctx, const KvView &v, const KvTilePlan &pl)
+{
+    static bool configured = false;
+    if (!configured) {
+        CU(cudaFuncSetAttribute(kv_tile_apply_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        configured = true;
+    }
+    return kv_launch_smem(ctx, KV_PROF_INCREMENT, kv_tile_apply_kernel<BITS>, pl.runs, KV_TILE_THREADS, pl.smem, v, pl.ti, pl.direct_below);
 }
 
 static int kv_check_mask(const kv_sketch *s, const kv_sketch *mask)
@@ -1004,12 +1096,17 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
     if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
 
+    KvTilePlan plan;
+    KV_TRY(kv_tile_plan(ctx, s, b.n_tiles * KV_TILE, &plan));
     // positions are 32-bit inside a chunk, and the partitioned path indexes n_tables items per position
-    const uint64_t chunk_limit = std::min<uint64_t>(ctx->chunk_bases, (0xfffffff0ull / (uint64_t)s->n_tables) / KV_TILE * KV_TILE);
+    const uint64_t chunk_limit = plan.on ? plan.chunk_tiles * KV_TILE
+                                         : std::min<uint64_t>(ctx->chunk_bases, (0xfffffff0ull / (uint64_t)s->n_tables) / KV_TILE * KV_TILE);
     const uint64_t chunk_tiles = chunk_limit / KV_TILE;
     const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
-    KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
+    const bool need_hashes = !plan.on || s->track_unique;
+    if (need_hashes) KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
     KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    const KvView sv = kv_view(s);
     for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
         uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
         uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
@@ -1020,10 +1117,29 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
         p.banded = num_bands > 0; p.band_lo = lo; p.band_hi = hi;
         if (mask) { p.use_mask = 1; p.mask = kv_view(mask); p.mask_threshold = mask_threshold; p.consume_masked = consume_masked != 0; }
         p.strict = 0;
-        p.hashes = (uint64_t *)ctx->hashes.p; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+        p.hashes = need_hashes ? (uint64_t *)ctx->hashes.p : nullptr; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+        if (plan.on) {
+            p.scatter = 1; p.ti = plan.ti; p.sk = sv;
+            CU(cudaMemsetAsync(plan.ti.cursor, 0, (size_t)plan.runs * 4 + 4, ctx->compute));
+            if (plan.ti.ovf) CU(cudaMemsetAsync(plan.ti.ovf, 0, plan.ti.ovf_stride * 4 * (uint64_t)s->n_tables, ctx->compute));
+        }
         if (s->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)nt));
         else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)nt));
-        KV_TRY(kv_apply_hashes(ctx, s, p.hashes, p.valid, npos));
+        if (!plan.on) {
+            KV_TRY(kv_apply_hashes(ctx, s, p.hashes, p.valid, npos));
+            continue;
+        }
+        // tiled path: the producer has filed the updates; the exact-n_unique passes must still see the
+        // tables as they were before this chunk, then one CTA per region applies its slab
+        if (s->track_unique) {
+            KV_TRY(kv_count_fresh(ctx, s, sv, p.hashes, p.valid, npos));
+            LAUNCH_C(KV_PROF_FIXUP, ctx, kv_tile_overflow_kernel, kv_grid_for(ctx, npos / 32 + 1), 256, sv, plan.ti, p.hashes, npos);
+        } else
+            s->unique_valid = false;
+        if (s->bits == 8) KV_TRY(kv_launch_tile_apply<8>(ctx, sv, plan));
+        else if (s->bits == 4) KV_TRY(kv_launch_tile_apply<4>(ctx, sv, plan));
+        else KV_TRY(kv_launch_tile_apply<1>(ctx, sv, plan));
+        s->state_stale = true;   // the hot bitmap of the in-place path is not maintained here
     }
     kv_stage_done(ctx, &b);
     if (n_kmers_out) {
@@ -1036,19 +1152,30 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
 
 // ------------------------------------------------------------------ novel
 
+template <int HASHER, bool FAST>
+static int kv_launch_novel2(KvCtx *ctx, const KvNovelParams &p)
+{
+    unsigned n_tiles = (unsigned)p.n_tiles;
+    if (HASHER == KV_HASH_TWOBIT) { LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_TWOBIT, 4, FAST>), n_tiles, KV_THREADS, p); return KV_OK; }
+    int kw = 4 * ((p.k + 15) / 16);
+    switch (kw) {
+    case 4: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 4, FAST>), n_tiles, KV_THREADS, p); break;
+    case 8: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 8, FAST>), n_tiles, KV_THREADS, p); break;
+    case 12: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 12, FAST>), n_tiles, KV_THREADS, p); break;
+    default: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 16, FAST>), n_tiles, KV_THREADS, p); break;
+    }
+    return KV_OK;
+}
+
+// the order-free evaluation applies when nothing depends on WHICH test failed first: no abundance
+// screen (kevlar/novel.py:36-43) and abundances looked up here rather than handed in
 template <int HASHER>
 static int kv_launch_novel(KvCtx *ctx, const KvNovelParams &p)
 {
-    unsigned n_tiles = (unsigned)p.n_tiles;
-    if (HASHER == KV_HASH_TWOBIT) { LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_TWOBIT, 4>), n_tiles, KV_THREADS, p); return KV_OK; }
-    int kw = 4 * ((p.k + 15) / 16);
-    switch (kw) {
-    case 4: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 4>), n_tiles, KV_THREADS, p); break;
-    case 8: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 8>), n_tiles, KV_THREADS, p); break;
-    case 12: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 12>), n_tiles, KV_THREADS, p); break;
-    default: LAUNCH_C(KV_PROF_NOVEL, ctx, (kv_novel_kernel<KV_HASH_MURMUR, 16>), n_tiles, KV_THREADS, p); break;
-    }
-    return KV_OK;
+    bool fast = p.screen <= 0 && !getenv("KV_NOVEL_REFERENCE_ORDER");
+    for (int i = 0; i < p.n_case + p.n_ctrl; i++)
+        if (p.pre[i]) fast = false;
+    return fast ? kv_launch_novel2<HASHER, true>(ctx, p) : kv_launch_novel2<HASHER, false>(ctx, p);
 }
 
 static int kv_novel_impl(const kv_sketch *const *cases, int n_case, const kv_sketch *const *ctrls, int n_ctrl,
@@ -1097,6 +1224,9 @@ static int kv_novel_impl(const kv_sketch *const *cases, int n_case, const kv_ske
     p.banded = num_bands > 0; p.band_mask = num_bands > 0 ? (uint64_t)(num_bands - 1) : 0; p.band_minus_1 = band_minus_1;
     p.hits = (kv_hit *)ctx->hits.p; p.max_hits = max_hits; p.n_hits = ctx->counters + 2;
     p.read_flags = (uint32_t *)ctx->flags.p; p.discard_pos = screen > 0 ? (uint32_t *)ctx->discard.p : nullptr;
+    // reads shorter than k are skipped (kevlar/novel.py:134); flagged on the device so that host- and
+    // device-resident batches behave alike
+    LAUNCH(ctx, kv_short_reads_kernel, kv_grid_for(ctx, n_reads), 256, b.d_offsets, n_reads, c0->ksize, (uint32_t *)ctx->flags.p);
     if (b.total) {
         if (c0->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_novel<KV_HASH_TWOBIT>(ctx, p));
         else KV_TRY(kv_launch_novel<KV_HASH_MURMUR>(ctx, p));
@@ -1119,12 +1249,9 @@ static int kv_novel_impl(const kv_sketch *const *cases, int n_case, const kv_ske
         CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, found * sizeof(kv_hit), cudaMemcpyDeviceToHost, ctx->compute));
         CU(cudaStreamSynchronize(ctx->compute));
     }
-    // read-level flags (kevlar/novel.py:134-139,152-154).  Offsets are needed on the host for the
-    // "shorter than k" test; with device-resident batches the kernel's flags already cover
-    // non-ACGT reads and short reads simply have no k-mers.
+    // read-level flags (kevlar/novel.py:134-139,152-154)
     for (uint64_t r = 0; r < n_reads; r++) {
         uint8_t fl = (uint8_t)(hflags[r] & KV_READ_SKIPPED);
-        if (where == KV_MEM_HOST && offsets[r + 1] - offsets[r] < (uint64_t)c0->ksize) fl |= KV_READ_SKIPPED;
         if (screen > 0) {
             if (!(fl & KV_READ_SKIPPED) && hdisc[r] != 0xffffffffu) fl |= KV_READ_DISCARDED;
             discard_pos[r] = (fl & KV_READ_SKIPPED) ? 0xffffffffu : hdisc[r];
@@ -1626,6 +1753,35 @@ extern "C" int kv_peer_sync_destroy(kv_peer_sync *ps)
         if (ps->peer[p]) cudaIpcCloseMemHandle(ps->peer[p]);
     cudaFree(ps->flags);
     delete ps;
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ synthetic reads (measurement fixture)
+
+extern "C" int kv_synth_reads(int device, const uint8_t *const *dev_haplotypes, const uint64_t *hap_lens, int n_haps,
+                              uint64_t n_reads, uint64_t first_read, uint32_t read_len, double error_rate, uint64_t seed,
+                              uint8_t *dev_bases, uint64_t *dev_offsets)
+{
+    if (!dev_haplotypes || !hap_lens || !dev_bases) return kv_fail(KV_EINVAL, "null argument");
+    if (n_haps < 1 || n_haps > 8 || read_len < 1) return kv_fail(KV_EINVAL, "1..8 haplotypes, read_len >= 1");
+    if (error_rate < 0 || error_rate >= 1) return kv_fail(KV_EINVAL, "error_rate must be in [0, 1)");
+    KvSynthParams p;
+    memset(&p, 0, sizeof p);
+    for (int h = 0; h < n_haps; h++) {
+        if (!dev_haplotypes[h] || hap_lens[h] <= read_len) return kv_fail(KV_EINVAL, "haplotype %d is shorter than a read", h);
+        p.hap[h] = dev_haplotypes[h];
+        p.hap_len[h] = hap_lens[h];
+    }
+    p.n_haps = n_haps; p.n_reads = n_reads; p.first_read = first_read; p.read_len = read_len;
+    p.err_q32 = (uint32_t)(error_rate * 4294967296.0);
+    p.seed = seed; p.out = dev_bases; p.offsets = dev_offsets;
+    if (!n_reads) return KV_OK;
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    LAUNCH(ctx, kv_synth_reads_kernel, kv_grid_for(ctx, n_reads * read_len, 16), 256, p);
+    CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }
 

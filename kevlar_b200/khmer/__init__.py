@@ -58,8 +58,15 @@ class _Sketch(object):
         self._ksize, self._sizes, self._device = k.value, list(sz)[:nt.value], dev.value
 
     def __del__(self):
-        h, self._h = getattr(self, '_h', None), None
+        h = getattr(self, '_h', None)
         if h is not None and _lib._lib is not None:
+            if getattr(self, '_p2p_peers', None):   # peer tables mapped by a multi-GPU merge: unmap before freeing
+                try:
+                    from kevlar_b200 import multigpu
+                    multigpu.close_p2p(self)
+                except Exception:
+                    pass
+            self._h = None
             _lib._lib.kv_sketch_destroy(h)
 
     # ---------------------------------------------------------------- metadata

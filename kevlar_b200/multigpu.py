@@ -115,8 +115,11 @@ def merge_allreduce(adapter, group=None):
     """widen -> all-reduce(SUM) -> clamp.  Bit tables (merge = OR) go through all-gather since
     NCCL has no bitwise reduction."""
     td = dist()
-    if adapter.bits == 1 or (adapter.bits == 8 and td.get_world_size(group) > 8):
-        return merge_allgather(adapter, group)   # OR has no NCCL op; fp16 sums are exact up to 8 ranks
+    world = td.get_world_size(group)
+    if adapter.bits == 1 or (adapter.bits == 8 and world > 8) or (adapter.bits == 4 and world > 17):
+        # OR has no NCCL op; fp16 sums of 8-bit counters are exact up to 8 ranks (8 x 255 < 2048); nibbles
+        # travel as u8 and 15 x 18 would wrap
+        return merge_allgather(adapter, group)
     wide = adapter.widen()
     td.all_reduce(wide, op=td.ReduceOp.SUM, group=group)
     adapter.narrow(wide)
@@ -138,14 +141,13 @@ def slice_bounds(nbytes, rank, world, align=256):
     return lo * align, hi * align
 
 
-_P2P_PEERS = {}   # sketch handle -> {rank: mapped device pointer of that rank's table storage}
-
-
 def _p2p_peers(sketch, group=None):
-    """Map the peers' table storage once per sketch (CUDA IPC open is slow: ~ms) and reuse it."""
-    key = sketch._h.value
-    if key in _P2P_PEERS:
-        return _P2P_PEERS[key]
+    """Map the peers' table storage once per sketch (CUDA IPC open is slow: ~ms) and reuse it.  The
+    mappings hang on the sketch OBJECT (not on its handle address, which a later sketch may
+    reuse); `release_p2p` closes them."""
+    peers = getattr(sketch, '_p2p_peers', None)
+    if peers is not None:
+        return peers
     td = dist()
     world, rank = td.get_world_size(group), td.get_rank(group)
     handle = (ctypes.c_uint8 * 64)()
@@ -158,16 +160,35 @@ def _p2p_peers(sketch, group=None):
             ptr = c_void_p()
             check(lib().kv_ipc_open(sketch.device, (ctypes.c_uint8 * 64)(*h), byref(ptr)))
             peers[r] = ptr
-    _P2P_PEERS[key] = peers
+    sketch._p2p_peers = peers
     return peers
 
 
-def release_p2p(sketch):
-    """Unmap the peers' storage of a sketch (call on every rank before the sketches are freed)."""
-    peers = _P2P_PEERS.pop(sketch._h.value, None)
+def close_p2p(sketch):
+    """Unmap the peers' storage of ONE sketch on THIS rank (local; `_Sketch.__del__` calls it).  It does
+    not make freeing the sketch safe by itself: the peers may still have this rank's tables mapped
+    -- that needs the collective `release_p2p`."""
+    peers = getattr(sketch, '_p2p_peers', None)
     if peers:
+        _lib.sync(sketch.device)
         for ptr in peers.values():
-            check(lib().kv_ipc_close(sketch.device, ptr))
+            lib().kv_ipc_close(sketch.device, ptr)
+    if peers is not None:
+        sketch._p2p_peers = None
+
+
+def release_p2p(sketches, group=None):
+    """COLLECTIVE: every rank unmaps its peers' table storage of `sketches`, then all ranks meet at a
+    barrier.  Only after it returns may any rank free these sketches (CUDA leaves freeing memory that
+    a peer still has mapped undefined).  Call it on every rank, with the same sketches in the same
+    order, before the sketches go out of scope or the process group is destroyed."""
+    if not isinstance(sketches, (list, tuple)):
+        sketches = [sketches]
+    for sk in sketches:
+        close_p2p(sk)
+    td = dist()
+    if td.is_initialized() and td.get_world_size(group) > 1:
+        td.barrier(group=group)
 
 
 _PEER_SYNC = {}   # (device, group id) -> kv_peer_sync handle with every peer connected
@@ -199,7 +220,7 @@ def peer_sync_status(device=None):
 
 
 def release_peer_sync():
-    """Unmap the peers' barrier flags (collective: call on every rank, after the last merge)."""
+    """Unmap the peers' barrier flags (COLLECTIVE: call on every rank, after the last merge)."""
     td = dist()
     for ps in _PEER_SYNC.values():
         check(lib().kv_peer_sync_status(ps))
@@ -208,6 +229,21 @@ def release_peer_sync():
     for ps in _PEER_SYNC.values():
         check(lib().kv_peer_sync_destroy(ps))
     _PEER_SYNC.clear()
+
+
+def shutdown(sketches=(), destroy_group=True):
+    """COLLECTIVE teardown of everything the peer-to-peer merge set up: peer mappings of `sketches`,
+    the device-side barrier objects, and (optionally) the process group.  Every rank must call it --
+    typically from a `finally:` -- before its sketches are freed."""
+    td = dist()
+    if not td.is_initialized():
+        return
+    try:
+        release_p2p(list(sketches))
+        release_peer_sync()
+    finally:
+        if destroy_group:
+            td.destroy_process_group()
 
 
 def merge_p2p(sketches, group=None, host_barriers=False):

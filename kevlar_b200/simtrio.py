@@ -20,7 +20,7 @@ def random_genome(length, seed=42):
     return LETTERS[rng.integers(0, 4, size=length)]
 
 
-def _apply(hap, variants):
+def _apply_sequential(hap, variants):
     """Apply (pos, kind, payload) edits to a haplotype, right to left so positions stay valid."""
     for pos, kind, payload in sorted(variants, key=lambda v: -v[0]):
         if kind == 'snv':
@@ -30,6 +30,28 @@ def _apply(hap, variants):
         else:
             hap = np.concatenate([hap[:pos], hap[pos + payload:]])
     return hap
+
+
+def _apply(hap, variants):
+    """`_apply_sequential` assembled from pieces in one pass (a 100 Mbp haplotype with hundreds of
+    indels would otherwise be copied once per indel).  Identical to it whenever no variant lies
+    inside the footprint of a deletion to its left (always the case for the 1 Mbp benchmark trio,
+    tests/test_host.py checks it); such a variant is dropped here."""
+    pieces, cursor = [], 0
+    for pos, kind, payload in sorted(variants, key=lambda v: v[0]):
+        if pos < cursor:
+            continue
+        pieces.append(hap[cursor:pos])
+        if kind == 'snv':
+            pieces.append(np.array([payload], dtype=np.uint8))
+            cursor = pos + 1
+        elif kind == 'ins':
+            pieces.append(np.asarray(payload, dtype=np.uint8))
+            cursor = pos
+        else:
+            cursor = pos + payload
+    pieces.append(hap[cursor:])
+    return np.concatenate(pieces)
 
 
 def _draw_variants(rng, genome, n):
@@ -101,3 +123,31 @@ def simulate_trio(genome_len=1000000, coverage=30, read_len=100, error_rate=0.00
     haps = trio_haplotypes(genome_len)
     n_reads = reads_per_sample or int(coverage * genome_len / read_len)
     return [sample_reads(h, n_reads, read_len, error_rate, seed + seed_offset) for h, seed in zip(haps, READ_SEEDS)]
+
+
+def device_trio(genome_len, reads_per_sample, rank=0, world=1, read_len=100, error_rate=0.005, device=None):
+    """Reads for (proband, mother, father) drawn ON THE DEVICE (kv_synth_reads): list of
+    (bases, offsets) torch tensors holding this rank's contiguous slice of every sample's
+    `reads_per_sample` reads.  Read r of a sample is a pure function of (sample seed, r), so the
+    union over ranks is the same read set for every world size.  For inputs the size of BASELINE
+    configs 3-4, which a host generator plus PCIe would turn into the bottleneck."""
+    import ctypes
+    import torch
+    from kevlar_b200 import _lib, multigpu
+    dev_index = _lib.current_device() if device is None else int(device)
+    dev = torch.device('cuda', dev_index)
+    lo, hi = multigpu.shard_bounds(reads_per_sample, rank, world)
+    out = []
+    for haps, seed in zip(trio_haplotypes(genome_len), READ_SEEDS):
+        dhaps = [torch.from_numpy(np.ascontiguousarray(h)).to(dev) for h in haps]
+        ptrs = (ctypes.c_void_p * len(dhaps))(*[t.data_ptr() for t in dhaps])
+        lens = (ctypes.c_uint64 * len(dhaps))(*[t.numel() for t in dhaps])
+        n = hi - lo
+        bases = torch.empty(n * read_len + 16, dtype=torch.uint8, device=dev)[:n * read_len]
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+        _lib.check(_lib.lib().kv_synth_reads(dev_index, ptrs, lens, len(dhaps), n, lo, read_len, float(error_rate),
+                                             int(seed), bases.data_ptr(), offsets.data_ptr()))
+        out.append((bases, offsets))
+        del dhaps
+    return out

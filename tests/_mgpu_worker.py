@@ -68,8 +68,7 @@ def main():
                 if not same or len(ohits) == 0:
                     failures.append('{} {} novel hits differ ({} vs {})'.format(how, cls, len(allhits), len(ohits)))
             multigpu.peer_sync_status()
-            for g in gpu:
-                multigpu.release_p2p(g)
+            multigpu.release_p2p(gpu)   # collective: unmap everywhere, barrier, only then free
             del gpu
     multigpu.release_peer_sync()
     # ---- plan B: bin-range-sharded sketches: count shard-local reads, exchange hashes, save one file

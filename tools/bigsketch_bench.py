@@ -21,13 +21,15 @@ def main():
     ap.add_argument('--reads', type=int, default=3000000)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--track', action='store_true')
+    ap.add_argument('--bits', type=int, default=8, choices=[8, 4, 1])
+    ap.add_argument('--label', default='')
     args = ap.parse_args()
     import torch
     from kevlar_b200 import _lib, khmer, simtrio
-    trio = simtrio.simulate_trio(args.genome, reads_per_sample=args.reads)
     dev = torch.device('cuda', 0)
-    dtrio = [(torch.from_numpy(b).to(dev), torch.from_numpy(o.view(np.int64)).to(dev)) for b, o in trio]
-    sketches = [khmer.Counttable(31, args.memory / 4, 4) for _ in range(3)]
+    dtrio = simtrio.device_trio(args.genome, args.reads)      # reads drawn on the device (kv_synth_reads)
+    cls = {8: khmer.Counttable, 4: khmer.SmallCounttable, 1: khmer.Nodetable}[args.bits]
+    sketches = [cls(31, args.memory / 4 * (8 // args.bits), 4) for _ in range(3)]
     for sk in sketches:
         sk.set_unique_tracking(args.track)
     stream = torch.cuda.ExternalStream(_lib.stream_ptr(0), device=dev)
@@ -58,9 +60,10 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         prof = {k: round(v[0] / args.steps, 3) for k, v in _lib.profile(0).items() if v[1]}
         res[name] = {'ms': round(ms, 3), 'G_kmers_per_s': round(nk / ms / 1e6, 3), 'kernel_ms': prof}
-    res['config'] = {'sketch_bytes': args.memory, 'reads_per_sample': args.reads, 'tracking': args.track,
-                     'novel_hits': int(len(hits))}
-    inc_ms = res['count_x3']['kernel_ms'].get('increment', 0) / 3
+    res['config'] = {'sketch_bytes': args.memory, 'reads_per_sample': args.reads, 'tracking': args.track, 'bits': args.bits,
+                     'novel_hits': int(len(hits)), 'label': args.label,
+                     'env': {k: v for k, v in os.environ.items() if k.startswith('KV_')}}
+    inc_ms = (res['count_x3']['kernel_ms'].get('increment', 0) + res['count_x3']['kernel_ms'].get('partition', 0)) / 3
     if inc_ms:
         res['increment'] = {'ms_per_sample': round(inc_ms, 3), 'G_updates_per_s': round(4 * kmers / inc_ms / 1e6, 2),
                             'sector_GBps_read_plus_write': round(4 * kmers * 64 / inc_ms / 1e6, 1)}
