@@ -113,7 +113,9 @@ def kmers_per_step(trio):
 # ----------------------------------------------------------------------------- clocks
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a
+    thread (a 10-step timed region lasts ~80 ms, too short for `nvidia-smi -lms`), nvidia-smi as the
+    fallback when the NVML binding is missing."""
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -122,8 +124,30 @@ class ClockSampler(object):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []
+        self.stop_flag = False
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        if vis:
+            try:
+                return int(vis.split(',')[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -133,11 +157,43 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            try:
+                smax = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            except Exception:
+                smax = None
+            if not self.samples:
+                return {'sm_mhz': None, 'sm_max_mhz': smax, 'reasons': ['no samples']}
+            names = (('hw_slowdown', 'nvmlClocksThrottleReasonHwSlowdown'),
+                     ('hw_thermal_slowdown', 'nvmlClocksThrottleReasonHwThermalSlowdown'),
+                     ('sw_thermal_slowdown', 'nvmlClocksThrottleReasonSwThermalSlowdown'),
+                     ('sw_power_cap', 'nvmlClocksThrottleReasonSwPowerCap'))
+            reasons = set()
+            for _, bits in self.samples:
+                for label, const in names:
+                    if bits & getattr(nv, const, 0):
+                        reasons.add(label)
+            return {'sm_mhz': float(np.median([s for s, _ in self.samples])), 'sm_max_mhz': smax,
+                    'samples': len(self.samples), 'reasons': sorted(reasons), 'source': 'NVML, 2 ms poll during the timed region'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)

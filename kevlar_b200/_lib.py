@@ -32,7 +32,7 @@ HIT_DTYPE = np.dtype([('read', '<u4'), ('offset', '<u4'), ('abund', 'u1', (MAX_S
 assert HIT_DTYPE.itemsize == 24
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, 'libkvsketch.so')
+LIBPATH = os.environ.get('KV_LIB_PATH') or os.path.join(_HERE, 'libkvsketch.so')   # KV_LIB_PATH: experiment builds
 
 # every symbol include/kvsketch.h declares: (name, restype, argtypes)
 _P = c_void_p

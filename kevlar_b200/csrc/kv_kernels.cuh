@@ -130,11 +130,18 @@ struct KvHashParams {
     // (table, region) run, as a 16-bit bucket offset inside the region
     int scatter;
     KvTileInfo ti;
-    KvView sk;
+    KvView sk;             // the sketch being updated (scatter and/or track0)
+    // K5, pass A of table 0 fused in: first0[bin0] = min(first0[bin0], tag0 | position) where the bucket is empty
+    int track0;
+    uint32_t *first0;
+    uint32_t tag0;
 };
 
+#ifndef KV_SCATTER_MIN_CTAS
+#define KV_SCATTER_MIN_CTAS 1   // resident CTAs per SM the scatter variant is compiled for
+#endif
 template <int HASHER, int KW, bool SCATTER>
-__global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(const __grid_constant__ KvHashParams p)
+__global__ void __launch_bounds__(KV_THREADS, SCATTER ? KV_SCATTER_MIN_CTAS : 1) kv_hash_kernel(const __grid_constant__ KvHashParams p)
 {
     __shared__ KvTileSmem sm;
     __shared__ KvTileList ls;
@@ -170,6 +177,11 @@ __global__ void __launch_bounds__(KV_THREADS) kv_hash_kernel(const __grid_consta
         if (p.hashes) p.hashes[tile_start + l - pos0] = h;
         if (ok) atomicOr(&s_valid[l >> 5], 1u << (l & 31));
         n_ok += ok;
+        if (ok && p.track0) {
+            uint64_t bin0;
+            if (kv_bin(p.sk, 0, h, bin0) && kv_bucket_empty(p.sk, 0, bin0))
+                atomicMin(p.first0 + bin0, p.tag0 | (uint32_t)(tile_start + l - pos0));
+        }
         if (SCATTER && ok) {
             // K3c: one cursor atomic + one 2-byte store per table (kevlar always builds 4 tables; more are
             // handled four at a time)
@@ -318,43 +330,6 @@ __global__ void kv_state_rebuild_kernel(KvView v, int t)
     for (uint64_t bin = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; bin < v.size[t]; bin += stride) {
         unsigned c = BITS == 8 ? v.tab[t][bin] : ((v.tab[t][bin >> 1] >> ((bin & 1) ? 0 : 4)) & 15u);
         if (c >= kv_hot_threshold<BITS>()) kv_mark_hot(v, t, bin);
-    }
-}
-
-// Occupancy bitmap of table t from its counters: one thread per 32 buckets, 16-byte loads.
-template <int BITS>
-__global__ void __launch_bounds__(256) kv_occ_rebuild_kernel(KvView v, int t)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_words = (v.size[t] + 31) / 32;
-    const uint64_t nbytes = BITS == 8 ? v.size[t] : v.size[t] / 2 + 1;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
-        uint32_t word = 0;
-        if (BITS == 8) {
-            const uint64_t b0 = i * 32;
-            if (b0 + 32 <= nbytes) {
-                const uint4 *p = (const uint4 *)(v.tab[t] + b0);
-                uint4 a = __ldcs(p), c = __ldcs(p + 1);
-                const uint32_t q[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    uint32_t nz = __vcmpne4(q[j], 0u);   // 0xff per non-zero byte
-                    word |= ((nz & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * j);
-                }
-            } else {
-                for (int j = 0; j < 32 && b0 + j < v.size[t]; j++)
-                    if (v.tab[t][b0 + j]) word |= 1u << j;
-            }
-        } else {
-            // 32 buckets = 16 bytes; even bucket = high nibble
-            const uint64_t y0 = i * 16;
-            for (int j = 0; j < 16 && y0 + j < nbytes; j++) {
-                unsigned byte = v.tab[t][y0 + j];
-                if (byte >> 4) word |= 1u << (2 * j);
-                if ((byte & 15u) && i * 32 + 2 * j + 1 < v.size[t]) word |= 1u << (2 * j + 1);
-            }
-        }
-        v.occ[t][i] = word;
     }
 }
 
@@ -726,97 +701,171 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
 // khmer's n_unique_kmers counts the add() calls that found at least one of their T buckets
 // empty, in single-threaded file order.  That number depends only on the
 // stream of hashes and on which buckets were empty when the batch started -- not on the
-// counter values -- so it is computed per batch, BEFORE the batch's increments, table by table:
-//   occurrence g is new  <=>  for some table t its bucket was empty at batch start (occ bit
-//                             clear) and g is the smallest position of the batch touching it.
-// pass A (per table): first[bin] = min(first[bin], g) for every valid g whose bucket is empty;
-// pass B (per table): every position recorded in first[] is flagged;   finally popcount of the flags.
-// first[] is ONE u32 array as long as the largest table (or bucket range, below), reused for each table in turn, so the
-// random atomics of a pass stay inside a (for the benchmark config L2-resident) 4-bytes-per-
-// bucket region instead of spreading over all tables at once.
-// Tables with more buckets than first[] holds (KV_FIRST_RANGE_LOG2, default 2^27 = 512 MB of first[])
-// are handled in bucket ranges [bin_lo, bin_lo + bin_n): one pass A + pass B per range, so the
-// scratch does not grow with the sketch.  (Ranges small enough to keep first[] in L2 were measured
-// and lose: every extra pass re-streams the hashes and redoes the modulo, ~60 us per 21 M k-mers,
-// more than the DRAM-resident atomics cost -- profiles/r01_notes.md.)
-__global__ void __launch_bounds__(256) kv_first_min_kernel(KvView v, int t, uint32_t *__restrict__ first,
-                                                           const uint64_t *__restrict__ hashes,
-                                                           const uint32_t *__restrict__ valid, uint64_t total,
-                                                           uint64_t bin_lo, uint64_t bin_n)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
-        if (valid && !((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
-        uint64_t bin;
-        if (kv_bin(v, t, __ldcs(hashes + g), bin) && bin - bin_lo < bin_n && kv_bucket_empty(v, t, bin))
-            atomicMin(first + (bin - bin_lo), (uint32_t)g);
-    }
-}
+// counter values -- so it is computed per chunk, BEFORE the chunk's increments:
+//   occurrence g is new  <=>  for some table t its bucket was empty at chunk start (occ bit
+//                             clear) and g is the smallest position of the chunk touching it.
+// first[] is ONE u32 array as long as the largest table (or bucket range), reused for every table
+// in turn.  An entry holds (epoch << 28 | position); every pass draws a fresh, SMALLER epoch, so
+// atomicMin makes the entries of older passes lose against anything written now and nothing is
+// ever swept or reset (the array is memset once every 15 passes).  Per chunk:
+//   table 0, pass A   fused into kv_hash_kernel: first[bin0] = min(first[bin0], tag | g) for every
+//                     k-mer whose table-0 bucket is empty;
+//   kv_first_compact  per position: owner of its table-0 bucket == itself -> new; owner is an
+//                     EARLIER position with the SAME hash -> a repeat: it can neither be new nor
+//                     change any minimum (the owner touches the same buckets before it), so it is
+//                     dropped; everything else -- owners, mere collisions, occupied or foreign
+//                     buckets -- goes on a compact (hash, position) list.  At sequencing depth the
+//                     list is a fraction of the stream (30x: ~1/5), and the passes over the other
+//                     tables cost what the list costs, not what the chunk costs;
+//   tables 1..T-1     kv_first_min_list (pass A over the list), then kv_first_own_list (pass B:
+//                     the position recorded in first[] is marked in fresh[], counted once).
+// Tables larger than first[] (KV_FIRST_RANGE_LOG2, default 2^31 entries = 8 GB) are walked in bucket
+// ranges [bin_lo, bin_lo + bin_n); then table 0 is not fused and the list holds every valid position.
+#define KV_POS_BITS 28
+#define KV_POS_MASK ((1u << KV_POS_BITS) - 1u)
 
-// Between pass A and pass B of table 0: which positions still matter for the other tables?
-// The minima in first[] only depend on the FIRST occurrence of each distinct hash -- a later
-// occurrence touches the same buckets at a larger position -- and it can never be new itself.  A
-// position whose table-0 bucket was empty at batch start knows that bucket's owner (the smallest
-// position touching it); if the owner is an earlier position with the SAME hash, this one is a
-// repeat and is dropped from the passes over tables 1..T-1.  At sequencing depth that is most of
-// the stream (30x coverage: ~3/4 of the k-mer occurrences).  Everything else stays: owners,
-// positions that merely collide with their owner, positions whose bucket was already occupied or
-// lives on another shard.  todo[] has the layout of valid[].
-__global__ void __launch_bounds__(256) kv_first_classify_kernel(KvView v, const uint32_t *__restrict__ first,
-                                                                const uint64_t *__restrict__ hashes,
-                                                                const uint32_t *__restrict__ valid, uint64_t total,
-                                                                uint32_t *__restrict__ todo)
+// all tables' occupancy bitmaps in one launch: blockIdx.y = table
+template <int BITS>
+__global__ void __launch_bounds__(256) kv_occ_rebuild_all_kernel(const __grid_constant__ KvView v)
 {
+    const int t = blockIdx.y;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t total_pad = (total + 31) & ~(uint64_t)31;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total_pad; g += stride) {
-        bool keep = g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
-        if (keep) {
-            const uint64_t h = __ldg(hashes + g);
-            uint64_t bin;
-            if (kv_bin(v, 0, h, bin) && kv_bucket_empty(v, 0, bin)) {
-                const uint32_t owner = __ldcg(first + bin);
-                if (owner < (uint32_t)g && __ldg(hashes + owner) == h) keep = false;
+    const uint64_t n_words = (v.size[t] + 31) / 32;
+    const uint64_t nbytes = BITS == 8 ? v.size[t] : v.size[t] / 2 + 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        uint32_t word = 0;
+        if (BITS == 8) {
+            const uint64_t b0 = i * 32;
+            if (b0 + 32 <= nbytes) {
+                const uint4 *p = (const uint4 *)(v.tab[t] + b0);
+                uint4 a = __ldcs(p), c = __ldcs(p + 1);
+                const uint32_t q[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint32_t nz = __vcmpne4(q[j], 0u);   // 0xff per non-zero byte
+                    word |= ((nz & 1u) | ((nz >> 7) & 2u) | ((nz >> 14) & 4u) | ((nz >> 21) & 8u)) << (4 * j);
+                }
+            } else {
+                for (int j = 0; j < 32 && b0 + j < v.size[t]; j++)
+                    if (v.tab[t][b0 + j]) word |= 1u << j;
+            }
+        } else {
+            // 32 buckets = 16 bytes; even bucket = high nibble
+            const uint64_t y0 = i * 16;
+            for (int j = 0; j < 16 && y0 + j < nbytes; j++) {
+                unsigned byte = v.tab[t][y0 + j];
+                if (byte >> 4) word |= 1u << (2 * j);
+                if ((byte & 15u) && i * 32 + 2 * j + 1 < v.size[t]) word |= 1u << (2 * j + 1);
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if ((threadIdx.x & 31) == 0) todo[g >> 5] = bal;
+        v.occ[t][i] = word;
     }
 }
 
-// pass B, bucket-major: stream first[] once; every recorded owner position gets its bit in
-// fresh[] (RED.OR into a bitmap of a few MB) and the entry is reset for the next table / batch.
-__global__ void __launch_bounds__(256) kv_first_resolve_kernel(uint32_t *__restrict__ first, uint64_t n_buckets,
-                                                               uint32_t *__restrict__ fresh)
+// FUSED0: table 0's pass A ran inside the hash kernel with tag `tag0`.  Writes fresh[] (every word of
+// the chunk), adds the new positions to *n_unique, and files the positions that still matter on the
+// list.  The list is segmented: the CTA working on positions [seg << KV_SEG_LOG2, +2^KV_SEG_LOG2) appends
+// to the list slots of the same index range through a shared-memory cursor and leaves the count in
+// seg_cnt[seg] -- no global counter that a million warps would fight over.
+#define KV_SEG_LOG2 12
+
+template <bool FUSED0>
+__global__ void __launch_bounds__(256) kv_first_compact_kernel(const __grid_constant__ KvView v, const uint32_t *__restrict__ first,
+                                                               const uint64_t *__restrict__ hashes,
+                                                               const uint32_t *__restrict__ valid, uint64_t total,
+                                                               uint32_t *__restrict__ fresh, uint64_t *__restrict__ list_h,
+                                                               uint32_t *__restrict__ list_p, uint32_t *__restrict__ seg_cnt,
+                                                               unsigned long long *n_unique)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t n_vec = n_buckets / 4;
-    uint4 *fv = (uint4 *)first;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        uint4 e = fv[i];
-        if ((e.x & e.y & e.z & e.w) == 0xffffffffu) continue;
-        if (e.x != 0xffffffffu) atomicOr(fresh + (e.x >> 5), 1u << (e.x & 31));
-        if (e.y != 0xffffffffu) atomicOr(fresh + (e.y >> 5), 1u << (e.y & 31));
-        if (e.z != 0xffffffffu) atomicOr(fresh + (e.z >> 5), 1u << (e.z & 31));
-        if (e.w != 0xffffffffu) atomicOr(fresh + (e.w >> 5), 1u << (e.w & 31));
-        fv[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    __shared__ unsigned s_cur;
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t n_segs = (total + (1u << KV_SEG_LOG2) - 1) >> KV_SEG_LOG2;
+    unsigned n_new = 0;
+    for (uint64_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        if (threadIdx.x == 0) s_cur = 0;
+        __syncthreads();
+        const uint64_t base = seg << KV_SEG_LOG2;
+        for (unsigned off = threadIdx.x; off < (1u << KV_SEG_LOG2); off += 256) {
+            const uint64_t g = base + off;
+            bool keep = g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
+            bool is_new = false;
+            uint64_t h = 0;
+            if (keep) {
+                h = __ldcs(hashes + g);
+                if (FUSED0) {
+                    uint64_t bin;
+                    if (kv_bin(v, 0, h, bin) && kv_bucket_empty(v, 0, bin)) {
+                        const uint32_t owner = __ldcg(first + bin) & KV_POS_MASK;   // this position took part in pass A
+                        if (owner == (uint32_t)g) is_new = true;
+                        else if (__ldg(hashes + owner) == h) keep = false;           // repeat of an earlier occurrence
+                    }
+                }
+            }
+            const unsigned new_bal = __ballot_sync(0xffffffffu, is_new);
+            const unsigned keep_bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0 && g < ((total + 31) & ~(uint64_t)31)) {
+                fresh[g >> 5] = new_bal;
+                n_new += __popc(new_bal);
+            }
+            if (keep_bal) {
+                unsigned wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_cur, (unsigned)__popc(keep_bal));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (keep) {
+                    const uint64_t slot = base + wbase + __popc(keep_bal & ((1u << lane) - 1u));
+                    list_h[slot] = h;
+                    list_p[slot] = (uint32_t)g;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) seg_cnt[seg] = s_cur;
     }
-    for (uint64_t b = n_vec * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += stride) {
-        uint32_t e = first[b];
-        if (e != 0xffffffffu) {
-            atomicOr(fresh + (e >> 5), 1u << (e & 31));
-            first[b] = 0xffffffffu;
+    if (lane == 0 && n_new) atomicAdd(n_unique, (unsigned long long)n_new);
+}
+
+// pass A of table t over the list
+__global__ void __launch_bounds__(256) kv_first_min_list_kernel(const __grid_constant__ KvView v, int t, uint32_t *__restrict__ first,
+                                                                uint32_t tag, const uint64_t *__restrict__ list_h,
+                                                                const uint32_t *__restrict__ list_p,
+                                                                const uint32_t *__restrict__ seg_cnt, uint64_t n_segs,
+                                                                uint64_t bin_lo, uint64_t bin_n)
+{
+    for (uint64_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const uint32_t cnt = seg_cnt[seg];
+        const uint64_t base = seg << KV_SEG_LOG2;
+        for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
+            uint64_t bin;
+            if (kv_bin(v, t, __ldg(list_h + base + i), bin) && bin - bin_lo < bin_n && kv_bucket_empty(v, t, bin))
+                atomicMin(first + (bin - bin_lo), tag | __ldg(list_p + base + i));
         }
     }
 }
 
-__global__ void kv_popcount_kernel(const uint32_t *__restrict__ words, uint64_t n_words, unsigned long long *out)
+// pass B of table t over the list: whoever is recorded in first[] is new (counted once over all tables)
+__global__ void __launch_bounds__(256) kv_first_own_list_kernel(const __grid_constant__ KvView v, int t, const uint32_t *__restrict__ first,
+                                                                uint32_t tag, const uint64_t *__restrict__ list_h,
+                                                                const uint32_t *__restrict__ list_p,
+                                                                const uint32_t *__restrict__ seg_cnt, uint64_t n_segs,
+                                                                uint64_t bin_lo, uint64_t bin_n, uint32_t *__restrict__ fresh,
+                                                                unsigned long long *n_unique)
 {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    unsigned mine = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) mine += __popc(words[i]);
-    mine = __reduce_add_sync(0xffffffffu, mine);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
+    unsigned n_new = 0;
+    for (uint64_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const uint32_t cnt = seg_cnt[seg];
+        const uint64_t base = seg << KV_SEG_LOG2;
+        for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
+            uint64_t bin;
+            const uint32_t g = __ldg(list_p + base + i);
+            if (kv_bin(v, t, __ldg(list_h + base + i), bin) && bin - bin_lo < bin_n && kv_bucket_empty(v, t, bin) &&
+                __ldcg(first + (bin - bin_lo)) == (tag | g)) {
+                const uint32_t bit = 1u << (g & 31);
+                n_new += !(atomicOr(fresh + (g >> 5), bit) & bit);
+            }
+        }
+    }
+    n_new = __reduce_add_sync(0xffffffffu, n_new);
+    if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(n_unique, (unsigned long long)n_new);
 }
 
 // khmer abundance_distribution (kevlar/dist.py:55): hist[counts.get(h)] += 1 for every position the
@@ -1127,6 +1176,25 @@ __global__ void __launch_bounds__(256) kv_synth_reads_kernel(KvSynthParams p)
         if (p.offsets && j == 0) p.offsets[r] = i;
     }
     if (p.offsets && blockIdx.x == 0 && threadIdx.x == 0) p.offsets[p.n_reads] = n_bases;
+}
+
+// reads the novel scan has something to say about (skipped, or discarded by the abundance screen) as a
+// compact list: at sequencing scale that is a handful out of millions, and the host only needs those
+struct KvReadNote {
+    uint32_t read, flags, discard;
+};
+
+__global__ void kv_read_notes_kernel(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ discard, uint64_t n_reads,
+                                     KvReadNote *__restrict__ notes, unsigned long long cap, unsigned long long *n_notes)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += stride) {
+        const uint32_t f = flags[r], d = discard ? discard[r] : 0xffffffffu;
+        if (f || d != 0xffffffffu) {
+            const unsigned long long slot = atomicAdd(n_notes, 1ULL);
+            if (slot < cap) notes[slot] = KvReadNote{(uint32_t)r, f, d};
+        }
+    }
 }
 
 // flag reads shorter than k as skipped (kevlar/novel.py:134): one thread per read

@@ -83,7 +83,7 @@ struct KvCtx {
     cudaStream_t compute = nullptr, copy = nullptr;
     KvSlot slot[2];
     int next_slot = 0;
-    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small, hist, todo;
+    KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small, hist;
     // sketches between these sizes take the region-partitioned update path (measured: 1.2-1.7x over
     // direct random atomics from 256 MB to 4 GB, break-even at 16 GB; profiles/r01_notes.md)
     uint64_t part_min_bytes = 128ull << 20, part_max_bytes = 8ull << 30;
@@ -95,7 +95,7 @@ struct KvCtx {
     uint64_t tile_chunk_bases = 256ull << 20; // positions per chunk on the tiled path                         [KV_TILE_CHUNK_BASES]
     int tile_direct_below = -1;               // regions with fewer offsets are updated in place (-1: region bytes / 64)
     int tile_block_log2 = 6;                  // slab layout: slots per interleave block (-1: run-major)               [KV_TILE_BLOCK_LOG2]
-    KvBuf tile_cursor, tile_slab, tile_ovf;
+    KvBuf tile_cursor, tile_slab, tile_ovf, notes;
     unsigned *dirty = nullptr;   // device: one overflow flag per chunk, 64 slots used round-robin
     unsigned dirty_next = 0;
     unsigned long long *counters = nullptr;   // device: [0] n_valid  [1] n_unique  [2] n_hits  [3] occupied  [5] redone chunks
@@ -108,8 +108,10 @@ struct KvCtx {
     double prof_ms[KV_PROF_CLASSES] = {0};
     uint64_t prof_n[KV_PROF_CLASSES] = {0};
     int sm_count = 148;
-    bool unique_classify = true;         // drop repeats after the table-0 pass (KV_NO_CLASSIFY switches it off)
-    uint64_t first_range = 1ull << 27;   // buckets covered by the n_unique first[] scratch: 512 MB (KV_FIRST_RANGE_LOG2)
+    bool unique_fuse0 = true;            // table 0's first-touch pass inside the hash kernel + compact list (KV_NO_CLASSIFY switches it off)
+    uint64_t first_range = 1ull << 31;   // buckets covered by the n_unique first[] scratch (4 B each; KV_FIRST_RANGE_LOG2)
+    int first_epoch = 0;                 // epochs left before first[] must be memset again (0: memset first)
+    KvBuf list_h, list_p, seg_cnt;
     size_t l2_persist = 0;     // bytes of L2 set aside for persisting accesses
     size_t l2_window_max = 0;
     uint64_t chunk_bases = 64ull << 20;
@@ -167,7 +169,7 @@ static int kv_ctx_get(int device, KvCtx **out)
         if (const char *env = getenv("KV_PART_MIN_BYTES")) c.part_min_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_MAX_BYTES")) c.part_max_bytes = strtoull(env, nullptr, 10);
         if (const char *env = getenv("KV_PART_REGION_LOG2")) c.part_region_log2 = std::max(4, std::min(30, atoi(env)));
-        if (getenv("KV_NO_CLASSIFY")) c.unique_classify = false;
+        if (getenv("KV_NO_CLASSIFY")) c.unique_fuse0 = false;
         if (const char *env = getenv("KV_UPDATE_PATH"))
             c.update_path = !strcmp(env, "direct") ? 1 : !strcmp(env, "part") ? 2 : !strcmp(env, "tile") ? 3 : 0;
         if (const char *env = getenv("KV_TILE_MIN_BYTES")) c.tile_min_bytes = strtoull(env, nullptr, 10);
@@ -906,62 +908,98 @@ static int kv_launch_partitioned(KvCtx *ctx, const KvView &v, const KvPartInfo &
     return KV_OK;
 }
 
-// exact n_unique_kmers contribution of one chunk (must run before the chunk's increments)
-// dist_counts != NULL: also histogram dist_counts.get(h) over the fresh positions into d_hist[256]
-static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const uint64_t *d_hashes, const uint32_t *d_valid,
-                          uint64_t n, const kv_sketch *dist_counts = nullptr, unsigned long long *d_hist = nullptr)
+// ---- exact n_unique_kmers (K5; kv_kernels.cuh has the algorithm)
+
+struct KvFreshPre {
+    bool fused0;        // table 0's pass A runs inside the hash kernel
+    uint32_t tag0;
+    uint64_t range;     // buckets covered by first[]
+};
+
+// a fresh epoch tag for one pass over first[] (15 passes per memset)
+static int kv_first_tag(KvCtx *ctx, uint32_t *tag)
+{
+    if (ctx->first_epoch == 0) {
+        CU(cudaMemsetAsync(ctx->first.p, 0xff, ctx->first.cap, ctx->compute));
+        ctx->first_epoch = 15;
+    }
+    *tag = (uint32_t)(--ctx->first_epoch) << KV_POS_BITS;
+    return KV_OK;
+}
+
+// Before the chunk is hashed: which buckets are empty right now (= at chunk start), the first[] scratch,
+// and -- when table 0 fits first[] -- the tag under which the hash kernel runs table 0's pass A.
+static int kv_fresh_prepare(KvCtx *ctx, kv_sketch *s, const KvView &v, bool may_fuse, KvFreshPre *pre)
 {
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
-    // first[] covers at most first_range buckets; larger tables are walked range by range
-    const uint64_t range = std::min(maxsize, ctx->first_range);
-    if (range * 4 > ctx->first.cap) {   // (re)allocated: establish the all-ones invariant the passes maintain
+    const uint64_t range = std::max<uint64_t>(1, std::min(maxsize, ctx->first_range));
+    if (range * 4 > ctx->first.cap) {
         if (kv_buf_ensure(ctx->first, range * 4) != KV_OK)
             return kv_fail(KV_ENOMEM, "exact n_unique_kmers tracking needs %llu bytes of scratch HBM; switch it off with "
                            "kv_sketch_set_unique_tracking(sketch, 0)", (unsigned long long)(range * 4));
-        CU(cudaMemsetAsync(ctx->first.p, 0xff, ctx->first.cap, ctx->compute));
+        ctx->first_epoch = 0;   // (re)allocated: memset before the first pass
     }
+    if (s->bits != 1) {   // one streaming pass over the counters, all tables in one launch
+        uint64_t words = 0;
+        for (int t = 0; t < s->n_tables; t++) words = std::max(words, (s->sizes[t] + 31) / 32);
+        dim3 grid(kv_grid_for(ctx, words, 16), (unsigned)s->n_tables);
+        if (s->bits == 8) LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_all_kernel<8>, grid, 256, v);
+        else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_all_kernel<4>, grid, 256, v);
+    }
+    pre->range = range;
+    pre->fused0 = may_fuse && s->sizes[0] <= range && s->sizes[0] > 0;
+    pre->tag0 = 0;
+    if (pre->fused0) KV_TRY(kv_first_tag(ctx, &pre->tag0));
+    return KV_OK;
+}
+
+// The chunk's contribution to n_unique_kmers; must run before the chunk's increments.  Leaves the bitmap
+// of new positions in ctx->fresh.  dist_counts != NULL: also histogram dist_counts.get(h) over them.
+static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const KvFreshPre &pre, const uint64_t *d_hashes,
+                          const uint32_t *d_valid, uint64_t n, const kv_sketch *dist_counts = nullptr,
+                          unsigned long long *d_hist = nullptr)
+{
+    if (n > (1ull << KV_POS_BITS)) return kv_fail(KV_EINVAL, "internal: n_unique chunk larger than 2^%d positions", KV_POS_BITS);
     const uint64_t n_words = (n + 31) / 32;
+    const uint64_t n_segs = (n + (1u << KV_SEG_LOG2) - 1) >> KV_SEG_LOG2, list_len = n_segs << KV_SEG_LOG2;
     KV_TRY(kv_buf_ensure(ctx->fresh, n_words * 4));
-    CU(cudaMemsetAsync(ctx->fresh.p, 0, n_words * 4, ctx->compute));
-    unsigned grid = kv_grid_for(ctx, n);
-    if (s->bits != 1)   // which buckets are empty right now (= at batch start): one streaming pass per table
-        for (int t = 0; t < s->n_tables; t++) {
-            uint64_t n_words = (s->sizes[t] + 31) / 32;
-            if (s->bits == 8) LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<8>, kv_grid_for(ctx, n_words, 16), 256, v, t);
-            else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_kernel<4>, kv_grid_for(ctx, n_words, 16), 256, v, t);
+    KV_TRY(kv_buf_ensure(ctx->list_h, list_len * 8));
+    KV_TRY(kv_buf_ensure(ctx->list_p, list_len * 4));
+    KV_TRY(kv_buf_ensure(ctx->seg_cnt, n_segs * 4));
+    uint32_t *first = (uint32_t *)ctx->first.p, *fresh = (uint32_t *)ctx->fresh.p, *seg_cnt = (uint32_t *)ctx->seg_cnt.p;
+    uint64_t *list_h = (uint64_t *)ctx->list_h.p;
+    uint32_t *list_p = (uint32_t *)ctx->list_p.p;
+    const unsigned grid = kv_grid_for(ctx, n);
+    const unsigned sgrid = (unsigned)std::min<uint64_t>(n_segs, (uint64_t)ctx->sm_count * 8);
+    if (pre.fused0)
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_compact_kernel<true>, sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, fresh,
+                 list_h, list_p, seg_cnt, s->d_unique);
+    else
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_compact_kernel<false>, sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, fresh,
+                 list_h, list_p, seg_cnt, s->d_unique);
+    for (int t = pre.fused0 ? 1 : 0; t < s->n_tables; t++)
+        for (uint64_t lo = 0; lo < s->sizes[t]; lo += pre.range) {
+            const uint64_t nb = std::min(pre.range, s->sizes[t] - lo);
+            uint32_t tag;
+            KV_TRY(kv_first_tag(ctx, &tag));
+            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_list_kernel, sgrid, 256, v, t, first, tag, (const uint64_t *)list_h,
+                     (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb);
+            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_own_list_kernel, sgrid, 256, v, t, (const uint32_t *)first, tag,
+                     (const uint64_t *)list_h, (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb, fresh,
+                     s->d_unique);
         }
-    kv_l2_window(ctx, ctx->first.p, range * 4);
-    // after table 0, repeats of an earlier hash are dropped from the other tables' passes
-    // (kv_first_classify_kernel); needs table 0 in one range so that every owner is in first[]
-    const bool classify = ctx->unique_classify && s->n_tables > 1 && s->sizes[0] <= range;
-    if (classify) KV_TRY(kv_buf_ensure(ctx->todo, n_words * 4));
-    const uint32_t *pass_valid = d_valid;
-    for (int t = 0; t < s->n_tables; t++)
-        for (uint64_t lo = 0; lo < s->sizes[t]; lo += range) {
-            const uint64_t nb = std::min(range, s->sizes[t] - lo);
-            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_kernel, grid, 256, v, t, (uint32_t *)ctx->first.p, d_hashes, pass_valid, n,
-                     lo, nb);
-            if (t == 0 && classify)
-                LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_classify_kernel, grid, 256, v, (const uint32_t *)ctx->first.p, d_hashes,
-                         d_valid, n, (uint32_t *)ctx->todo.p);
-            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_resolve_kernel, kv_grid_for(ctx, nb / 4 + 1), 256,
-                     (uint32_t *)ctx->first.p, nb, (uint32_t *)ctx->fresh.p);
-            if (t == 0 && classify) pass_valid = (const uint32_t *)ctx->todo.p;
-        }
-    kv_l2_window(ctx, nullptr, 0);
-    LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_popcount_kernel, kv_grid_for(ctx, n_words), 256, (const uint32_t *)ctx->fresh.p, n_words,
-             s->d_unique);
     if (dist_counts)
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_abund_dist_kernel, grid, 256, kv_view(dist_counts), d_hashes,
-                 (const uint32_t *)ctx->fresh.p, n, d_hist);
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_abund_dist_kernel, grid, 256, kv_view(dist_counts), d_hashes, (const uint32_t *)fresh, n,
+                 d_hist);
     return KV_OK;
 }
 
 // apply one chunk of hashes (device, n < 2^32) to the sketch: exact-unique bookkeeping first
 // (it must see the buckets as they were before this chunk), then the saturating increments
 static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, const uint32_t *d_valid, uint64_t n,
-                           const kv_sketch *dist_counts = nullptr, unsigned long long *d_hist = nullptr)
+                           const kv_sketch *dist_counts = nullptr, unsigned long long *d_hist = nullptr,
+                           const KvFreshPre *fused = nullptr)
 {
     if (!n) return KV_OK;
     KvView v = kv_view(s);
@@ -969,7 +1007,12 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
         KV_TRY(kv_state_rebuild_locked(ctx, s));
         s->state_stale = false;
     }
-    if (s->track_unique || dist_counts) KV_TRY(kv_count_fresh(ctx, s, v, d_hashes, d_valid, n, dist_counts, d_hist));
+    if (s->track_unique || dist_counts) {
+        KvFreshPre pre;
+        if (fused) pre = *fused;   // the caller ran kv_fresh_prepare before hashing (table 0's pass A is done)
+        else KV_TRY(kv_fresh_prepare(ctx, s, v, false, &pre));
+        KV_TRY(kv_count_fresh(ctx, s, v, pre, d_hashes, d_valid, n, dist_counts, d_hist));
+    }
     if (!s->track_unique) s->unique_valid = false;
     // abundance_distribution counts a k-mer into the tracking sketch only when it was new there
     if (dist_counts) d_valid = (const uint32_t *)ctx->fresh.p;
@@ -1026,7 +1069,8 @@ static int kv_tile_plan(KvCtx *ctx, const kv_sketch *s, uint64_t batch_pos, KvTi
     if (!runs || runs >= (1ull << 30)) return KV_OK;   // nothing held here / absurdly many regions: in-place updates
     pl->ti.run_base[s->n_tables] = (uint32_t)runs;
     pl->ti.run_base[KV_TABLES_DEV] = (uint32_t)runs;   // kv_slab_index reads the total there
-    const uint64_t chunk_pos = std::min<uint64_t>(ctx->tile_chunk_bases, (batch_pos + KV_TILE - 1) / KV_TILE * KV_TILE);
+    uint64_t chunk_pos = std::min<uint64_t>(ctx->tile_chunk_bases, (batch_pos + KV_TILE - 1) / KV_TILE * KV_TILE);
+    if (s->track_unique) chunk_pos = std::min<uint64_t>(chunk_pos, 1ull << KV_POS_BITS);   // n_unique positions are 28-bit
     // slots per run: mean + 6 % + 8 sigma + slack, for offsets spread by the hash; anything beyond (skewed
     // inputs) is updated in place by the producer
     const double mean = (double)chunk_pos / (double)min_regions;
@@ -1118,6 +1162,15 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
         if (mask) { p.use_mask = 1; p.mask = kv_view(mask); p.mask_threshold = mask_threshold; p.consume_masked = consume_masked != 0; }
         p.strict = 0;
         p.hashes = need_hashes ? (uint64_t *)ctx->hashes.p : nullptr; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+        KvFreshPre pre;
+        if (s->track_unique) {
+            if (s->state_stale && !plan.on) {   // (the in-place path rebuilds its hot bitmap anyway; do it before occ is derived)
+                KV_TRY(kv_state_rebuild_locked(ctx, s));
+                s->state_stale = false;
+            }
+            KV_TRY(kv_fresh_prepare(ctx, s, sv, ctx->unique_fuse0, &pre));
+            if (pre.fused0) { p.track0 = 1; p.first0 = (uint32_t *)ctx->first.p; p.tag0 = pre.tag0; p.sk = sv; }
+        }
         if (plan.on) {
             p.scatter = 1; p.ti = plan.ti; p.sk = sv;
             CU(cudaMemsetAsync(plan.ti.cursor, 0, (size_t)plan.runs * 4 + 4, ctx->compute));
@@ -1126,13 +1179,13 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
         if (s->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)nt));
         else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)nt));
         if (!plan.on) {
-            KV_TRY(kv_apply_hashes(ctx, s, p.hashes, p.valid, npos));
+            KV_TRY(kv_apply_hashes(ctx, s, p.hashes, p.valid, npos, nullptr, nullptr, s->track_unique ? &pre : nullptr));
             continue;
         }
         // tiled path: the producer has filed the updates; the exact-n_unique passes must still see the
         // tables as they were before this chunk, then one CTA per region applies its slab
         if (s->track_unique) {
-            KV_TRY(kv_count_fresh(ctx, s, sv, p.hashes, p.valid, npos));
+            KV_TRY(kv_count_fresh(ctx, s, sv, pre, p.hashes, p.valid, npos));
             LAUNCH_C(KV_PROF_FIXUP, ctx, kv_tile_overflow_kernel, kv_grid_for(ctx, npos / 32 + 1), 256, sv, plan.ti, p.hashes, npos);
         } else
             s->unique_valid = false;
@@ -1233,36 +1286,56 @@ static int kv_novel_impl(const kv_sketch *const *cases, int n_case, const kv_ske
     }
     kv_stage_done(ctx, &b);
 
-    // results back to the host
-    std::vector<uint32_t> hflags(n_reads), hdisc;
+    // results back to the host: the hit count, and the reads with a flag or a discard position as a
+    // compact list (the per-read arrays stay on the device unless nearly every read is noted)
+    const uint64_t note_cap = std::max<uint64_t>(4096, n_reads / 16);
+    KV_TRY(kv_buf_ensure(ctx->notes, note_cap * sizeof(KvReadNote)));
+    CU(cudaMemsetAsync(ctx->counters + 6, 0, sizeof(unsigned long long), ctx->compute));
+    LAUNCH(ctx, kv_read_notes_kernel, kv_grid_for(ctx, n_reads), 256, (const uint32_t *)ctx->flags.p,
+           screen > 0 ? (const uint32_t *)ctx->discard.p : (const uint32_t *)nullptr, n_reads, (KvReadNote *)ctx->notes.p,
+           (unsigned long long)note_cap, ctx->counters + 6);
     CU(cudaMemcpyAsync(ctx->h_counters + 2, ctx->counters + 2, 8, cudaMemcpyDeviceToHost, ctx->compute));
-    CU(cudaMemcpyAsync(hflags.data(), ctx->flags.p, n_reads * 4, cudaMemcpyDeviceToHost, ctx->compute));
-    if (screen > 0) {
-        hdisc.resize(n_reads);
-        CU(cudaMemcpyAsync(hdisc.data(), ctx->discard.p, n_reads * 4, cudaMemcpyDeviceToHost, ctx->compute));
-    }
+    CU(cudaMemcpyAsync(ctx->h_counters + 6, ctx->counters + 6, 8, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     uint64_t found = ctx->h_counters[2];
+    const uint64_t n_notes = ctx->h_counters[6];
     if (found > max_hits) { *n_hits = found; return kv_fail(KV_EOVERFLOW, "hit buffer too small: %llu hits, room for %llu", (unsigned long long)found, (unsigned long long)max_hits); }
     std::vector<kv_hit> hh(found);
-    if (found) {
-        CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, found * sizeof(kv_hit), cudaMemcpyDeviceToHost, ctx->compute));
-        CU(cudaStreamSynchronize(ctx->compute));
-    }
-    // read-level flags (kevlar/novel.py:134-139,152-154)
-    for (uint64_t r = 0; r < n_reads; r++) {
-        uint8_t fl = (uint8_t)(hflags[r] & KV_READ_SKIPPED);
+    if (found) CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, found * sizeof(kv_hit), cudaMemcpyDeviceToHost, ctx->compute));
+    // read-level flags (kevlar/novel.py:134-139,152-154); hdisc = discard position of the reads that have one
+    memset(read_flags, 0, n_reads);
+    if (screen > 0) for (uint64_t r = 0; r < n_reads; r++) discard_pos[r] = 0xffffffffu;
+    auto note = [&](uint64_t r, uint32_t f, uint32_t d) {
+        uint8_t fl = (uint8_t)(f & KV_READ_SKIPPED);
         if (screen > 0) {
-            if (!(fl & KV_READ_SKIPPED) && hdisc[r] != 0xffffffffu) fl |= KV_READ_DISCARDED;
-            discard_pos[r] = (fl & KV_READ_SKIPPED) ? 0xffffffffu : hdisc[r];
+            if (!(fl & KV_READ_SKIPPED) && d != 0xffffffffu) fl |= KV_READ_DISCARDED;
+            discard_pos[r] = (fl & KV_READ_SKIPPED) ? 0xffffffffu : d;
         }
         read_flags[r] = fl;
+    };
+    if (n_notes <= note_cap) {
+        std::vector<KvReadNote> notes(n_notes);
+        if (n_notes) CU(cudaMemcpyAsync(notes.data(), ctx->notes.p, n_notes * sizeof(KvReadNote), cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        for (const KvReadNote &nt : notes) note(nt.read, nt.flags, nt.discard);
+    } else {   // nearly every read is noted: fetch the per-read arrays
+        std::vector<uint32_t> hflags(n_reads), hd;
+        CU(cudaMemcpyAsync(hflags.data(), ctx->flags.p, n_reads * 4, cudaMemcpyDeviceToHost, ctx->compute));
+        if (screen > 0) {
+            hd.resize(n_reads);
+            CU(cudaMemcpyAsync(hd.data(), ctx->discard.p, n_reads * 4, cudaMemcpyDeviceToHost, ctx->compute));
+        }
+        CU(cudaStreamSynchronize(ctx->compute));
+        for (uint64_t r = 0; r < n_reads; r++) note(r, hflags[r], screen > 0 ? hd[r] : 0xffffffffu);
     }
+    // a discarded read keeps its raw discard position for the hit filter below even when it is also skipped
+    auto raw_discard = [&](uint32_t r) -> uint32_t { return screen > 0 ? discard_pos[r] : 0xffffffffu; };
     uint64_t kept = 0;
     for (uint64_t i = 0; i < found; i++) {
         const kv_hit &h = hh[i];
         if (read_flags[h.read] & KV_READ_SKIPPED) continue;
-        if (screen > 0 && hdisc[h.read] != 0xffffffffu && h.offset > hdisc[h.read]) continue;
+        const uint32_t d = raw_discard(h.read);
+        if (d != 0xffffffffu && h.offset > d) continue;
         hh[kept++] = h;
     }
     std::sort(hh.begin(), hh.begin() + kept, [](const kv_hit &a, const kv_hit &b2) {
@@ -1449,7 +1522,9 @@ extern "C" int kv_add_hashes(kv_sketch *s, const uint64_t *hashes, uint64_t n)
     CU(cudaSetDevice(s->device));
     KV_TRY(kv_buf_ensure(ctx->misc, n * 8));
     CU(cudaMemcpyAsync(ctx->misc.p, hashes, n * 8, cudaMemcpyHostToDevice, ctx->compute));
-    KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p, nullptr, n));
+    const uint64_t step = std::min<uint64_t>(ctx->chunk_bases, 1ull << 26);
+    for (uint64_t o = 0; o < n; o += step)
+        KV_TRY(kv_apply_hashes(ctx, s, (const uint64_t *)ctx->misc.p + o, nullptr, std::min(step, n - o)));
     CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }

@@ -790,6 +790,12 @@ def test_ranged_first_touch_passes_are_exact():
                     KV_FIRST_RANGE_LOG2='10')
 
 
+def test_unfused_first_touch_passes_are_exact():
+    """n_unique_kmers without the fused table-0 pass / compact list (the route taken by add(), by the
+    abundance distribution and by tables larger than the scratch): same numbers."""
+    _rerun_in_child('(consume and not saturation) or count_simple or full_size', KV_NO_CLASSIFY='1')
+
+
 def test_khmer_namespace_drop_in(kv, tmp_path):
     """INTEGRATION.md route 1: code written against the `khmer` namespace the way the reference
     uses it -- threads sharing one ReadParser into consume_seqfile, then one get() per k-mer per
