@@ -58,8 +58,9 @@ def parse_args():
                     help='murmur = Counttable (what `kevlar count` builds); twobit = Countgraph')
     ap.add_argument('--counter-size', type=int, default=8, choices=[8, 4, 1],
                     help='bits per counter at the same 64 MB per sketch (4 = SmallCount*, 1 = Node*); the headline is 8')
-    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p', 'p2p_host', 'sharded'],
-                    help="N>1: how per-GPU work is combined; 'sharded' = plan B, bin-range-sharded sketches")
+    ap.add_argument('--merge', default='p2p', choices=['allreduce', 'allgather', 'p2p', 'p2p_host', 'sharded', 'span'],
+                    help="N>1: how per-GPU work is combined; 'sharded' = plan B (hash all-gather), 'span' = plan B with "
+                         "spanning sketches (tables spread over all GPUs, exchange fused into the apply kernel)")
     ap.add_argument('--reads-per-sample', type=int, default=READS_PER_SAMPLE)
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -70,6 +71,9 @@ def parse_args():
     ap.add_argument('--c3-memory', type=float, default=C3_MEMORY)
     ap.add_argument('--c3-steps', type=int, default=2)
     ap.add_argument('--c3-no-parity', action='store_true')
+    ap.add_argument('--c4', action='store_true', help='also run the config-4-shaped part: 4-bit spanning sketches across all GPUs')
+    ap.add_argument('--c4-gb-per-gpu', type=float, default=16.0, help='GB of each of the 3 sketches held per GPU')
+    ap.add_argument('--c4-reads', type=int, default=C3_READS, help='reads per sample (all ranks together)')
     return ap.parse_args()
 
 
@@ -312,11 +316,15 @@ class GpuTrio(object):
         name, buckets = sketch_shape(args)
         cls = getattr(khmer, name)
         self.sharded = world > 1 and args.merge == 'sharded'
+        self.span = world > 1 and args.merge == 'span'
         if self.sharded:   # plan B: every rank holds 1/world of every table; reads stay sharded
             self.sketches = [multigpu.ShardedSketch(cls, K, buckets, N_TABLES) for _ in range(3)]
+        elif self.span:    # plan B, spanning sketches: one virtual table over the HBM of all ranks
+            self.spans = [multigpu.SpanningSketch(cls, K, buckets, N_TABLES) for _ in range(3)]
+            self.sketches = [sp.sketch for sp in self.spans]
         else:
             self.sketches = [cls(K, buckets, N_TABLES) for _ in range(3)]
-        if args.no_unique and not self.sharded:
+        if args.no_unique and not self.sharded and not self.span:
             for sk in self.sketches:
                 sk.set_unique_tracking(False)
         self.trio = trio
@@ -329,7 +337,29 @@ class GpuTrio(object):
         self.last_hits = None
 
     def plain_sketches(self):
-        return [] if self.sharded else list(self.sketches)
+        return [] if (self.sharded or self.span) else list(self.sketches)
+
+    def step_span(self, resident):
+        khmer = self.khmer
+        for sp in self.spans:
+            sp.clear()
+        for i, sp in enumerate(self.spans):
+            if resident:
+                b, o = self.dev[i]
+                sp.consume_batch(b.data_ptr(), (o.data_ptr(), o.numel() - 1), where=khmer.MEM_DEVICE, n_positions=b.numel())
+            else:
+                b, o = self.pinned[i]
+                sp.consume_batch(b.numpy(), o.numpy().view(np.uint64))
+        if resident:
+            b, o = self.dev[0]
+            hits = khmer.novel_batch(self.sketches[:1], self.sketches[1:], b.data_ptr(), (o.data_ptr(), o.numel() - 1, b.numel()),
+                                     CASE_MIN, CTRL_MAX, where=khmer.MEM_DEVICE)[0]
+        else:
+            b, o = self.pinned[0]
+            hits = khmer.novel_batch(self.sketches[:1], self.sketches[1:], b.numpy(), o.numpy().view(np.uint64), CASE_MIN,
+                                     CTRL_MAX)[0]
+        self.last_hits = hits
+        return hits
 
     def step_sharded(self):
         # host buffers in both arms: hash locally, exchange, apply to the local bin ranges
@@ -347,6 +377,8 @@ class GpuTrio(object):
     def step(self, resident):
         if self.sharded:
             return self.step_sharded()
+        if self.span:
+            return self.step_span(resident)
         khmer = self.khmer
         for sk in self.sketches:
             sk.clear()
@@ -685,6 +717,115 @@ def run_c3(args, rank, world, barrier, phase):
     return out, sketches
 
 
+# ----------------------------------------------------------------------------- config 4 (shape)
+
+def run_c4(args, rank, world, barrier, phase):
+    """BASELINE config 4's SHAPE at a size one run can afford: 4-bit SmallCounttable sketches that do not
+    fit one GPU, spread over the HBM of all ranks (spanning sketches), reads drawn on the device and sharded,
+    updates exchanged inside the tiled apply kernel (2 B per update over NVLink), novel scan shard-local with
+    plain loads that cross NVLink for remote pages.  Full-size checks are properties: the same reads counted
+    under a different read-to-rank assignment give byte-identical sketches and the same number of hits."""
+    import torch
+    from kevlar_b200 import _lib, khmer, multigpu, simtrio
+    td = torch.distributed
+    device = _lib.current_device()
+    dev = torch.device('cuda', device)
+    n_total = args.c4_reads
+    buckets = args.c4_gb_per_gpu * 1e9 * world * 2 / N_TABLES          # 4-bit: two buckets per byte
+    spans = [multigpu.SpanningSketch(khmer.SmallCounttable, K, buckets, N_TABLES) for _ in range(3)]
+    sketches = [sp.sketch for sp in spans]
+    phase('c4: 3 spanning sketches of {:.0f} GB allocated ({:.0f} GB per GPU each)'.format(
+        args.c4_gb_per_gpu * world, args.c4_gb_per_gpu))
+    stream = torch.cuda.ExternalStream(_lib.stream_ptr(device), device=dev)
+    state = {}
+
+    def draw(shift):
+        r = (rank + shift) % world
+        return simtrio.device_trio(args.c3_genome, n_total, r, world, read_len=READ_LEN)
+
+    def count(trio):
+        for sp in spans:
+            sp.clear()
+        for sp, (b, o) in zip(spans, trio):
+            sp.consume_batch(b.data_ptr(), (o.data_ptr(), o.numel() - 1), where=khmer.MEM_DEVICE, n_positions=b.numel())
+
+    def scan(trio):
+        b, o = trio[0]
+        state['hits'] = khmer.novel_batch(sketches[:1], sketches[1:], b.data_ptr(), (o.data_ptr(), o.numel() - 1, b.numel()),
+                                          CASE_MIN, CTRL_MAX, where=khmer.MEM_DEVICE)[0]
+
+    def timed(fn):
+        barrier()
+        torch.cuda.synchronize()
+        _lib.sync(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        _lib.sync(device)
+        torch.cuda.synchronize()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def local_checksums():
+        out = []
+        for sk in sketches:
+            ptr, nbytes = sk.flat_device_buffer()
+            out.append(sketch_checksum(torch, sk))
+        return out
+
+    trio = draw(0)
+    count(trio)
+    scan(trio)          # warm-up
+    _lib.profile(1)
+    ms_count = timed(lambda: count(trio))
+    prof_count = _lib.profile(1)
+    ms_scan = timed(lambda: scan(trio))
+    prof_scan = _lib.profile(0)
+    sums_a = local_checksums()
+    hits_a = torch.tensor([len(state['hits'])], dtype=torch.int64, device=dev)
+    occ_a = [sp.n_occupied() for sp in spans]
+    del trio
+    trio = draw(1)      # every rank counts the NEXT rank's slice: same reads, different owners
+    count(trio)
+    scan(trio)
+    sums_b = local_checksums()
+    hits_b = torch.tensor([len(state['hits'])], dtype=torch.int64, device=dev)
+    if world > 1:
+        td.all_reduce(hits_a)
+        td.all_reduce(hits_b)
+    t = torch.tensor([ms_count, ms_scan], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_count, ms_scan = t.tolist()
+    nk = n_total * (READ_LEN - K + 1)
+    out = None
+    if rank == 0:
+        out = {
+            'workload': 'C4 shape: 4-bit SmallCounttable, {} tables, 3 sketches of {:.0f} GB each spanning {} GPU(s) ({:.0f} GB per '
+                        'GPU and sketch), {} reads x {} bp per sample drawn on the device and sharded, k={}'.format(
+                            N_TABLES, args.c4_gb_per_gpu * world, world, args.c4_gb_per_gpu, n_total, READ_LEN, K),
+            'count': {'ms': ms_count, 'kmers_per_s': 3 * nk / (ms_count / 1e3), 'kernel_ms_rank0': {k: round(v[0], 3) for k, v in prof_count.items() if v[1]}},
+            'novel': {'ms': ms_scan, 'kmers_per_s': nk / (ms_scan / 1e3), 'kernel_ms_rank0': {k: round(v[0], 3) for k, v in prof_scan.items() if v[1]}},
+            'value': 4 * nk / ((ms_count + ms_scan) / 1e3), 'unit': 'k-mers/s',
+            'nvlink_bytes_per_kmer': {
+                'count': 'updates cross NVLink as 16-bit offsets pulled by the owner of the region: {} tables x 2 B x {}/{} = {:.1f} B per '
+                         'k-mer (the hash all-gather of the first design moved 8 B x {} per position)'.format(
+                             N_TABLES, world - 1, world, N_TABLES * 2.0 * (world - 1) / max(world, 1), world - 1),
+                'novel': 'counter loads for remote pages: one 32 B sector per table touch x {}/{} of the touches'.format(world - 1, world)},
+            'properties_at_full_size': {
+                'same_sketch_bytes_under_a_rotated_read_assignment': sums_a == sums_b,
+                'same_hit_count_under_a_rotated_read_assignment': int(hits_a.item()) == int(hits_b.item()),
+                'novel_hits_all_ranks': int(hits_a.item()), 'n_occupied': occ_a},
+        }
+    del sketches[:]
+    state.clear()
+    for sp in spans:
+        sp.close()
+    barrier()
+    return out
+
+
 def run_ours(args):
     t_start = time.perf_counter()
     import torch
@@ -775,7 +916,14 @@ def measure(args, rank, world, barrier, phase, live):
             live.remove(sk)
         del c3_sketches
 
-    if world > 1 and args.merge == 'p2p':
+    c4 = None
+    if args.c4 and not runner.sharded:
+        c4 = run_c4(args, rank, world, barrier, phase)
+    if getattr(runner, 'span', False):
+        runner.sketches = []
+        for sp in runner.spans:
+            sp.close()
+    if world > 1 and args.merge in ('p2p', 'span'):
         multigpu.peer_sync_status()   # raises if a device-side barrier ever timed out
     if rank != 0:
         return None
@@ -867,6 +1015,8 @@ def measure(args, rank, world, barrier, phase, live):
     }
     if c3 is not None:
         line['c3'] = c3
+    if c4 is not None:
+        line['c4'] = c4
 
     if world == 1 and not args.no_cpu_baseline:
         from oracle import khmer_oracle as ko

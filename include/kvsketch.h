@@ -223,6 +223,35 @@ int kv_novel_from_counts(const kv_sketch *like, int n_case, int n_ctrl, const ui
                          int ctrl_max, int screen, int num_bands, int64_t band_minus_1, kv_hit *hits,
                          uint64_t max_hits, uint64_t *n_hits, uint8_t *read_flags, uint32_t *discard_pos);
 
+/* Spanning sketches (SURVEY 8e plan B, second design; no reference counterpart): a sketch larger than one GPU
+ * whose tables live in ONE virtual address range mapped on every rank, piece r of every table in the HBM of
+ * rank r (CUDA virtual memory management; pieces are shared between the ranks' processes as POSIX file
+ * descriptors).  Every call that reads the sketch -- kv_get_hashes, kv_novel_batch, kv_kmer_counts_batch,
+ * kv_sketch_stats, kv_sketch_save, kv_sketch_read_table -- works on it unchanged from any rank (remote
+ * pieces are reached over NVLink).  Updates are COLLECTIVE: kv_consume_batch_span takes THIS rank's reads,
+ * files their updates by (table, region) in slabs that the other ranks map over CUDA IPC, and the rank
+ * holding a region applies the slabs of all ranks in shared memory -- the all-to-all of the update stream
+ * (2 bytes per update) is fused into that kernel.  Protocol:
+ *   kv_sketch_create_span   on every rank (same arguments but `rank`): returns the handle, one file descriptor
+ *                           per table for this rank's physical memory (mem_fds_out[n_tables]) and a
+ *                           128-byte handle for its exchange buffers;
+ *   kv_sketch_span_attach   once per peer, with the peer's n_tables descriptors (passed over a Unix socket,
+ *                           SCM_RIGHTS) and exchange handle;
+ *   kv_sketch_span_ready    after all peers are attached.
+ * kv_consume_batch_span: every rank passes the same n_chunks >= ceil(its positions / chunk_positions) (the
+ * maximum over the ranks; ranks that run out of reads take part with empty slabs) and its kv_peer_sync.
+ * kv_sketch_clear clears the local pieces (call it on every rank).  n_unique_kmers is not tracked. */
+int kv_sketch_create_span(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int rank, int world,
+                          int device, uint64_t chunk_positions, kv_sketch **out, int *mem_fds_out,
+                          uint8_t xchg_handle_out[128]);
+int kv_sketch_span_attach(kv_sketch *s, int peer_rank, const int *mem_fds, const uint8_t xchg_handle[128]);
+int kv_sketch_span_ready(kv_sketch *s);
+int kv_sketch_span_info(const kv_sketch *s, int *rank, int *world, uint64_t *piece_bytes, uint64_t *chunk_positions);
+struct kv_peer_sync;
+int kv_consume_batch_span(kv_sketch *s, struct kv_peer_sync *ps, const uint8_t *bases, const uint64_t *offsets,
+                          uint64_t n_reads, int where, uint64_t n_chunks, int num_bands, int band, const kv_sketch *mask,
+                          int mask_threshold, int consume_masked, uint64_t *n_kmers_out);
+
 /* CUDA IPC plumbing for kv_sketch_merge_peers: export this sketch's flat allocation
  * (64-byte handle) / map a peer's.  */
 int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);

@@ -568,6 +568,21 @@ __global__ void __launch_bounds__(256, KV_INC_MIN_CTAS) kv_part_apply_kernel(KvV
 // Regions that received only a few offsets are cheaper to update in place (cnt * 64 B of sector
 // traffic against 2 x region bytes): those go through the exact global path.  Bit tables (Bloom
 // filters) keep their bytes and use shared-memory ORs.
+// khmer add() on sketches that have no hot bitmap (spanning sketches): the exact update for every hash
+__global__ void __launch_bounds__(256) kv_add_exact_kernel(const __grid_constant__ KvView v, const uint64_t *__restrict__ hashes,
+                                                           const uint32_t *__restrict__ valid, uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        if (valid && !((valid[g >> 5] >> (g & 31)) & 1u)) continue;
+        const uint64_t h = hashes[g];
+        for (int t = 0; t < v.n_tables; t++) {
+            uint64_t bin;
+            if (kv_bin(v, t, h, bin)) kv_bucket_inc_exact(v, t, bin);
+        }
+    }
+}
+
 // the producer's overflow marks (tracked sketches), applied in place once the n_unique passes are done
 __global__ void __launch_bounds__(256) kv_tile_overflow_kernel(const __grid_constant__ KvView v, const __grid_constant__ KvTileInfo ti,
                                                                const uint64_t *__restrict__ hashes, uint64_t n_pos)
@@ -590,21 +605,50 @@ __global__ void __launch_bounds__(256) kv_tile_overflow_kernel(const __grid_cons
 #define KV_TILE_THREADS 512
 #define KV_TILE_BATCH 60000u     // offsets applied between two clamps: 255 + 60000 < 65536
 
-template <int BITS>
-__global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __grid_constant__ KvView v, const __grid_constant__ KvTileInfo ti,
-                                                                        uint32_t direct_below)
+// Spanning sketches (the tables spread over the HBM of `n` ranks): the slabs of ALL ranks feed a region,
+// and only the rank whose HBM holds the region applies them -- the all-to-all of the update stream happens
+// inside this kernel, as peer loads over NVLink of exactly the slabs a CTA needs.
+struct KvTileSources {
+    int n;                                   // 1: only `ti` (ordinary sketch)
+    int rank;
+    const uint32_t *cursor[KV_MAX_RANKS];
+    const uint16_t *slab[KV_MAX_RANKS];
+    uint64_t piece[KV_TABLES_DEV];           // bytes of table t per rank
+};
+
+template <int BITS, bool SPAN>
+__global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __grid_constant__ KvView v, const __grid_constant__ KvTileInfo ti0,
+                                                                        uint32_t direct_below, const __grid_constant__ KvTileSources src)
 {
     extern __shared__ uint32_t sm_tile[];   // BITS 8/4: (1 << rb) / 2 words of two 16-bit counters; BITS 1: (1 << rb) / 32 words
     const uint32_t run = blockIdx.x;
-    const uint32_t want = ti.cursor[run];
-    const uint32_t cnt = want < ti.cap ? want : ti.cap;
-    if (cnt == 0) return;
     int t = 0;
-    while (t + 1 < v.n_tables && run >= ti.run_base[t + 1]) t++;
-    const uint64_t bucket0 = (uint64_t)(run - ti.run_base[t]) << ti.rb;
-    const uint32_t nb = (uint32_t)((v.size[t] - bucket0) < (1ull << ti.rb) ? (v.size[t] - bucket0) : (1ull << ti.rb));
-    if (cnt < direct_below) {   // sparse region: in place
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) kv_bucket_inc_exact(v, t, bucket0 + ti.slab[kv_slab_index(ti, run, i)]);
+    while (t + 1 < v.n_tables && run >= ti0.run_base[t + 1]) t++;
+    const uint64_t bucket0 = (uint64_t)(run - ti0.run_base[t]) << ti0.rb;
+    if (SPAN) {
+        // whose HBM holds this region?  (pieces are multiples of 2 MB, regions are <= 64 KB and aligned)
+        const uint64_t byte0 = BITS == 8 ? bucket0 : (BITS == 4 ? bucket0 >> 1 : bucket0 >> 3);
+        if ((int)(byte0 / src.piece[t]) != src.rank) return;
+    }
+    const uint32_t nb = (uint32_t)((v.size[t] - bucket0) < (1ull << ti0.rb) ? (v.size[t] - bucket0) : (1ull << ti0.rb));
+    const int n_src = SPAN ? src.n : 1;
+    // how many offsets each source filed for this region: all (remote) cursors are fetched at once
+    __shared__ uint32_t s_cnt[KV_MAX_RANKS];
+    if ((int)threadIdx.x < n_src) {
+        const uint32_t want = SPAN ? src.cursor[threadIdx.x][run] : ti0.cursor[run];
+        s_cnt[threadIdx.x] = want < ti0.cap ? want : ti0.cap;
+    }
+    __syncthreads();
+    uint32_t total = 0;
+    for (int q = 0; q < n_src; q++) total += s_cnt[q];
+    if (total == 0) return;
+    if (total < direct_below) {   // sparse region: in place
+        for (int q = 0; q < n_src; q++) {
+            KvTileInfo ti = ti0;
+            if (SPAN) { ti.cursor = const_cast<uint32_t *>(src.cursor[q]); ti.slab = const_cast<uint16_t *>(src.slab[q]); }
+            const uint32_t cnt = s_cnt[q];
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) kv_bucket_inc_exact(v, t, bucket0 + ti.slab[kv_slab_index(ti, run, i)]);
+        }
         return;
     }
     if (BITS == 1) {
@@ -612,9 +656,14 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
         const uint32_t nbytes = (nb + 7) >> 3, nwords = (nbytes + 3) >> 2;
         for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) sm_tile[w] = 0;
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t o = ti.slab[kv_slab_index(ti, run, i)];
-            atomicOr(&sm_tile[o >> 5], 1u << (o & 31));
+        for (int q = 0; q < n_src; q++) {
+            KvTileInfo ti = ti0;
+            if (SPAN) { ti.cursor = const_cast<uint32_t *>(src.cursor[q]); ti.slab = const_cast<uint16_t *>(src.slab[q]); }
+            const uint32_t cnt = s_cnt[q];
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+                const uint32_t o = ti.slab[kv_slab_index(ti, run, i)];
+                atomicOr(&sm_tile[o >> 5], 1u << (o & 31));
+            }
         }
         __syncthreads();
         // OR the collected bits into the table (bytes of a region are not shared with other regions:
@@ -646,8 +695,24 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
             ((uint16_t *)sm_tile)[b] = b < nb ? g[b] : 0;
     } else {
         const uint8_t *g = v.tab[t] + (bucket0 >> 1);   // even bucket = high nibble
-        const uint32_t nbytes = (nb + 1) >> 1;
-        for (uint32_t y = threadIdx.x; y < nbytes; y += blockDim.x) {
+        const uint32_t nbytes = (nb + 1) >> 1, nvec = nbytes >> 4;
+        const uint4 *gv = (const uint4 *)g;
+        uint4 *sv = (uint4 *)sm_tile;
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {   // 16 bytes = 32 counters -> 16 words
+            const uint4 x = __ldcs(gv + i);
+            const uint32_t q[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t hi = (q[j] >> 4) & 0x0f0f0f0fu, lo = q[j] & 0x0f0f0f0fu;
+                uint4 w;
+                w.x = __byte_perm(hi, lo, 0x0400) & 0x00ff00ffu;
+                w.y = __byte_perm(hi, lo, 0x0501) & 0x00ff00ffu;
+                w.z = __byte_perm(hi, lo, 0x0602) & 0x00ff00ffu;
+                w.w = __byte_perm(hi, lo, 0x0703) & 0x00ff00ffu;
+                sv[4 * i + j] = w;
+            }
+        }
+        for (uint32_t y = (nvec << 4) + threadIdx.x; y < nbytes; y += blockDim.x) {   // ragged end of the table
             const unsigned byte = g[y];
             sm_tile[y] = (byte >> 4) | ((byte & 15u) << 16);
         }
@@ -655,18 +720,29 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
     __syncthreads();
     // ---- apply, at most KV_TILE_BATCH offsets between clamps
     const uint32_t nwords = (nb + 1) >> 1;
-    for (uint32_t base = 0; base < cnt; base += KV_TILE_BATCH) {
-        const uint32_t end = base + KV_TILE_BATCH < cnt ? base + KV_TILE_BATCH : cnt;
-        for (uint32_t i = base + threadIdx.x; i < end; i += blockDim.x) {
-            const uint32_t o = __ldcs(ti.slab + kv_slab_index(ti, run, i));
-            atomicAdd(&sm_tile[o >> 1], 1u << (16 * (o & 1)));
-        }
-        __syncthreads();
-        if (end < cnt) {
-            for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) sm_tile[w] = __vminu2(sm_tile[w], maxv | (maxv << 16));
-            __syncthreads();
+    uint32_t since = 0;   // offsets applied since the last clamp
+    for (int q = 0; q < n_src; q++) {
+        KvTileInfo ti = ti0;
+        if (SPAN) { ti.cursor = const_cast<uint32_t *>(src.cursor[q]); ti.slab = const_cast<uint16_t *>(src.slab[q]); }
+        const uint32_t cnt = s_cnt[q];
+        for (uint32_t base = 0; base < cnt;) {
+            if (since == KV_TILE_BATCH) {
+                __syncthreads();
+                for (uint32_t w = threadIdx.x; w < nwords; w += blockDim.x) sm_tile[w] = __vminu2(sm_tile[w], maxv | (maxv << 16));
+                __syncthreads();
+                since = 0;
+            }
+            const uint32_t room = KV_TILE_BATCH - since;
+            const uint32_t end = cnt - base < room ? cnt : base + room;
+            for (uint32_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+                const uint32_t o = __ldcs(ti.slab + kv_slab_index(ti, run, i));
+                atomicAdd(&sm_tile[o >> 1], 1u << (16 * (o & 1)));
+            }
+            since += end - base;
+            base = end;
         }
     }
+    __syncthreads();
     // ---- clamp + narrow + store
     if (BITS == 8) {
         uint8_t *g = v.tab[t] + bucket0;
@@ -688,8 +764,24 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
         }
     } else {
         uint8_t *g = v.tab[t] + (bucket0 >> 1);
-        const uint32_t nbytes = (nb + 1) >> 1;
-        for (uint32_t y = threadIdx.x; y < nbytes; y += blockDim.x) {
+        const uint32_t nbytes = (nb + 1) >> 1, nvec = nbytes >> 4;
+        uint4 *gv = (uint4 *)g;
+        const uint4 *sv = (const uint4 *)sm_tile;
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            uint32_t q[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 w = sv[4 * i + j];
+                const uint32_t a = __vminu2(w.x, 0x000f000fu), b = __vminu2(w.y, 0x000f000fu), c = __vminu2(w.z, 0x000f000fu),
+                               d = __vminu2(w.w, 0x000f000fu);
+                // byte k of the result = (even counter << 4) | odd counter of word k
+                const uint32_t hi = __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+                const uint32_t lo = __byte_perm(__byte_perm(a, b, 0x0062), __byte_perm(c, d, 0x0062), 0x5410);
+                q[j] = (hi << 4) | lo;
+            }
+            gv[i] = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+        for (uint32_t y = (nvec << 4) + threadIdx.x; y < nbytes; y += blockDim.x) {
             const uint32_t w = __vminu2(sm_tile[y], 0x000f000fu);
             g[y] = (uint8_t)(((w & 15u) << 4) | (w >> 16));
         }

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>   // driver API types only; entry points are fetched with cudaGetDriverEntryPoint (libcuda is never linked)
+
 #include "kv_kernels.cuh"
 
 // ------------------------------------------------------------------ errors
@@ -259,6 +261,25 @@ static inline unsigned kv_grid_for(const KvCtx *c, uint64_t n, int per_sm = 8)
 
 // ------------------------------------------------------------------ sketch
 
+// a sketch whose tables span the HBM of several GPUs (see "spanning sketches" below)
+struct KvSpan {
+    int rank, world;
+    uint64_t piece[KV_TABLES_DEV];       // bytes of table t that each rank holds (a multiple of the VMM granularity)
+    uint64_t va_bytes;
+    CUdeviceptr va;
+    CUmemGenericAllocationHandle phys[KV_MAX_RANKS][KV_TABLES_DEV];   // one physical allocation per (rank, table): cuMemMap cannot map at an offset
+    bool have[KV_MAX_RANKS];
+    bool ready;
+    // tiled-update exchange buffers: mine (cudaMalloc, exported over CUDA IPC) and the peers' (mapped)
+    KvTileInfo ti;                       // fixed geometry: rb, run_base, cap, cursor = mine, slab = mine
+    uint32_t runs;
+    uint64_t chunk_pos;
+    size_t smem;
+    uint32_t direct_below;
+    uint32_t *cursor[KV_MAX_RANKS];
+    uint16_t *slab[KV_MAX_RANKS];
+};
+
 struct kv_sketch {
     int hasher, bits, ksize, n_tables, device;
     uint64_t sizes[KV_TABLES_DEV];    // buckets held here (the whole table, or this shard's bin range)
@@ -278,6 +299,7 @@ struct kv_sketch {
     bool state_stale;                 // tables were written behind the kernels' back: rebuild the hot bitmap before the next update
     uint64_t n_unique;                // host copy, updated at stats time
     unsigned long long *d_unique;     // device accumulator
+    KvSpan *span;                     // non-NULL: the tables span the HBM of several GPUs (kv_sketch_create_span)
 };
 
 static uint64_t kv_table_bytes(int bits, uint64_t size)
@@ -285,7 +307,28 @@ static uint64_t kv_table_bytes(int bits, uint64_t size)
     return bits == 8 ? size : (bits == 4 ? size / 2 + 1 : size / 8 + 1);
 }
 
+// device -> host copy of bytes [off, off + n) of table t; for spanning sketches one copy per piece (a
+// single memcpy must not straddle physical allocations that live on different GPUs)
+static cudaError_t kv_table_d2h(KvCtx *ctx, const kv_sketch *s, int t, uint64_t off, void *dst, uint64_t n);
+
 static int kv_state_rebuild_locked(KvCtx *ctx, kv_sketch *s);
+static void kv_span_free(kv_sketch *s);
+static int kv_tile_rb_for(const KvCtx *ctx, const kv_sketch *s);
+static int kv_tile_blk_for(const KvCtx *ctx, uint64_t runs);
+
+static cudaError_t kv_table_d2h(KvCtx *ctx, const kv_sketch *s, int t, uint64_t off, void *dst, uint64_t n)
+{
+    const uint8_t *src = s->flat + s->toff[t];
+    if (!s->span) return cudaMemcpyAsync(dst, src + off, n, cudaMemcpyDeviceToHost, ctx->compute);
+    const uint64_t piece = s->span->piece[t];
+    while (n) {
+        const uint64_t room = piece - off % piece, m = std::min(n, room);
+        cudaError_t e = cudaMemcpyAsync(dst, src + off, m, cudaMemcpyDeviceToHost, ctx->compute);
+        if (e != cudaSuccess) return e;
+        off += m; n -= m; dst = (uint8_t *)dst + m;
+    }
+    return cudaSuccess;
+}
 
 static KvView kv_view(const kv_sketch *s)
 {
@@ -454,6 +497,7 @@ extern "C" int kv_sketch_destroy(kv_sketch *s)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(ctx->compute));
+    if (s->span) kv_span_free(s);
     if (s->flat) cudaFree(s->flat);
     if (s->state) cudaFree(s->state);
     if (s->d_unique) cudaFree(s->d_unique);
@@ -468,6 +512,11 @@ extern "C" int kv_sketch_clear(kv_sketch *s)
     KV_TRY(kv_ctx_get(s->device, &ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
+    if (s->span) {   // every rank clears the pieces it holds (collective by convention)
+        for (int t = 0; t < s->n_tables; t++)
+            CU(cudaMemsetAsync(s->flat + s->toff[t] + (uint64_t)s->span->rank * s->span->piece[t], 0, s->span->piece[t], ctx->compute));
+        return KV_OK;
+    }
     CU(cudaMemsetAsync(s->flat, 0, s->flat_bytes, ctx->compute));
     if (s->state) CU(cudaMemsetAsync(s->state, 0, s->state_words * 4, ctx->compute));
     CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
@@ -521,7 +570,7 @@ extern "C" int kv_sketch_read_table(kv_sketch *s, int t, uint8_t *host_out, uint
     KV_TRY(kv_ctx_get(s->device, &ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
-    CU(cudaMemcpyAsync(host_out, s->flat + s->toff[t], nbytes, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(kv_table_d2h(ctx, s, t, 0, host_out, nbytes));
     CU(cudaStreamSynchronize(ctx->compute));
     return KV_OK;
 }
@@ -530,6 +579,7 @@ extern "C" int kv_sketch_write_table(kv_sketch *s, int t, const uint8_t *host_in
 {
     if (!s || t < 0 || t >= s->n_tables || !host_in) return kv_fail(KV_EINVAL, "bad arguments");
     if (nbytes != s->nbytes[t]) return kv_fail(KV_EINVAL, "table %d holds %llu bytes", t, (unsigned long long)s->nbytes[t]);
+    if (s->span) return kv_fail(KV_EINVAL, "raw table writes are not supported on spanning sketches");
     KvCtx *ctx;
     KV_TRY(kv_ctx_get(s->device, &ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -582,6 +632,263 @@ extern "C" int kv_sketch_stats(kv_sketch *s, uint64_t *n_occupied, uint64_t *n_u
     return KV_OK;
 }
 
+// ------------------------------------------------------------------ spanning sketches (SURVEY 8e plan B)
+//
+// A sketch larger than one GPU: every table lives in ONE virtual address range that is mapped on every
+// rank, piece r of each table backed by physical HBM of rank r (CUDA virtual memory management; the
+// pieces are shared between the processes as POSIX file descriptors).  Kernels see an ordinary KvView --
+// a counter load or atomic lands in whichever GPU's HBM holds the page, over NVLink when it is a peer's --
+// so get / novel / save / stats need no sharded variants.  Updates go through the tiled path with the
+// exchange fused into the apply kernel: every rank files the updates of ITS reads under (table, region)
+// in its own slabs, and the apply kernel of the rank that holds a region pulls that region's slab from
+// every rank over NVLink (2 bytes per update) and applies it in shared memory.
+
+struct KvDrv {
+    bool ok = false;
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemExport)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImport)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*MemGetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+};
+
+static KvDrv g_drv;
+
+static int kv_drv_load()
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (g_drv.ok) return KV_OK;
+    struct { const char *name; void **fn; } want[] = {
+        {"cuMemCreate", (void **)&g_drv.MemCreate}, {"cuMemRelease", (void **)&g_drv.MemRelease},
+        {"cuMemExportToShareableHandle", (void **)&g_drv.MemExport}, {"cuMemImportFromShareableHandle", (void **)&g_drv.MemImport},
+        {"cuMemAddressReserve", (void **)&g_drv.MemAddressReserve}, {"cuMemAddressFree", (void **)&g_drv.MemAddressFree},
+        {"cuMemMap", (void **)&g_drv.MemMap}, {"cuMemUnmap", (void **)&g_drv.MemUnmap},
+        {"cuMemSetAccess", (void **)&g_drv.MemSetAccess}, {"cuMemGetAllocationGranularity", (void **)&g_drv.MemGetGranularity},
+    };
+    for (auto &w : want) {
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint(w.name, w.fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !*w.fn) {
+            cudaGetLastError();
+            return kv_fail(KV_ECUDA, "CUDA driver entry point %s is not available", w.name);
+        }
+    }
+    g_drv.ok = true;
+    return KV_OK;
+}
+
+#define CUD(expr)                                                                                         \
+    do {                                                                                                  \
+        CUresult r_ = (expr);                                                                             \
+        if (r_ != CUDA_SUCCESS) return kv_fail(KV_ECUDA, "%s failed with CUresult %d (%s:%d)", #expr, (int)r_, __FILE__, __LINE__); \
+    } while (0)
+
+
+static CUmemAllocationProp kv_span_prop(int device)
+{
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+
+// map rank r's physical allocations: piece r of every table
+static int kv_span_map(kv_sketch *s, int r)
+{
+    KvSpan *sp = s->span;
+    for (int t = 0; t < s->n_tables; t++)
+        CUD(g_drv.MemMap(sp->va + s->toff[t] + (uint64_t)r * sp->piece[t], sp->piece[t], 0, sp->phys[r][t], 0));
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_create_span(int hasher, int bits, int ksize, int n_tables, const uint64_t *sizes, int rank, int world,
+                                     int device, uint64_t chunk_positions, kv_sketch **out, int *mem_fds_out,
+                                     uint8_t xchg_handle_out[128])
+{
+    if (!out || !sizes || !mem_fds_out || !xchg_handle_out) return kv_fail(KV_EINVAL, "null argument");
+    if (hasher != KV_HASH_MURMUR && hasher != KV_HASH_TWOBIT) return kv_fail(KV_EINVAL, "unknown hasher %d", hasher);
+    if (bits != 8 && bits != 4 && bits != 1) return kv_fail(KV_EINVAL, "counter width must be 8, 4 or 1 bits");
+    if (n_tables < 1 || n_tables > KV_TABLES_DEV) return kv_fail(KV_EINVAL, "n_tables must be between 1 and %d", KV_TABLES_DEV);
+    if (world < 1 || world > KV_MAX_RANKS || rank < 0 || rank >= world) return kv_fail(KV_EINVAL, "rank %d of %d", rank, world);
+    int kmax = hasher == KV_HASH_TWOBIT ? KV_MAX_KSIZE_TWOBIT : KV_MAX_KSIZE_MURMUR;
+    if (ksize < 1 || ksize > kmax) return kv_fail(KV_EINVAL, "k-mer size %d not supported (1..%d for this hasher)", ksize, kmax);
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    KV_TRY(kv_drv_load());
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));   // make sure the primary context is current for the driver calls
+    CUmemAllocationProp prop = kv_span_prop(device);
+    size_t gran = 0;
+    CUD(g_drv.MemGetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    if (gran < (2u << 20)) gran = 2u << 20;
+    kv_sketch *s = new kv_sketch();
+    memset(s, 0, sizeof *s);
+    KvSpan *sp = new KvSpan();
+    memset(sp, 0, sizeof *sp);
+    s->span = sp;
+    s->hasher = hasher; s->bits = bits; s->ksize = ksize; s->n_tables = n_tables; s->device = device;
+    s->shard = 0; s->n_shards = 1;
+    sp->rank = rank; sp->world = world;
+    uint64_t va_off = 0;
+    for (int t = 0; t < n_tables; t++) {
+        if (sizes[t] < 1 || sizes[t] >= (1ull << 62)) { delete sp; delete s; return kv_fail(KV_EINVAL, "bad table size"); }
+        s->sizes[t] = s->msizes[t] = sizes[t];
+        s->lo[t] = 0;
+        s->nbytes[t] = kv_table_bytes(bits, sizes[t]);
+        const uint64_t per = (s->nbytes[t] + world - 1) / world;
+        sp->piece[t] = (per + gran - 1) / gran * gran;
+        s->toff[t] = va_off;
+        va_off += sp->piece[t] * (uint64_t)world;
+    }
+    sp->va_bytes = va_off;
+    s->flat_bytes = va_off;
+    for (int t = 0; t < n_tables; t++) {
+        CUresult r = g_drv.MemCreate(&sp->phys[rank][t], sp->piece[t], &prop, 0);
+        if (r != CUDA_SUCCESS)
+            return kv_fail(r == CUDA_ERROR_OUT_OF_MEMORY ? KV_ENOMEM : KV_ECUDA, "cuMemCreate(%llu bytes) failed with CUresult %d",
+                           (unsigned long long)sp->piece[t], (int)r);
+    }
+    sp->have[rank] = true;
+    CUD(g_drv.MemAddressReserve(&sp->va, sp->va_bytes, gran, 0, 0));
+    s->flat = (uint8_t *)sp->va;
+    KV_TRY(kv_span_map(s, rank));
+    {   // my pieces are accessible right away (zero-filled below); the peers' after kv_sketch_span_ready
+        CUmemAccessDesc acc;
+        memset(&acc, 0, sizeof acc);
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        for (int t = 0; t < n_tables; t++)
+            CUD(g_drv.MemSetAccess(sp->va + s->toff[t] + (uint64_t)rank * sp->piece[t], sp->piece[t], &acc, 1));
+    }
+    for (int t = 0; t < n_tables; t++)
+        CU(cudaMemsetAsync(s->flat + s->toff[t] + (uint64_t)rank * sp->piece[t], 0, sp->piece[t], ctx->compute));
+    for (int t = 0; t < n_tables; t++) {
+        int fd = -1;
+        CUD(g_drv.MemExport(&fd, sp->phys[rank][t], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+        mem_fds_out[t] = fd;
+    }
+    // fixed geometry of the tiled update (same on every rank)
+    const int rb = kv_tile_rb_for(ctx, s);
+    uint64_t runs = 0, min_regions = UINT64_MAX;
+    for (int t = 0; t < n_tables; t++) {
+        sp->ti.run_base[t] = (uint32_t)runs;
+        const uint64_t nr = ((sizes[t] - 1) >> rb) + 1;
+        runs += nr;
+        min_regions = std::min(min_regions, nr);
+    }
+    if (runs >= (1ull << 30)) return kv_fail(KV_EINVAL, "too many regions");
+    sp->ti.run_base[n_tables] = sp->ti.run_base[KV_TABLES_DEV] = (uint32_t)runs;
+    sp->runs = (uint32_t)runs;
+    sp->chunk_pos = std::max<uint64_t>(KV_TILE, (chunk_positions ? chunk_positions : ctx->tile_chunk_bases) / KV_TILE * KV_TILE);
+    const double mean = (double)sp->chunk_pos / (double)min_regions;
+    const int blk_log2 = std::max(3, kv_tile_blk_for(ctx, runs));
+    const uint64_t blk = 1ull << blk_log2;
+    uint64_t cap = (uint64_t)(mean * 1.0625 + 8.0 * sqrt(mean) + 64.0);
+    cap = (cap + blk - 1) / blk * blk;
+    sp->ti.rb = rb; sp->ti.cap = (uint32_t)cap; sp->ti.blk_log2 = blk_log2;
+    sp->smem = bits == 1 ? ((size_t)1 << rb) / 8 : ((size_t)1 << rb) * 2;
+    const uint64_t region_bytes = ((uint64_t)1 << rb) * (uint64_t)bits / 8;
+    sp->direct_below = ctx->tile_direct_below >= 0 ? (uint32_t)ctx->tile_direct_below : (uint32_t)std::max<uint64_t>(1, region_bytes / 64);
+    CU(cudaMalloc((void **)&sp->cursor[rank], runs * 4 + 16));
+    CU(cudaMalloc((void **)&sp->slab[rank], runs * cap * 2));
+    sp->ti.cursor = sp->cursor[rank];
+    sp->ti.slab = sp->slab[rank];
+    sp->ti.ovf_any = (unsigned *)(sp->cursor[rank] + runs);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, sp->cursor[rank]));
+    memcpy(xchg_handle_out, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, sp->slab[rank]));
+    memcpy(xchg_handle_out + 64, &h, 64);
+    CU(cudaMalloc((void **)&s->d_unique, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(s->d_unique, 0, sizeof(unsigned long long), ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    s->track_unique = false;   // the order-dependent statistic is defined for one stream of reads
+    s->unique_valid = false;
+    *out = s;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_span_attach(kv_sketch *s, int peer_rank, const int *mem_fds, const uint8_t xchg_handle[128])
+{
+    if (!s || !s->span || !xchg_handle || !mem_fds) return kv_fail(KV_EINVAL, "not a spanning sketch");
+    KvSpan *sp = s->span;
+    if (peer_rank < 0 || peer_rank >= sp->world || peer_rank == sp->rank || sp->have[peer_rank])
+        return kv_fail(KV_EINVAL, "bad or repeated peer rank %d", peer_rank);
+    CU(cudaSetDevice(s->device));
+    for (int t = 0; t < s->n_tables; t++)
+        CUD(g_drv.MemImport(&sp->phys[peer_rank][t], (void *)(uintptr_t)mem_fds[t], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    sp->have[peer_rank] = true;
+    KV_TRY(kv_span_map(s, peer_rank));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, xchg_handle, 64);
+    CU(cudaIpcOpenMemHandle((void **)&sp->cursor[peer_rank], h, cudaIpcMemLazyEnablePeerAccess));
+    memcpy(&h, xchg_handle + 64, 64);
+    CU(cudaIpcOpenMemHandle((void **)&sp->slab[peer_rank], h, cudaIpcMemLazyEnablePeerAccess));
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_span_ready(kv_sketch *s)
+{
+    if (!s || !s->span) return kv_fail(KV_EINVAL, "not a spanning sketch");
+    KvSpan *sp = s->span;
+    for (int r = 0; r < sp->world; r++)
+        if (!sp->have[r]) return kv_fail(KV_EINVAL, "rank %d is not attached yet", r);
+    CU(cudaSetDevice(s->device));
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = s->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CUD(g_drv.MemSetAccess(sp->va, sp->va_bytes, &acc, 1));
+    sp->ready = true;
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_span_info(const kv_sketch *s, int *rank, int *world, uint64_t *piece_bytes, uint64_t *chunk_positions)
+{
+    if (!s || !s->span) return kv_fail(KV_EINVAL, "not a spanning sketch");
+    if (rank) *rank = s->span->rank;
+    if (world) *world = s->span->world;
+    if (chunk_positions) *chunk_positions = s->span->chunk_pos;
+    if (piece_bytes) for (int t = 0; t < s->n_tables; t++) piece_bytes[t] = s->span->piece[t];
+    return KV_OK;
+}
+
+// unmap + release everything that is not plain cudaMalloc memory (called by kv_sketch_destroy)
+static void kv_span_free(kv_sketch *s)
+{
+    KvSpan *sp = s->span;
+    if (!sp) return;
+    for (int r = 0; r < sp->world; r++) {
+        if (r != sp->rank) {
+            if (sp->cursor[r]) cudaIpcCloseMemHandle(sp->cursor[r]);
+            if (sp->slab[r]) cudaIpcCloseMemHandle(sp->slab[r]);
+        }
+        if (sp->have[r] && g_drv.ok) {
+            for (int t = 0; t < s->n_tables; t++) {
+                g_drv.MemUnmap(sp->va + s->toff[t] + (uint64_t)r * sp->piece[t], sp->piece[t]);
+                g_drv.MemRelease(sp->phys[r][t]);
+            }
+        }
+    }
+    if (sp->va && g_drv.ok) g_drv.MemAddressFree(sp->va, sp->va_bytes);
+    if (sp->cursor[sp->rank]) cudaFree(sp->cursor[sp->rank]);
+    if (sp->slab[sp->rank]) cudaFree(sp->slab[sp->rank]);
+    delete sp;
+    s->span = nullptr;
+    s->flat = nullptr;
+}
+
 // ------------------------------------------------------------------ OXLI v4 I/O
 
 extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
@@ -613,7 +920,7 @@ extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
         fwrite(&s->sizes[t], 8, 1, f);
         for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
             size_t n = (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o);
-            if (cudaMemcpyAsync(stage, s->flat + s->toff[t] + o, n, cudaMemcpyDeviceToHost, ctx->compute) != cudaSuccess ||
+            if (kv_table_d2h(ctx, s, t, o, stage, n) != cudaSuccess ||
                 cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "D2H copy failed"); break; }
             if (fwrite(stage, 1, n, f) != n) { rc = kv_fail(KV_EIO, "short write to %s", path); break; }
         }
@@ -1003,6 +1310,11 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
 {
     if (!n) return KV_OK;
     KvView v = kv_view(s);
+    if (s->span) {   // no hot bitmap, no n_unique: the exact update for every hash (add(), mask building ... -- small inputs)
+        if (dist_counts) return kv_fail(KV_EINVAL, "abundance distribution is not defined on spanning sketches");
+        LAUNCH_C(KV_PROF_INCREMENT, ctx, kv_add_exact_kernel, kv_grid_for(ctx, n), 256, v, d_hashes, d_valid, n);
+        return KV_OK;
+    }
     if (s->state_stale) {
         KV_TRY(kv_state_rebuild_locked(ctx, s));
         s->state_stale = false;
@@ -1044,6 +1356,29 @@ static int kv_apply_hashes(KvCtx *ctx, kv_sketch *s, const uint64_t *d_hashes, c
 
 // ---- K3c: tiled update path
 
+// Region size: 2^rb buckets, the configured value for large tables; small tables get smaller regions so that
+// every table still has thousands of runs (few runs = the cursor atomics of a whole chunk pile onto few words).
+static int kv_tile_rb_for(const KvCtx *ctx, const kv_sketch *s)
+{
+    if (s->bits == 1) return 16;
+    uint64_t smallest = UINT64_MAX;
+    for (int t = 0; t < s->n_tables; t++)
+        if (s->sizes[t]) smallest = std::min(smallest, s->sizes[t]);
+    int rb = ctx->tile_rb;
+    while (rb > 8 && (smallest >> rb) < 8192) rb--;
+    return rb;
+}
+
+// Slab interleave block: the write frontier (runs x block x 2 bytes) should stay well inside L2, or the
+// 2-byte stores reach HBM as partial sectors.
+static int kv_tile_blk_for(const KvCtx *ctx, uint64_t runs)
+{
+    if (ctx->tile_block_log2 < 0) return ctx->tile_block_log2;
+    int blk = ctx->tile_block_log2;
+    while (blk > 3 && ((runs << blk) * 2) > (24ull << 20)) blk--;
+    return blk;
+}
+
 struct KvTilePlan {
     bool on;
     KvTileInfo ti;
@@ -1056,9 +1391,18 @@ struct KvTilePlan {
 static int kv_tile_plan(KvCtx *ctx, const kv_sketch *s, uint64_t batch_pos, KvTilePlan *pl)
 {
     memset(pl, 0, sizeof *pl);
+    if (s->span) {   // fixed at creation: every rank must use the same geometry and the exported buffers
+        pl->on = true;
+        pl->ti = s->span->ti;
+        pl->runs = s->span->runs;
+        pl->smem = s->span->smem;
+        pl->direct_below = s->span->direct_below;
+        pl->chunk_tiles = s->span->chunk_pos / KV_TILE;
+        return KV_OK;
+    }
     bool on = ctx->update_path == 3 || (ctx->update_path == 0 && s->flat_bytes >= ctx->tile_min_bytes);
     if (!on) return KV_OK;
-    const int rb = s->bits == 1 ? 16 : ctx->tile_rb;
+    const int rb = kv_tile_rb_for(ctx, s);
     uint64_t runs = 0, min_regions = UINT64_MAX;
     for (int t = 0; t < s->n_tables; t++) {
         pl->ti.run_base[t] = (uint32_t)runs;
@@ -1075,7 +1419,8 @@ static int kv_tile_plan(KvCtx *ctx, const kv_sketch *s, uint64_t batch_pos, KvTi
     // inputs) is updated in place by the producer
     const double mean = (double)chunk_pos / (double)min_regions;
     uint64_t cap = (uint64_t)(mean * 1.0625 + 8.0 * sqrt(mean) + 64.0);
-    const uint64_t blk = ctx->tile_block_log2 >= 0 ? (1ull << ctx->tile_block_log2) : 16;
+    const int blk_log2 = kv_tile_blk_for(ctx, runs);
+    const uint64_t blk = blk_log2 >= 0 ? (1ull << blk_log2) : 16;
     cap = (cap + blk - 1) / blk * blk;
     if (cap >= 0xffffffffull) return KV_OK;
     KV_TRY(kv_buf_ensure(ctx->tile_cursor, runs * 4 + 16));
@@ -1085,7 +1430,7 @@ static int kv_tile_plan(KvCtx *ctx, const kv_sketch *s, uint64_t batch_pos, KvTi
     pl->ti.cap = (uint32_t)cap;
     pl->ti.cursor = (uint32_t *)ctx->tile_cursor.p;
     pl->ti.slab = (uint16_t *)ctx->tile_slab.p;
-    pl->ti.blk_log2 = ctx->tile_block_log2;
+    pl->ti.blk_log2 = blk_log2;
     pl->ti.ovf_any = (unsigned *)((uint32_t *)ctx->tile_cursor.p + runs);   // cleared together with the cursors
     if (s->track_unique) {
         pl->ti.ovf_stride = chunk_pos / 32 + 1;
@@ -1100,15 +1445,34 @@ static int kv_tile_plan(KvCtx *ctx, const kv_sketch *s, uint64_t batch_pos, KvTi
     return KV_OK;
 }
 
-template <int BITS>
-static int kv_launch_tile_apply(KvCtx *ctx, const KvView &v, const KvTilePlan &pl)
+template <int BITS, bool SPAN>
+static int kv_launch_tile_apply2(KvCtx *ctx, const KvView &v, const KvTilePlan &pl, const KvTileSources &src)
 {
     static bool configured = false;
     if (!configured) {
-        CU(cudaFuncSetAttribute(kv_tile_apply_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CU(cudaFuncSetAttribute(kv_tile_apply_kernel<BITS, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         configured = true;
     }
-    return kv_launch_smem(ctx, KV_PROF_INCREMENT, kv_tile_apply_kernel<BITS>, pl.runs, KV_TILE_THREADS, pl.smem, v, pl.ti, pl.direct_below);
+    return kv_launch_smem(ctx, KV_PROF_INCREMENT, kv_tile_apply_kernel<BITS, SPAN>, pl.runs, KV_TILE_THREADS, pl.smem, v, pl.ti, pl.direct_below, src);
+}
+
+static int kv_launch_tile_apply(KvCtx *ctx, const kv_sketch *s, const KvView &v, const KvTilePlan &pl)
+{
+    KvTileSources src;
+    memset(&src, 0, sizeof src);
+    src.n = 1;
+    if (s->span) {
+        src.n = s->span->world;
+        src.rank = s->span->rank;
+        for (int r = 0; r < s->span->world; r++) { src.cursor[r] = s->span->cursor[r]; src.slab[r] = s->span->slab[r]; }
+        for (int t = 0; t < s->n_tables; t++) src.piece[t] = s->span->piece[t];
+        if (s->bits == 8) return kv_launch_tile_apply2<8, true>(ctx, v, pl, src);
+        if (s->bits == 4) return kv_launch_tile_apply2<4, true>(ctx, v, pl, src);
+        return kv_launch_tile_apply2<1, true>(ctx, v, pl, src);
+    }
+    if (s->bits == 8) return kv_launch_tile_apply2<8, false>(ctx, v, pl, src);
+    if (s->bits == 4) return kv_launch_tile_apply2<4, false>(ctx, v, pl, src);
+    return kv_launch_tile_apply2<1, false>(ctx, v, pl, src);
 }
 
 static int kv_check_mask(const kv_sketch *s, const kv_sketch *mask)
@@ -1120,14 +1484,20 @@ static int kv_check_mask(const kv_sketch *s, const kv_sketch *mask)
     return KV_OK;
 }
 
-extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
-                                int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
-                                int consume_masked, uint64_t *n_kmers_out)
+struct kv_peer_sync;
+static int kv_peer_barrier_locked(KvCtx *ctx, kv_peer_sync *ps);
+
+// span_sync != NULL: `s` is a spanning sketch and the call is COLLECTIVE -- every rank runs exactly
+// n_chunks chunks (empty ones when its batch is shorter), with two device-side rank barriers per chunk
+static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                           int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
+                           int consume_masked, uint64_t *n_kmers_out, kv_peer_sync *span_sync, uint64_t n_chunks)
 {
     if (!s) return kv_fail(KV_EINVAL, "null sketch");
     if (n_kmers_out) *n_kmers_out = 0;
-    if (n_reads == 0) return KV_OK;
-    if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
+    if (s->span && !span_sync) return kv_fail(KV_EINVAL, "spanning sketches are updated with kv_consume_batch_span (collective)");
+    if (n_reads == 0 && !span_sync) return KV_OK;
+    if (n_reads && (!bases || !offsets)) return kv_fail(KV_EINVAL, "null batch pointers");
     KV_TRY(kv_check_mask(s, mask));
     uint64_t lo = 0, hi = 0;
     if (num_bands > 0) KV_TRY(kv_band_interval(num_bands, band, &lo, &hi));
@@ -1136,8 +1506,9 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     KvBatch b;
-    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
-    if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
+    memset(&b, 0, sizeof b);
+    if (n_reads) KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+    if (b.total == 0 && !span_sync) { kv_stage_done(ctx, &b); return KV_OK; }
     CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
 
     KvTilePlan plan;
@@ -1151,7 +1522,20 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
     if (need_hashes) KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
     KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
     const KvView sv = kv_view(s);
-    for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
+    const uint64_t own_chunks = (b.n_tiles + chunk_tiles - 1) / chunk_tiles;
+    if (span_sync && own_chunks > n_chunks)
+        return kv_fail(KV_EINVAL, "this rank's batch needs %llu chunks, the collective call announced %llu",
+                       (unsigned long long)own_chunks, (unsigned long long)n_chunks);
+    const uint64_t total_chunks = span_sync ? n_chunks : own_chunks;
+    for (uint64_t ci = 0; ci < total_chunks; ci++) {
+        const uint64_t t0 = ci * chunk_tiles;
+        if (t0 >= b.n_tiles) {   // collective call, nothing left here: take part in the exchange with empty slabs
+            CU(cudaMemsetAsync(plan.ti.cursor, 0, (size_t)plan.runs * 4 + 4, ctx->compute));
+            KV_TRY(kv_peer_barrier_locked(ctx, span_sync));
+            KV_TRY(kv_launch_tile_apply(ctx, s, sv, plan));
+            KV_TRY(kv_peer_barrier_locked(ctx, span_sync));
+            continue;
+        }
         uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
         uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
         KvHashParams p;
@@ -1189,9 +1573,9 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
             LAUNCH_C(KV_PROF_FIXUP, ctx, kv_tile_overflow_kernel, kv_grid_for(ctx, npos / 32 + 1), 256, sv, plan.ti, p.hashes, npos);
         } else
             s->unique_valid = false;
-        if (s->bits == 8) KV_TRY(kv_launch_tile_apply<8>(ctx, sv, plan));
-        else if (s->bits == 4) KV_TRY(kv_launch_tile_apply<4>(ctx, sv, plan));
-        else KV_TRY(kv_launch_tile_apply<1>(ctx, sv, plan));
+        if (span_sync) KV_TRY(kv_peer_barrier_locked(ctx, span_sync));   // every rank has filed this chunk's updates
+        KV_TRY(kv_launch_tile_apply(ctx, s, sv, plan));
+        if (span_sync) KV_TRY(kv_peer_barrier_locked(ctx, span_sync));   // every rank has read my slabs: they may be refilled
         s->state_stale = true;   // the hot bitmap of the in-place path is not maintained here
     }
     kv_stage_done(ctx, &b);
@@ -1201,6 +1585,24 @@ extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64
         *n_kmers_out = ctx->h_counters[0];
     }
     return KV_OK;
+}
+
+extern "C" int kv_consume_batch(kv_sketch *s, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                                int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
+                                int consume_masked, uint64_t *n_kmers_out)
+{
+    return kv_consume_impl(s, bases, offsets, n_reads, where, num_bands, band, mask, mask_threshold, consume_masked, n_kmers_out,
+                           nullptr, 0);
+}
+
+extern "C" int kv_consume_batch_span(kv_sketch *s, kv_peer_sync *ps, const uint8_t *bases, const uint64_t *offsets,
+                                     uint64_t n_reads, int where, uint64_t n_chunks, int num_bands, int band,
+                                     const kv_sketch *mask, int mask_threshold, int consume_masked, uint64_t *n_kmers_out)
+{
+    if (!s || !s->span || !s->span->ready) return kv_fail(KV_EINVAL, "not a (ready) spanning sketch");
+    if (!ps) return kv_fail(KV_EINVAL, "a spanning update needs the device-side rank barrier (kv_peer_sync)");
+    return kv_consume_impl(s, bases, offsets, n_reads, where, num_bands, band, mask, mask_threshold, consume_masked, n_kmers_out,
+                           ps, n_chunks);
 }
 
 // ------------------------------------------------------------------ novel
@@ -1783,6 +2185,20 @@ extern "C" int kv_peer_sync_connect(kv_peer_sync *ps, int peer_rank, const uint8
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     CU(cudaIpcOpenMemHandle(&ps->peer[peer_rank], h, cudaIpcMemLazyEnablePeerAccess));
+    return KV_OK;
+}
+
+static int kv_peer_barrier_locked(KvCtx *ctx, kv_peer_sync *ps)
+{
+    KvPeerFlags f;
+    memset(&f, 0, sizeof f);
+    for (int p = 0; p < ps->world; p++) {
+        if (p != ps->rank && !ps->peer[p]) return kv_fail(KV_EINVAL, "peer %d is not connected", p);
+        f.peer[p] = (uint32_t *)ps->peer[p];
+    }
+    f.mine = ps->flags; f.rank = ps->rank; f.world = ps->world;
+    ps->epoch++;
+    LAUNCH_C(KV_PROF_MERGE, ctx, kv_peer_barrier_kernel, 1, 32, f, ps->epoch, ps->timeout_ns, ps->timed_out);
     return KV_OK;
 }
 

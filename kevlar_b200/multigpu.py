@@ -485,3 +485,152 @@ def novel_batch_sharded(cases, ctrls, bases, offsets, case_min, ctrl_max, screen
             continue
         check(rc)
         return hits[:n.value], flags[:n_reads], discard[:n_reads]
+
+
+# ----------------------------------------------------------------------------------------------
+# Plan B, second design: spanning sketches.  Every table is ONE virtual address range mapped on every rank,
+# piece r in the HBM of rank r (CUDA VMM, include/kvsketch.h: kv_sketch_create_span).  Reads stay sharded;
+# what crosses NVLink per update is a 2-byte offset (pulled by the rank that owns the region, inside the
+# kernel that applies it) instead of an 8-byte hash broadcast to every rank; queries are plain loads
+# that land in whichever GPU holds the page, so khmer.novel_batch, get, save, n_occupied work unchanged.
+
+def _exchange_fds(my_fds, group=None):
+    """All-to-all exchange of file descriptors between the ranks of one node (SCM_RIGHTS over Unix
+    sockets).  Returns {rank: [fds]} for every peer."""
+    import socket
+    import struct
+    import uuid
+    td = dist()
+    world, rank = td.get_world_size(group), td.get_rank(group)
+    tag = [uuid.uuid4().hex if rank == 0 else None]
+    td.broadcast_object_list(tag, src=0, group=group)
+    path = lambda r: '/tmp/kvspan_{}_{}.sock'.format(tag[0], r)   # noqa: E731
+    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    server.bind(path(rank))
+    server.listen(world)
+    td.barrier(group=group)
+    try:
+        for p in range(world):
+            if p == rank:
+                continue
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(path(p))
+            socket.send_fds(c, [struct.pack('i', rank)], list(my_fds))
+            c.close()
+        got = {}
+        for _ in range(world - 1):
+            conn, _ = server.accept()
+            msg, fds, _, _ = socket.recv_fds(conn, 16, len(my_fds))
+            got[struct.unpack('i', msg[:4])[0]] = list(fds)
+            conn.close()
+    finally:
+        server.close()
+        td.barrier(group=group)
+        os.unlink(path(rank))
+    return got
+
+
+class SpanningSketch(object):
+    """A khmer-style sketch whose tables span the HBM of all ranks of `group`.  `.sketch` is an ordinary
+    kevlar_b200.khmer sketch object for everything that reads (get, novel_batch, save, n_occupied, ...);
+    `consume_batch`, `clear` and `close` are COLLECTIVE."""
+
+    def __init__(self, cls, ksize, starting_size, n_tables, primes=None, group=None, chunk_positions=0):
+        td = dist()
+        self.group = group
+        self.world = td.get_world_size(group) if td.is_initialized() else 1
+        self.rank = td.get_rank(group) if td.is_initialized() else 0
+        sizes = [int(p) for p in primes] if primes else _lib.primes_below(int(starting_size), int(n_tables))
+        arr = (c_uint64 * len(sizes))(*sizes)
+        handle, fds, xchg = c_void_p(), (c_int * len(sizes))(), (ctypes.c_uint8 * 128)()
+        device = _lib.current_device()
+        check(lib().kv_sketch_create_span(cls._hasher, cls._bits, int(ksize), len(sizes), arr, self.rank, self.world, device,
+                                          int(chunk_positions), byref(handle), fds, xchg))
+        self.sketch = cls(0, 0, 0, _handle=handle)
+        if self.world > 1:
+            peer_fds = _exchange_fds(list(fds), group)
+            handles = [None] * self.world
+            td.all_gather_object(handles, bytes(xchg), group=group)
+            for r in range(self.world):
+                if r != self.rank:
+                    check(lib().kv_sketch_span_attach(handle, r, (c_int * len(sizes))(*peer_fds[r]),
+                                                      (ctypes.c_uint8 * 128)(*handles[r])))
+                    for f in peer_fds[r]:
+                        os.close(f)
+        for f in fds:
+            os.close(f)
+        check(lib().kv_sketch_span_ready(handle))
+        chunk = c_uint64()
+        check(lib().kv_sketch_span_info(handle, None, None, None, byref(chunk)))
+        self.chunk_positions = chunk.value
+        if self.world > 1:
+            self._sync = _peer_sync(device, group)
+            td.barrier(group=group)
+        else:   # a one-rank "collective": same code path, the barriers have nobody to wait for
+            ps, unused = c_void_p(), (ctypes.c_uint8 * 64)()
+            check(lib().kv_peer_sync_create(device, 0, 1, byref(ps), unused))
+            self._sync = ps
+
+    def ksize(self):
+        return self.sketch.ksize()
+
+    def hashsizes(self):
+        return self.sketch.hashsizes()
+
+    def n_occupied(self):
+        return self.sketch.n_occupied()
+
+    def save(self, filename):
+        """One ordinary OXLI file, written by rank 0 (it reads the peers' pieces over NVLink)."""
+        td = dist()
+        if self.rank == 0:
+            self.sketch.save(filename)
+        if self.world > 1:
+            td.barrier(group=self.group)
+
+    def clear(self):
+        self.sketch.clear()
+        if self.world > 1:
+            _lib.sync(self.sketch.device)
+            dist().barrier(group=self.group)
+
+    def consume_batch(self, bases, offsets, num_bands=None, band=None, mask=None, threshold=0, consume_masked=False,
+                      where=_lib.MEM_HOST, n_positions=None):
+        """Count THIS rank's reads; afterwards the sketch has seen the reads of all ranks.  Returns the number
+        of k-mers counted by all ranks."""
+        import torch
+        td = dist()
+        if where == _lib.MEM_HOST:
+            bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+            bptr, optr, n_reads, n_pos = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, len(bases)
+        else:
+            bptr, (optr, n_reads) = bases, offsets
+            n_pos = int(n_positions)
+        mine = -(-((n_pos + 1023) // 1024 * 1024) // self.chunk_positions)
+        dev = torch.device('cuda', self.sketch.device)
+        chunks = torch.tensor([mine], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            td.all_reduce(chunks, op=td.ReduceOp.MAX, group=self.group)
+        n = c_uint64()
+        check(lib().kv_consume_batch_span(self.sketch._h, self._sync, bptr, optr, n_reads, where, int(chunks.item()),
+                                          int(num_bands or 0), int(band or 0), mask._h if mask is not None else None,
+                                          int(threshold), int(bool(consume_masked)), byref(n)))
+        if self.world == 1:
+            return n.value
+        total = torch.tensor([n.value], dtype=torch.int64, device=dev)
+        td.all_reduce(total, op=td.ReduceOp.SUM, group=self.group)
+        return int(total.item())
+
+    def close(self):
+        """COLLECTIVE: nobody touches the sketch any more; unmap and free everywhere."""
+        if self.sketch is None:
+            return
+        _lib.sync(self.sketch.device)
+        if self.world > 1:
+            dist().barrier(group=self.group)
+        self.sketch = None   # kv_sketch_destroy: unmaps the peers' pieces, frees mine
+        if self.world > 1:
+            dist().barrier(group=self.group)
+        else:
+            lib().kv_peer_sync_destroy(self._sync)
+        self._sync = None

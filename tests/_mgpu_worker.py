@@ -35,7 +35,8 @@ def main():
     samples = [reads(child, 6000, 1) + [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT'] * 700, reads(genome, 6000, 2),
                reads(genome, 6000, 3)]
     failures = []
-    for how in ('allreduce', 'allgather', 'p2p', 'p2p_host'):
+    only = os.environ.get('KV_MGPU_ONLY', '')
+    for how in (() if only else ('allreduce', 'allgather', 'p2p', 'p2p_host')):
         for cls in ('Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'):
             gpu, cpu = [], []
             for seqs in samples:
@@ -70,10 +71,75 @@ def main():
             multigpu.peer_sync_status()
             multigpu.release_p2p(gpu)   # collective: unmap everywhere, barrier, only then free
             del gpu
-    multigpu.release_peer_sync()
-    # ---- plan B: bin-range-sharded sketches: count shard-local reads, exchange hashes, save one file
     import tempfile
     shared = os.environ.get('KV_TEST_SHARED_DIR') or tempfile.gettempdir()
+    # ---- plan B, second design: spanning sketches (tables spread over the HBM of all ranks, updates exchanged
+    # inside the tiled apply kernel, queries as plain loads over NVLink).  Tables of 20 M buckets so that several
+    # ranks hold pieces; banded and masked counts; the saved file, n_occupied and the shard-local novel scan
+    # must equal the single-process oracle.
+    for cls in ('Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'):
+        span, cpu = [], []
+        for si, seqs in enumerate(samples):
+            bases, offs = ko.reads_to_batch(seqs)
+            mb, mo = multigpu.shard_batch(bases, offs, rank, world)
+            sk = multigpu.SpanningSketch(getattr(kv.khmer, cls), 25, 20000003, 4, chunk_positions=131072)
+            c = getattr(ko, cls)(25, 20000003, 4)
+            bands = (3, 1) if si == 2 else (None, None)
+            n_span = sk.consume_batch(mb, mo, num_bands=bands[0], band=bands[1])
+            n_cpu = c.consume_batch(bases, offs, num_bands=bands[0] or 0, band=bands[1] or 0)
+            if n_span != n_cpu:
+                failures.append('spanning {} k-mer count {} != {}'.format(cls, n_span, n_cpu))
+            if sk.n_occupied() != c.n_occupied():
+                failures.append('spanning {} n_occupied {} != {}'.format(cls, sk.n_occupied(), c.n_occupied()))
+            for t in range(4):   # every rank reads the whole table through its own mapping
+                if sk.sketch.table_bytes(t) != c.table_bytes(t):
+                    failures.append('spanning {} sample {} table {} differs on rank {}'.format(cls, si, t, rank))
+            path = os.path.join(shared, 'kv_span_{}_{}.sketch'.format(cls, si))
+            sk.save(path)
+            if rank == 0:
+                ref = path + '.oracle'
+                c.save(ref)
+                if open(path, 'rb').read() != open(ref, 'rb').read():
+                    failures.append('spanning {} sample {}: saved file differs from the oracle file'.format(cls, si))
+                os.remove(ref)
+                os.remove(path)
+            span.append(sk)
+            cpu.append(c)
+        if cls in ('Counttable', 'Countgraph'):
+            bases, offs = ko.reads_to_batch(samples[0])
+            mb, mo = multigpu.shard_batch(bases, offs, rank, world)
+            lo, _ = multigpu.shard_bounds(len(samples[0]), rank, world)
+            hits, flags, _ = kv.khmer.novel_batch([span[0].sketch], [s.sketch for s in span[1:]], mb, mo, 6, 1)
+            allhits = multigpu.gather_hits(hits, lo)
+            ohits, _ = ko.novel_batch(cpu[:1], cpu[1:], bases, offs, 6, 1)
+            allhits = allhits[np.lexsort((allhits['offset'], allhits['read']))]
+            same = len(allhits) == len(ohits) and (allhits['read'] == ohits['read']).all() and \
+                (allhits['offset'] == ohits['offset']).all() and (allhits['abund'][:, :3] == ohits['abund'][:, :3]).all()
+            if not same or len(ohits) == 0:
+                failures.append('spanning {} novel hits differ ({} vs {})'.format(cls, len(allhits), len(ohits)))
+            # a second batch on top (clear, then two halves == one batch)
+            span[0].clear()
+            half = len(mo) // 2
+            span[0].consume_batch(mb[:int(mo[half])], mo[:half + 1])
+            span[0].consume_batch(mb[int(mo[half]):], mo[half:] - mo[half])
+            for t in range(4):
+                if span[0].sketch.table_bytes(t) != cpu[0].table_bytes(t):
+                    failures.append('spanning {} two-batch table {} differs'.format(cls, t))
+        for sk in span:
+            sk.close()
+        del span
+    if only == 'span':
+        multigpu.release_peer_sync()
+        torch.distributed.barrier()
+        if failures:
+            print('RANK', rank, 'FAILURES:', failures)
+            sys.exit(1)
+        if rank == 0:
+            print('spanning sketches OK on', world, 'ranks')
+        torch.distributed.destroy_process_group()
+        return
+    multigpu.release_peer_sync()
+    # ---- plan B: bin-range-sharded sketches: count shard-local reads, exchange hashes, save one file
     for cls in ('Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'):
         sharded, cpu = [], []
         for si, seqs in enumerate(samples):
@@ -119,7 +185,7 @@ def main():
         sys.exit(1)
     if rank == 0:
         print('multi-GPU merge OK on', world, 'ranks: allreduce/allgather/p2p/p2p_host x 4 sketch types, novel hits identical; '
-              'bin-range-sharded count / save / novel identical to the oracle')
+              'spanning and bin-range-sharded count / save / novel identical to the oracle')
     torch.distributed.destroy_process_group()
 
 

@@ -1089,3 +1089,61 @@ def test_synth_reads_fixture(kv):
         if any(read in t or read.translate(comp)[::-1] in t for t in text):
             exact += 1
     assert 80 <= exact < 200   # (1 - 0.005)^100 = 61 % of the reads are error-free in expectation
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Nodetable'])
+def test_spanning_sketch_single_rank(kv, oracle, tmp_path, name):
+    """A spanning sketch (CUDA virtual-memory tables + the collective tiled update) on ONE rank: the
+    degenerate case of tests/_mgpu_worker.py, so that the allocation, the multi-source apply kernel
+    and save / get / novel on such a sketch are covered on a single-GPU box too."""
+    from kevlar_b200 import multigpu
+    reads = random_reads(21, 3000, 40, 150) + [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT'] * 500
+    bases, offs = oracle.reads_to_batch(reads)
+    sk = multigpu.SpanningSketch(getattr(kv.khmer, name), 21, 3000017, 4, chunk_positions=65536)
+    c = getattr(oracle, name)(21, 3000017, 4)
+    assert sk.consume_batch(bases, offs) == c.consume_batch(bases, offs)
+    for t in range(4):
+        assert sk.sketch.table_bytes(t) == c.table_bytes(t)
+    assert sk.n_occupied() == c.n_occupied()
+    kmer = 'ACGTTGCAAGGCTTAACCGGT'
+    assert sk.sketch.get(kmer) == c.get(kmer) > 0
+    sk.sketch.add(kmer)
+    c.add(kmer)
+    assert sk.sketch.get(kmer) == c.get(kmer)
+    path = str(tmp_path / 'span.sketch')
+    sk.save(path)
+    c.save(path + '.o')
+    assert open(path, 'rb').read() == open(path + '.o', 'rb').read()
+    sk.clear()
+    assert sk.n_occupied() == 0
+    sk.close()
+
+
+def _bands_namespace(kv, prefix, **over):
+    from kevlar_b200 import bands
+    na = [golden_data('microtrios/trio-na-{}.fq.gz'.format(w)) for w in ('proband', 'mother', 'father')]
+    argv = ['--case', na[0], '--control', na[1], '--control', na[2], '-k', '31', '--memory', '500K', '--case-min', '5',
+            '--ctrl-max', '1', '--num-bands', '8', '-n', '1', '--filter-memory', '1M', '--out-prefix', prefix]
+    ns = bands.parser().parse_args(argv)
+    for key, val in over.items():
+        setattr(ns, key, val)
+    return ns
+
+
+def test_banded_chain_matches_reference(kv, tmp_path):
+    """BASELINE config 5's chain on one GPU: `novel --num-bands 8 --band b` for b = 1..8, `unband`, `filter`
+    recount -- every intermediate file equal to what the reference's own modules produce over the oracle
+    (tests/golden/make_golden_bands.py).  The reference's band quirk makes the union of the bands differ
+    from an unbanded run, so the pin is the reference chain, band by band."""
+    from kevlar_b200 import bands
+    prefix = str(tmp_path / 'chain')
+    kv.logstream = io.StringIO()
+    try:
+        result = bands.run(_bands_namespace(kv, prefix), rank=0, world=1)
+    finally:
+        kv.logstream = None
+    for b in range(1, 9):
+        assert open('{}.band{}.augfastq'.format(prefix, b)).read() == open(golden_gen('bands8_band{}.out'.format(b))).read(), b
+    assert open(result['unband']).read() == open(golden_gen('bands8_unband.out')).read()
+    assert open(result['filter']).read() == open(golden_gen('bands8_filter.out')).read()
+    assert open(result['filter']).read().count('@') >= 10

@@ -513,3 +513,31 @@ def test_simlike_host_logic_against_reference_outputs(oracle):
         got = spanning_kmer_abundances(c['alt'], c['refr'], sk[0], sk[1:-1], sk[-1], dropoutliers=c['dropoutliers'])
         assert got == (c['abundances'], c['refr_abunds'], c['ndropped'])
     assert discard_outlier_abunds([10, 11, 12, 90], [[1, 1, 1, 1], [0, 40, 0, 0]]) == ([11, 12], [[1, 1, 1, 1], [0, 0, 0]])
+
+
+def test_band_assignment_covers_every_band_once():
+    """Config 5 driver: band b runs on rank (b-1) mod world -- every band exactly once for any world size."""
+    from kevlar_b200 import bands
+    for num_bands in (1, 2, 8, 16, 23):
+        for world in (1, 2, 3, 8):
+            got = sorted(b for r in range(world) for b in bands.band_of_rank(num_bands, r, world))
+            assert got == list(range(1, num_bands + 1))
+    ns = bands.parser().parse_args(['--case', 'a.fq', 'b.fq', '--control', 'c.fq', '--num-bands', '4', '--out-prefix', 'x'])
+    argv = bands.novel_band_args(ns, 3, 'x.band3.augfastq')
+    assert argv[:1] == ['novel'] and argv[argv.index('--band') + 1] == '3' and argv[argv.index('--case') + 1:][:2] == ['a.fq', 'b.fq']
+
+
+def test_simtrio_piecewise_haplotypes_equal_sequential():
+    """The measurement fixture builds haplotypes from pieces in one pass; for the benchmark trio (1 Mbp) the
+    result must be what the original edit-by-edit construction gave, so the C2 workload is unchanged."""
+    from kevlar_b200 import simtrio
+    new = simtrio.trio_haplotypes(1000000)
+    piecewise = simtrio._apply
+    simtrio._apply = simtrio._apply_sequential
+    try:
+        old = simtrio.trio_haplotypes(1000000)
+    finally:
+        simtrio._apply = piecewise
+    for a, b in zip(new, old):
+        for x, y in zip(a, b):
+            assert len(x) == len(y) and (x == y).all()
