@@ -71,9 +71,12 @@ def parse_args():
     ap.add_argument('--c3-memory', type=float, default=C3_MEMORY)
     ap.add_argument('--c3-steps', type=int, default=2)
     ap.add_argument('--c3-no-parity', action='store_true')
+    ap.add_argument('--c5', action='store_true', help='also time the banded chain (8 bands + unband + filter) over FASTQ files; default at N>1')
+    ap.add_argument('--no-c5', action='store_true')
     ap.add_argument('--c4', action='store_true', help='also run the config-4-shaped part: 4-bit spanning sketches across all GPUs')
     ap.add_argument('--c4-gb-per-gpu', type=float, default=16.0, help='GB of each of the 3 sketches held per GPU')
     ap.add_argument('--c4-reads', type=int, default=C3_READS, help='reads per sample (all ranks together)')
+    ap.add_argument('--c4-chunk', type=int, default=1 << 30, help='positions per rank and exchange round of the spanning update')
     return ap.parse_args()
 
 
@@ -382,17 +385,14 @@ class GpuTrio(object):
         khmer = self.khmer
         for sk in self.sketches:
             sk.clear()
-        for i, sk in enumerate(self.sketches):
-            if resident:
-                b, o = self.dev[i]
-                sk.consume_batch(b.data_ptr(), (o.data_ptr(), o.numel() - 1), where=khmer.MEM_DEVICE, wait=False)
-            else:
-                b, o = self.pinned[i]
-                sk.consume_batch(b.numpy(), o.numpy().view(np.uint64), wait=False)
-        if self.world > 1:
-            if self.args.merge != 'p2p':   # NCCL runs on torch's stream; 'p2p' stays on the library's own stream
-                self.lib.sync(self.device)
-            self.multigpu.merge_sketches(self.sketches, how=self.args.merge)
+        if resident:
+            batches = [(b.data_ptr(), (o.data_ptr(), o.numel() - 1)) for b, o in self.dev]
+        else:
+            batches = [(b.numpy(), o.numpy().view(np.uint64)) for b, o in self.pinned]
+        # N = 1: tracked consume.  N > 1: untracked consume of this rank's shards, the exact n_unique_kmers of the
+        # sharded stream (occupancy exchange + first-touch passes), then the merge
+        self.multigpu.count_sharded(self.sketches, batches, how=self.args.merge, where=khmer.MEM_DEVICE if resident else khmer.MEM_HOST,
+                                    exact_unique=not self.args.no_unique)
         if resident:
             b, o = self.dev[0]
             hits, flags, _ = khmer.novel_batch(self.sketches[:1], self.sketches[1:], b.data_ptr(),
@@ -500,11 +500,23 @@ def multi_rank_parity(args, runner, rank, world, torch, multigpu, phase):
     hits = hits[np.lexsort((hits['offset'], hits['read']))]
     same_hits = len(hits) == len(ohits) and bool((hits['read'] == ohits['read']).all()) and \
         bool((hits['offset'] == ohits['offset']).all()) and bool((hits['abund'][:, :3] == ohits['abund'][:, :3]).all())
-    ok = identical and same_tables and same_hits
+    # n_unique_kmers of the sharded stream (rank order = file order) against the single-threaded oracle -- the
+    # order-dependent number cannot come from the multi-threaded count above; one sample, small worlds only (time)
+    unique_note = ''
+    same_unique = True
+    if world <= 2 and not args.no_unique:
+        seq = getattr(ko, name)(K, buckets, N_TABLES)
+        for r in range(world):
+            trio = simtrio.simulate_trio(1000000, reads_per_sample=args.reads_per_sample, seed_offset=1000 * r)
+            seq.consume_batch(trio[0][0], trio[0][1])
+        same_unique = runner.sketches[0].n_unique_kmers() == seq.n_unique_kmers()
+        unique_note = ', n_unique_kmers {} == single-threaded oracle'.format(seq.n_unique_kmers())
+        phase('oracle n_unique (single thread) done')
+    ok = identical and same_tables and same_hits and same_unique
     text = ('bit-exact at N={}: merged sketches identical on all ranks (device checksums), rank 0 tables == oracle over all '
-            '{} shards, {} gathered hits == oracle').format(world, world, len(ohits)) if ok else \
-        'MISMATCH (ranks identical: {}, tables: {}, hits: {} [{} vs {}])'.format(identical, same_tables, same_hits,
-                                                                                 len(hits), len(ohits))
+            '{} shards, {} gathered hits == oracle{}').format(world, world, len(ohits), unique_note) if ok else \
+        'MISMATCH (ranks identical: {}, tables: {}, hits: {} [{} vs {}], n_unique: {})'.format(
+            identical, same_tables, same_hits, len(hits), len(ohits), same_unique)
     return ok, text
 
 
@@ -732,7 +744,7 @@ def run_c4(args, rank, world, barrier, phase):
     dev = torch.device('cuda', device)
     n_total = args.c4_reads
     buckets = args.c4_gb_per_gpu * 1e9 * world * 2 / N_TABLES          # 4-bit: two buckets per byte
-    spans = [multigpu.SpanningSketch(khmer.SmallCounttable, K, buckets, N_TABLES) for _ in range(3)]
+    spans = [multigpu.SpanningSketch(khmer.SmallCounttable, K, buckets, N_TABLES, chunk_positions=args.c4_chunk) for _ in range(3)]
     sketches = [sp.sketch for sp in spans]
     phase('c4: 3 spanning sketches of {:.0f} GB allocated ({:.0f} GB per GPU each)'.format(
         args.c4_gb_per_gpu * world, args.c4_gb_per_gpu))
@@ -822,6 +834,55 @@ def run_c4(args, rank, world, barrier, phase):
     state.clear()
     for sp in spans:
         sp.close()
+    barrier()
+    return out
+
+
+# ----------------------------------------------------------------------------- config 5 (banded chain)
+
+def run_c5(args, rank, world, trio0, barrier, phase):
+    """BASELINE config 5's chain through the FILE-based CLI path: the C2 trio of rank 0 written as FASTQ,
+    `kevlar novel --num-bands 8 --band b` for every band (band b on rank (b-1) mod world, kevlar_b200.bands),
+    `unband`, `filter` recount on rank 0.  Reported as wall-clock k-mer events per second: every band hashes all
+    reads of the three samples (3 counts + 1 scan per band), as the reference's banding does."""
+    import tempfile
+    import torch
+    import kevlar_b200
+    from kevlar_b200 import bands
+    td = torch.distributed
+    shared = [tempfile.mkdtemp(prefix='kv_c5_') if rank == 0 else None]
+    if world > 1:
+        td.broadcast_object_list(shared, src=0)
+    tmp = shared[0]
+    names = ['proband', 'mother', 'father']
+    if rank == 0:
+        for name, (b, o) in zip(names, trio0):
+            reads = b.reshape(-1, READ_LEN)
+            qual = b'I' * READ_LEN
+            with open(os.path.join(tmp, name + '.fq'), 'wb') as fh:
+                fh.write(b''.join(b'@r%d\n%s\n+\n%s\n' % (i, reads[i].tobytes(), qual) for i in range(len(reads))))
+    barrier()
+    files = [os.path.join(tmp, n + '.fq') for n in names]
+    ns = bands.parser().parse_args(['--case', files[0], '--control', files[1], '--control', files[2], '-k', str(K), '--memory',
+                                    str(MEMORY / 8), '--case-min', str(CASE_MIN), '--ctrl-max', str(CTRL_MAX), '--num-bands', '8',
+                                    '--filter-memory', '1M', '--out-prefix', os.path.join(tmp, 'c5')])
+    saved = kevlar_b200.logstream
+    kevlar_b200.logstream = open(os.devnull, 'w')
+    barrier()
+    t0 = time.perf_counter()
+    result = bands.run(ns, rank, world, barrier=barrier)
+    secs = time.perf_counter() - t0
+    kevlar_b200.logstream = saved
+    out = None
+    if rank == 0:
+        nk = kmers_per_step(trio0)
+        n_reads = sum(1 for line in open(result['filter']) if line.startswith('@r'))
+        out = {'workload': 'C5: C2 trio as FASTQ files, novel --num-bands 8 (sketch memory/8 per band, band b on rank (b-1) mod {}), '
+                           'unband, filter recount; file-based CLI path'.format(world),
+               'seconds': secs, 'kmer_events': 8 * nk, 'value': 8 * nk / secs, 'unit': 'k-mers/s',
+               'reads_after_filter': n_reads}
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
     barrier()
     return out
 
@@ -919,6 +980,11 @@ def measure(args, rank, world, barrier, phase, live):
     c4 = None
     if args.c4 and not runner.sharded:
         c4 = run_c4(args, rank, world, barrier, phase)
+    c5 = None
+    if args.c5 or (world > 1 and not args.no_c5):
+        trio0 = trio if rank == 0 else None
+        c5 = run_c5(args, rank, world, trio0, barrier, phase)
+        phase('c5: banded chain done')
     if getattr(runner, 'span', False):
         runner.sketches = []
         for sp in runner.spans:
@@ -1017,6 +1083,8 @@ def measure(args, rank, world, barrier, phase, live):
         line['c3'] = c3
     if c4 is not None:
         line['c4'] = c4
+    if c5 is not None:
+        line['c5'] = c5
 
     if world == 1 and not args.no_cpu_baseline:
         from oracle import khmer_oracle as ko

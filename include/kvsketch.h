@@ -252,6 +252,20 @@ int kv_consume_batch_span(kv_sketch *s, struct kv_peer_sync *ps, const uint8_t *
                           uint64_t n_reads, int where, uint64_t n_chunks, int num_bands, int band, const kv_sketch *mask,
                           int mask_threshold, int consume_masked, uint64_t *n_kmers_out);
 
+/* n_unique_kmers (kevlar/count.py:84 logs it) when the reads of one sample are sharded over R ranks in file
+ * order.  After every rank has counted its shard into a ZEROED partial sketch:
+ *   kv_sketch_occupancy   device pointers to the sketch's per-table occupancy bitmaps (1 bit per bucket, LSB
+ *                         first; refreshed from the counters by the call; owned by the sketch);
+ *   the caller ORs the bitmaps of all LOWER ranks into scratch bitmaps of its own (rank 0: all zero);
+ *   kv_unique_batch       the first-touch passes over THIS rank's reads with those bitmaps as the occupied set
+ *                         (they are updated as the batch's chunks go by) -> this rank's share of n_unique;
+ *   kv_sketch_set_unique  stores the sum over the ranks in the merged sketch. */
+int kv_sketch_occupancy(kv_sketch *s, uint32_t **dev_words_out, uint64_t *n_words_out);
+int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occupied, const uint8_t *bases, const uint64_t *offsets,
+                    uint64_t n_reads, int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
+                    int consume_masked, uint64_t *n_unique_out);
+int kv_sketch_set_unique(kv_sketch *s, uint64_t n_unique);
+
 /* CUDA IPC plumbing for kv_sketch_merge_peers: export this sketch's flat allocation
  * (64-byte handle) / map a peer's.  */
 int kv_sketch_ipc_export(kv_sketch *s, uint8_t handle_out[64]);

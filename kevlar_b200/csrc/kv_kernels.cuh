@@ -614,6 +614,9 @@ struct KvTileSources {
     const uint32_t *cursor[KV_MAX_RANKS];
     const uint16_t *slab[KV_MAX_RANKS];
     uint64_t piece[KV_TABLES_DEV];           // bytes of table t per rank
+    uint32_t own_lo[KV_TABLES_DEV];          // first region of table t that lives in this rank's HBM
+    uint32_t own_n[KV_TABLES_DEV];           // how many of them
+    uint32_t own_total;
 };
 
 template <int BITS, bool SPAN>
@@ -621,27 +624,48 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
                                                                         uint32_t direct_below, const __grid_constant__ KvTileSources src)
 {
     extern __shared__ uint32_t sm_tile[];   // BITS 8/4: (1 << rb) / 2 words of two 16-bit counters; BITS 1: (1 << rb) / 32 words
-    const uint32_t run = blockIdx.x;
-    int t = 0;
-    while (t + 1 < v.n_tables && run >= ti0.run_base[t + 1]) t++;
-    const uint64_t bucket0 = (uint64_t)(run - ti0.run_base[t]) << ti0.rb;
-    if (SPAN) {
-        // whose HBM holds this region?  (pieces are multiples of 2 MB, regions are <= 64 KB and aligned)
-        const uint64_t byte0 = BITS == 8 ? bucket0 : (BITS == 4 ? bucket0 >> 1 : bucket0 >> 3);
-        if ((int)(byte0 / src.piece[t]) != src.rank) return;
-    }
-    const uint32_t nb = (uint32_t)((v.size[t] - bucket0) < (1ull << ti0.rb) ? (v.size[t] - bucket0) : (1ull << ti0.rb));
-    const int n_src = SPAN ? src.n : 1;
-    // how many offsets each source filed for this region: all (remote) cursors are fetched at once
     __shared__ uint32_t s_cnt[KV_MAX_RANKS];
+    // ordinary sketch: one CTA per run.  Spanning sketch: a resident grid strides over the runs whose regions
+    // live in THIS rank's HBM (src.own_*), so no CTA is spent on a region somebody else applies.
+    const uint32_t n_work = SPAN ? src.own_total : ti0.run_base[KV_TABLES_DEV];
+    const int n_src = SPAN ? src.n : 1;
+    // work item -> (table, run)
+    auto locate = [&](uint32_t work, int &t) -> uint32_t {
+        t = 0;
+        if (SPAN) {
+            uint32_t first = 0;
+            while (t + 1 < v.n_tables && work >= first + src.own_n[t]) { first += src.own_n[t]; t++; }
+            return ti0.run_base[t] + src.own_lo[t] + (work - first);
+        }
+        while (t + 1 < v.n_tables && work >= ti0.run_base[t + 1]) t++;
+        return work;
+    };
+    // how many offsets source q filed for a region: thread q fetches its (remote) cursor one region AHEAD, so
+    // the NVLink round trip overlaps the work on the current region
+    uint32_t ahead = 0;
+    if ((int)threadIdx.x < n_src && blockIdx.x < n_work) {
+        int t0;
+        const uint32_t r0 = locate(blockIdx.x, t0);
+        ahead = SPAN ? src.cursor[threadIdx.x][r0] : ti0.cursor[r0];
+    }
+  for (uint32_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+    if (work != blockIdx.x) __syncthreads();   // the previous region is stored: shared memory may be reused
+    int t;
+    const uint32_t run = locate(work, t);
+    const uint64_t bucket0 = (uint64_t)(run - ti0.run_base[t]) << ti0.rb;
+    const uint32_t nb = (uint32_t)((v.size[t] - bucket0) < (1ull << ti0.rb) ? (v.size[t] - bucket0) : (1ull << ti0.rb));
     if ((int)threadIdx.x < n_src) {
-        const uint32_t want = SPAN ? src.cursor[threadIdx.x][run] : ti0.cursor[run];
-        s_cnt[threadIdx.x] = want < ti0.cap ? want : ti0.cap;
+        s_cnt[threadIdx.x] = ahead < ti0.cap ? ahead : ti0.cap;
+        if (work + gridDim.x < n_work) {
+            int tn;
+            const uint32_t rn = locate(work + gridDim.x, tn);
+            ahead = SPAN ? src.cursor[threadIdx.x][rn] : ti0.cursor[rn];
+        }
     }
     __syncthreads();
     uint32_t total = 0;
     for (int q = 0; q < n_src; q++) total += s_cnt[q];
-    if (total == 0) return;
+    if (total == 0) continue;
     if (total < direct_below) {   // sparse region: in place
         for (int q = 0; q < n_src; q++) {
             KvTileInfo ti = ti0;
@@ -649,7 +673,7 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
             const uint32_t cnt = s_cnt[q];
             for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) kv_bucket_inc_exact(v, t, bucket0 + ti.slab[kv_slab_index(ti, run, i)]);
         }
-        return;
+        continue;
     }
     if (BITS == 1) {
         uint8_t *g = v.tab[t] + (bucket0 >> 3);
@@ -672,7 +696,7 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
             const uint8_t add = (uint8_t)(sm_tile[b >> 2] >> (8 * (b & 3)));
             if (add) g[b] |= add;
         }
-        return;
+        continue;
     }
     const unsigned maxv = BITS == 8 ? 255u : 15u;
     // ---- load + widen: 16 counters per thread and iteration
@@ -721,6 +745,19 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
     // ---- apply, at most KV_TILE_BATCH offsets between clamps
     const uint32_t nwords = (nb + 1) >> 1;
     uint32_t since = 0;   // offsets applied since the last clamp
+    if (SPAN && total <= KV_TILE_BATCH) {
+        // common case: everything fits between two clamps -- one loop over the offsets of ALL sources, so
+        // local and peer loads are in flight together
+        for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+            uint32_t i = j;
+            int q = 0;
+            while (i >= s_cnt[q]) { i -= s_cnt[q]; q++; }
+            KvTileInfo ti = ti0;
+            ti.slab = const_cast<uint16_t *>(src.slab[q]);
+            const uint32_t o = __ldcs(ti.slab + kv_slab_index(ti, run, i));
+            atomicAdd(&sm_tile[o >> 1], 1u << (16 * (o & 1)));
+        }
+    } else
     for (int q = 0; q < n_src; q++) {
         KvTileInfo ti = ti0;
         if (SPAN) { ti.cursor = const_cast<uint32_t *>(src.cursor[q]); ti.slab = const_cast<uint16_t *>(src.slab[q]); }
@@ -786,6 +823,7 @@ __global__ void __launch_bounds__(KV_TILE_THREADS) kv_tile_apply_kernel(const __
             g[y] = (uint8_t)(((w & 15u) << 4) | (w >> 16));
         }
     }
+  }
 }
 
 // ----------------------------------------------------------------------- K5
@@ -958,6 +996,23 @@ __global__ void __launch_bounds__(256) kv_first_own_list_kernel(const __grid_con
     }
     n_new = __reduce_add_sync(0xffffffffu, n_new);
     if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(n_unique, (unsigned long long)n_new);
+}
+
+// mark every bucket of the listed k-mers as occupied (kv_unique_batch between the chunks of one rank)
+__global__ void __launch_bounds__(256) kv_occ_mark_list_kernel(const __grid_constant__ KvView v, const uint64_t *__restrict__ list_h,
+                                                               const uint32_t *__restrict__ seg_cnt, uint64_t n_segs)
+{
+    for (uint64_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const uint32_t cnt = seg_cnt[seg];
+        const uint64_t base = seg << KV_SEG_LOG2;
+        for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
+            const uint64_t h = __ldg(list_h + base + i);
+            for (int t = 0; t < v.n_tables; t++) {
+                uint64_t bin;
+                if (kv_bin(v, t, h, bin)) atomicOr(v.occ[t] + (bin >> 5), 1u << (bin & 31));
+            }
+        }
+    }
 }
 
 // khmer abundance_distribution (kevlar/dist.py:55): hist[counts.get(h)] += 1 for every position the

@@ -1236,7 +1236,7 @@ static int kv_first_tag(KvCtx *ctx, uint32_t *tag)
 
 // Before the chunk is hashed: which buckets are empty right now (= at chunk start), the first[] scratch,
 // and -- when table 0 fits first[] -- the tag under which the hash kernel runs table 0's pass A.
-static int kv_fresh_prepare(KvCtx *ctx, kv_sketch *s, const KvView &v, bool may_fuse, KvFreshPre *pre)
+static int kv_fresh_prepare(KvCtx *ctx, const kv_sketch *s, const KvView &v, bool may_fuse, KvFreshPre *pre, bool rebuild_occ = true)
 {
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
@@ -1247,7 +1247,7 @@ static int kv_fresh_prepare(KvCtx *ctx, kv_sketch *s, const KvView &v, bool may_
                            "kv_sketch_set_unique_tracking(sketch, 0)", (unsigned long long)(range * 4));
         ctx->first_epoch = 0;   // (re)allocated: memset before the first pass
     }
-    if (s->bits != 1) {   // one streaming pass over the counters, all tables in one launch
+    if (s->bits != 1 && rebuild_occ) {   // one streaming pass over the counters, all tables in one launch
         uint64_t words = 0;
         for (int t = 0; t < s->n_tables; t++) words = std::max(words, (s->sizes[t] + 31) / 32);
         dim3 grid(kv_grid_for(ctx, words, 16), (unsigned)s->n_tables);
@@ -1263,10 +1263,11 @@ static int kv_fresh_prepare(KvCtx *ctx, kv_sketch *s, const KvView &v, bool may_
 
 // The chunk's contribution to n_unique_kmers; must run before the chunk's increments.  Leaves the bitmap
 // of new positions in ctx->fresh.  dist_counts != NULL: also histogram dist_counts.get(h) over them.
-static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const KvFreshPre &pre, const uint64_t *d_hashes,
+static int kv_count_fresh(KvCtx *ctx, const kv_sketch *s, const KvView &v, const KvFreshPre &pre, const uint64_t *d_hashes,
                           const uint32_t *d_valid, uint64_t n, const kv_sketch *dist_counts = nullptr,
-                          unsigned long long *d_hist = nullptr)
+                          unsigned long long *d_hist = nullptr, unsigned long long *d_unique = nullptr)
 {
+    if (!d_unique) d_unique = s->d_unique;
     if (n > (1ull << KV_POS_BITS)) return kv_fail(KV_EINVAL, "internal: n_unique chunk larger than 2^%d positions", KV_POS_BITS);
     const uint64_t n_words = (n + 31) / 32;
     const uint64_t n_segs = (n + (1u << KV_SEG_LOG2) - 1) >> KV_SEG_LOG2, list_len = n_segs << KV_SEG_LOG2;
@@ -1281,10 +1282,10 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const KvFre
     const unsigned sgrid = (unsigned)std::min<uint64_t>(n_segs, (uint64_t)ctx->sm_count * 8);
     if (pre.fused0)
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_compact_kernel<true>, sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, fresh,
-                 list_h, list_p, seg_cnt, s->d_unique);
+                 list_h, list_p, seg_cnt, d_unique);
     else
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_compact_kernel<false>, sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, fresh,
-                 list_h, list_p, seg_cnt, s->d_unique);
+                 list_h, list_p, seg_cnt, d_unique);
     for (int t = pre.fused0 ? 1 : 0; t < s->n_tables; t++)
         for (uint64_t lo = 0; lo < s->sizes[t]; lo += pre.range) {
             const uint64_t nb = std::min(pre.range, s->sizes[t] - lo);
@@ -1294,7 +1295,7 @@ static int kv_count_fresh(KvCtx *ctx, kv_sketch *s, const KvView &v, const KvFre
                      (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb);
             LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_own_list_kernel, sgrid, 256, v, t, (const uint32_t *)first, tag,
                      (const uint64_t *)list_h, (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb, fresh,
-                     s->d_unique);
+                     d_unique);
         }
     if (dist_counts)
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_abund_dist_kernel, grid, 256, kv_view(dist_counts), d_hashes, (const uint32_t *)fresh, n,
@@ -1453,7 +1454,14 @@ static int kv_launch_tile_apply2(KvCtx *ctx, const KvView &v, const KvTilePlan &
         CU(cudaFuncSetAttribute(kv_tile_apply_kernel<BITS, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         configured = true;
     }
-    return kv_launch_smem(ctx, KV_PROF_INCREMENT, kv_tile_apply_kernel<BITS, SPAN>, pl.runs, KV_TILE_THREADS, pl.smem, v, pl.ti, pl.direct_below, src);
+    unsigned grid = pl.runs;
+    if (SPAN) {   // resident grid striding over this rank's regions
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kv_tile_apply_kernel<BITS, SPAN>, KV_TILE_THREADS, pl.smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(src.own_total, (uint64_t)ctx->sm_count * per_sm));
+    }
+    return kv_launch_smem(ctx, KV_PROF_INCREMENT, kv_tile_apply_kernel<BITS, SPAN>, grid, KV_TILE_THREADS, pl.smem, v, pl.ti, pl.direct_below, src);
 }
 
 static int kv_launch_tile_apply(KvCtx *ctx, const kv_sketch *s, const KvView &v, const KvTilePlan &pl)
@@ -1465,7 +1473,17 @@ static int kv_launch_tile_apply(KvCtx *ctx, const kv_sketch *s, const KvView &v,
         src.n = s->span->world;
         src.rank = s->span->rank;
         for (int r = 0; r < s->span->world; r++) { src.cursor[r] = s->span->cursor[r]; src.slab[r] = s->span->slab[r]; }
-        for (int t = 0; t < s->n_tables; t++) src.piece[t] = s->span->piece[t];
+        const uint64_t region_bytes = std::max<uint64_t>(1, (((uint64_t)1 << pl.ti.rb) * (uint64_t)s->bits) / 8);
+        for (int t = 0; t < s->n_tables; t++) {
+            src.piece[t] = s->span->piece[t];
+            // regions of table t inside this rank's piece (pieces are multiples of 2 MB, regions powers of two <= 64 KB)
+            const uint64_t n_regions = pl.ti.run_base[t + 1] - pl.ti.run_base[t];
+            const uint64_t lo = std::min<uint64_t>(n_regions, (uint64_t)s->span->rank * s->span->piece[t] / region_bytes);
+            const uint64_t hi = std::min<uint64_t>(n_regions, (uint64_t)(s->span->rank + 1) * s->span->piece[t] / region_bytes);
+            src.own_lo[t] = (uint32_t)lo;
+            src.own_n[t] = (uint32_t)(hi - lo);
+            src.own_total += src.own_n[t];
+        }
         if (s->bits == 8) return kv_launch_tile_apply2<8, true>(ctx, v, pl, src);
         if (s->bits == 4) return kv_launch_tile_apply2<4, true>(ctx, v, pl, src);
         return kv_launch_tile_apply2<1, true>(ctx, v, pl, src);
@@ -2015,6 +2033,118 @@ extern "C" int kv_abund_dist_batch(const kv_sketch *counts, kv_sketch *tracking,
     kv_stage_done(ctx, &b);
     CU(cudaMemcpyAsync(dist_out, d_hist, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
+    return KV_OK;
+}
+
+// ------------------------------------------------------------------ n_unique_kmers across ranks
+//
+// khmer's n_unique_kmers is defined on ONE stream of reads.  With the reads sharded contiguously over R ranks
+// (rank-major order = file order) an occurrence on rank r is new  <=>  it is the first on rank r to touch a
+// bucket that was empty at the start AND that no lower rank touches.  So, once every rank has counted its
+// shard into a zeroed partial sketch: rank r ORs the occupancy bitmaps of the partial sketches of ranks < r
+// (kv_sketch_occupancy, exchanged by the caller), and kv_unique_batch re-runs the first-touch passes over its
+// reads with THAT as the occupied set; the sum over the ranks is the reference's number.
+
+extern "C" int kv_sketch_occupancy(kv_sketch *s, uint32_t **dev_words_out, uint64_t *n_words_out)
+{
+    if (!s || !dev_words_out || !n_words_out) return kv_fail(KV_EINVAL, "null argument");
+    if (s->span || s->n_shards > 1) return kv_fail(KV_EINVAL, "occupancy bitmaps are kept for ordinary sketches only");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    const KvView v = kv_view(s);
+    if (s->bits != 1) {
+        uint64_t words = 0;
+        for (int t = 0; t < s->n_tables; t++) words = std::max(words, (s->sizes[t] + 31) / 32);
+        dim3 grid(kv_grid_for(ctx, words, 16), (unsigned)s->n_tables);
+        if (s->bits == 8) LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_all_kernel<8>, grid, 256, v);
+        else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_all_kernel<4>, grid, 256, v);
+        CU(cudaStreamSynchronize(ctx->compute));
+    }
+    for (int t = 0; t < s->n_tables; t++) {
+        // a bit table IS its occupancy bitmap (same bit order); its allocation is padded to 256 bytes
+        dev_words_out[t] = s->bits == 1 ? (uint32_t *)(s->flat + s->toff[t]) : v.occ[t];
+        n_words_out[t] = (s->sizes[t] + 31) / 32;
+    }
+    return KV_OK;
+}
+
+extern "C" int kv_sketch_set_unique(kv_sketch *s, uint64_t n_unique)
+{
+    if (!s) return kv_fail(KV_EINVAL, "null sketch");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    unsigned long long v = n_unique;
+    CU(cudaMemcpyAsync(s->d_unique, &v, 8, cudaMemcpyHostToDevice, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    s->n_unique = n_unique;
+    s->unique_valid = true;
+    return KV_OK;
+}
+
+extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occupied, const uint8_t *bases, const uint64_t *offsets,
+                               uint64_t n_reads, int where, int num_bands, int band, const kv_sketch *mask,
+                               int mask_threshold, int consume_masked, uint64_t *n_unique_out)
+{
+    if (!like || !dev_occupied || !n_unique_out) return kv_fail(KV_EINVAL, "null argument");
+    *n_unique_out = 0;
+    if (n_reads == 0) return KV_OK;
+    if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
+    KV_TRY(kv_check_mask(like, mask));
+    uint64_t lo = 0, hi = 0;
+    if (num_bands > 0) KV_TRY(kv_band_interval(num_bands, band, &lo, &hi));
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(like->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(like->device));
+    KvBatch b;
+    KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
+    if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
+    // the view the first-touch kernels see: `like`'s geometry, the caller's bitmaps as the occupied set
+    KvView v = kv_view(like);
+    v.bits = 8;   // (kv_bucket_empty reads occ[] for counters and the table itself for bit tables: always occ[] here)
+    for (int t = 0; t < like->n_tables; t++) {
+        if (!dev_occupied[t]) return kv_fail(KV_EINVAL, "null occupancy bitmap for table %d", t);
+        v.occ[t] = dev_occupied[t];
+    }
+    unsigned long long *d_unique = ctx->counters + 7;
+    CU(cudaMemsetAsync(d_unique, 0, sizeof(unsigned long long), ctx->compute));
+    CU(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->compute));
+    const uint64_t chunk_limit = std::min<uint64_t>(ctx->chunk_bases, 1ull << KV_POS_BITS);
+    const uint64_t chunk_tiles = chunk_limit / KV_TILE;
+    const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
+    KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
+    KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
+        const uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
+        const uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
+        KvHashParams p;
+        memset(&p, 0, sizeof p);
+        p.bases = b.d_bases; p.offsets = b.d_offsets; p.tile_first = (const uint32_t *)ctx->tile_first.p;
+        p.total = b.total; p.tile0 = t0; p.k = like->ksize;
+        p.banded = num_bands > 0; p.band_lo = lo; p.band_hi = hi;
+        if (mask) { p.use_mask = 1; p.mask = kv_view(mask); p.mask_threshold = mask_threshold; p.consume_masked = consume_masked != 0; }
+        p.hashes = (uint64_t *)ctx->hashes.p; p.valid = (uint32_t *)ctx->valid.p; p.n_valid = ctx->counters;
+        KvFreshPre pre;
+        KV_TRY(kv_fresh_prepare(ctx, like, v, ctx->unique_fuse0, &pre, false));
+        if (pre.fused0) { p.track0 = 1; p.first0 = (uint32_t *)ctx->first.p; p.tag0 = pre.tag0; p.sk = v; }
+        if (like->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)nt));
+        else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)nt));
+        KV_TRY(kv_count_fresh(ctx, like, v, pre, p.hashes, p.valid, npos, nullptr, nullptr, d_unique));
+        if (t0 + chunk_tiles < b.n_tiles) {   // later chunks of this rank must see this chunk's buckets as occupied
+            const uint64_t n_segs = (npos + (1u << KV_SEG_LOG2) - 1) >> KV_SEG_LOG2;
+            const unsigned sgrid = (unsigned)std::min<uint64_t>(n_segs, (uint64_t)ctx->sm_count * 8);
+            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_mark_list_kernel, sgrid, 256, v, (const uint64_t *)ctx->list_h.p,
+                     (const uint32_t *)ctx->seg_cnt.p, n_segs);
+        }
+    }
+    kv_stage_done(ctx, &b);
+    CU(cudaMemcpyAsync(ctx->h_counters + 7, d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    *n_unique_out = ctx->h_counters[7];
     return KV_OK;
 }
 

@@ -324,6 +324,102 @@ def merge_sketch(sketch, how='p2p', group=None):
     return sketch
 
 
+def _device_words(ptr, n_words, device, keepalive):
+    """A torch int32 view of `n_words` device words at `ptr` (no copy)."""
+    import torch
+
+    class _Raw(object):
+        pass
+    raw = _Raw()
+    raw.__cuda_array_interface__ = {'shape': (int(n_words),), 'typestr': '<i4', 'data': (int(ptr), False), 'version': 3}
+    raw._keepalive = keepalive
+    return torch.as_tensor(raw, device=torch.device('cuda', device))
+
+
+def _occupancy_view(sketch):
+    """(int32 tensor over the sketch's occupancy bitmaps of ALL tables as one range -- no copy --, word offset of
+    every table inside it).  The per-table bitmaps sit back to back (with zero padding) in one allocation."""
+    nt = len(sketch.hashsizes())
+    ptrs, nwords = (c_void_p * nt)(), (c_uint64 * nt)()
+    check(lib().kv_sketch_occupancy(sketch._h, ptrs, nwords))
+    base = int(ptrs[0])
+    starts = [(int(ptrs[t]) - base) // 4 for t in range(nt)]
+    assert all(st >= 0 for st in starts) and (int(ptrs[nt - 1]) - base) % 4 == 0
+    total = starts[-1] + int(nwords[nt - 1])
+    return _device_words(base, total, sketch.device, sketch), starts
+
+
+def unique_across_ranks(sketches, batches, where=_lib.MEM_HOST, num_bands=None, band=None, mask=None, threshold=0,
+                        consume_masked=False, group=None):
+    """khmer's n_unique_kmers for samples whose reads are sharded contiguously over the ranks (rank order = file
+    order).  COLLECTIVE; call it after every rank has counted its shards into its zeroed partial `sketches`
+    and BEFORE the merge.  Each rank ORs the occupancy bitmaps of all lower ranks' partial sketches and re-runs
+    the first-touch passes over its own reads with that as the occupied set (kv_unique_batch); the sum over the
+    ranks is the number the reference logs (kevlar/count.py:84).  `batches` = one (bases, offsets) per sketch, in
+    the form `consume_batch` takes for `where`.  Returns one number per sketch."""
+    import torch
+    td = dist()
+    world = td.get_world_size(group) if td.is_initialized() else 1
+    rank = td.get_rank(group) if td.is_initialized() else 0
+    lowers = []
+    for sketch in sketches:
+        mine, starts = _occupancy_view(sketch)
+        lower = torch.zeros_like(mine)
+        if world > 1:
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            td.all_gather(gathered, mine, group=group)
+            for q in range(rank):
+                lower |= gathered[q]
+            del gathered
+        lowers.append((lower, starts))
+    torch.cuda.synchronize(torch.device('cuda', sketches[0].device))
+    shares = []
+    for sketch, (lower, starts), (bases, offsets) in zip(sketches, lowers, batches):
+        occ = (c_void_p * len(starts))(*[lower.data_ptr() + 4 * st for st in starts])
+        if where == _lib.MEM_HOST:
+            bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+            bptr, optr, n_reads = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1
+        else:
+            bptr, (optr, n_reads) = bases, offsets
+        n = c_uint64()
+        check(lib().kv_unique_batch(sketch._h, occ, bptr, optr, n_reads, where, int(num_bands or 0), int(band or 0),
+                                    mask._h if mask is not None else None, int(threshold), int(bool(consume_masked)), byref(n)))
+        shares.append(n.value)
+    total = torch.tensor(shares, dtype=torch.int64, device=torch.device('cuda', sketches[0].device))
+    if world > 1:
+        td.all_reduce(total, op=td.ReduceOp.SUM, group=group)
+    return [int(x) for x in total.tolist()]
+
+
+def count_sharded(sketches, batches, how='p2p', where=_lib.MEM_HOST, num_bands=None, band=None, mask=None, threshold=0,
+                  consume_masked=False, exact_unique=True, group=None):
+    """`kevlar count` of one or more samples on all ranks (plan A): THIS rank's contiguous shard of each sample's
+    reads goes into the matching sketch (which must be empty), the partial sketches are merged, and -- with
+    `exact_unique` -- every merged sketch reports the reference's n_unique_kmers.  COLLECTIVE.  `sketches` /
+    `batches` may be single objects or equally long lists."""
+    single = not isinstance(sketches, (list, tuple))
+    if single:
+        sketches, batches = [sketches], [batches]
+    td = dist()
+    world = td.get_world_size(group) if td.is_initialized() else 1
+    kw = dict(num_bands=num_bands, band=band, mask=mask, threshold=threshold, consume_masked=consume_masked, where=where)
+    if world == 1:
+        for sketch, (bases, offsets) in zip(sketches, batches):
+            sketch.consume_batch(bases, offsets, wait=False, **kw)
+        return
+    for sketch, (bases, offsets) in zip(sketches, batches):
+        sketch.set_unique_tracking(False)
+        sketch.consume_batch(bases, offsets, wait=False, **kw)
+    uniques = unique_across_ranks(sketches, batches, group=group, **kw) if exact_unique else None
+    if how != 'p2p':
+        _lib.sync(sketches[0].device)
+    merge_sketches(sketches, how=how, group=group)
+    if uniques is not None:
+        _lib.sync(sketches[0].device)
+        for sketch, n_unique in zip(sketches, uniques):
+            check(lib().kv_sketch_set_unique(sketch._h, n_unique))
+
+
 def gather_hits(hits, read_base, group=None):
     """Collect every rank's novel hits on rank 0 with batch-global read indices."""
     td = dist()

@@ -71,6 +71,26 @@ def main():
             multigpu.peer_sync_status()
             multigpu.release_p2p(gpu)   # collective: unmap everywhere, barrier, only then free
             del gpu
+    # ---- n_unique_kmers across ranks: reads sharded in file order, partial sketches merged, the merged sketch
+    # reports the number the single-threaded reference logs (order-dependent)
+    for cls in (() if only else ('Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph')):
+        for si, seqs in enumerate(samples):
+            bases, offs = ko.reads_to_batch(seqs)
+            mb, mo = multigpu.shard_batch(bases, offs, rank, world)
+            bands = (5, 3) if si == 1 else (None, None)
+            g = getattr(kv.khmer, cls)(25, 30000, 4)
+            c = getattr(ko, cls)(25, 30000, 4)
+            multigpu.count_sharded(g, (mb, mo), num_bands=bands[0], band=bands[1])
+            c.consume_batch(bases, offs, num_bands=bands[0] or 0, band=bands[1] or 0)
+            if g.n_unique_kmers() != c.n_unique_kmers():
+                failures.append('count_sharded {} sample {}: n_unique {} != {} on rank {}'.format(
+                    cls, si, g.n_unique_kmers(), c.n_unique_kmers(), rank))
+            for t in range(4):
+                if g.table_bytes(t) != c.table_bytes(t):
+                    failures.append('count_sharded {} table {} differs'.format(cls, t))
+            multigpu.peer_sync_status()
+            multigpu.release_p2p([g])
+            del g
     import tempfile
     shared = os.environ.get('KV_TEST_SHARED_DIR') or tempfile.gettempdir()
     # ---- plan B, second design: spanning sketches (tables spread over the HBM of all ranks, updates exchanged

@@ -778,7 +778,7 @@ def test_multi_chunk_batches_are_exact():
     2048-position chunk (a few reads per chunk)."""
     # (the saturation test is left out: it asserts that the overflow redo fires, which needs big chunks)
     _rerun_in_child('(consume and not saturation) or count_simple or novel_cli_microtrio or count_cli_with_mask '
-                    'or abundance_distribution or dist_passes',
+                    'or abundance_distribution or dist_passes or unique_across_shards',
                     KV_CHUNK_BASES='2048')
 
 
@@ -1147,3 +1147,44 @@ def test_banded_chain_matches_reference(kv, tmp_path):
     assert open(result['unband']).read() == open(golden_gen('bands8_unband.out')).read()
     assert open(result['filter']).read() == open(golden_gen('bands8_filter.out')).read()
     assert open(result['filter']).read().count('@') >= 10
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'])
+def test_unique_across_shards_on_one_gpu(kv, oracle, name, monkeypatch):
+    """kv_sketch_occupancy + kv_unique_batch, the building blocks of n_unique_kmers across ranks
+    (multigpu.unique_across_ranks), played through on ONE GPU: the reads are cut into three shards in file
+    order, each shard is counted into its own zeroed sketch, shard r's first-touch passes run with the OR of the
+    occupancy of shards < r as the occupied set, and the shares add up to the single-stream n_unique_kmers."""
+    torch = pytest.importorskip('torch')
+    from ctypes import byref, c_uint64, c_void_p
+    from kevlar_b200 import multigpu
+    from kevlar_b200._lib import check, lib
+    reads = random_reads(61, 2500, 30, 140) + [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT'] * 300 + random_reads(62, 500, 30, 140)
+    bases, offs = oracle.reads_to_batch(reads)
+    c = getattr(oracle, name)(21, 20000, 4)
+    c.consume_batch(bases, offs)
+    parts, shards = [], []
+    for r in range(3):
+        mb, mo = multigpu.shard_batch(bases, offs, r, 3)
+        g = getattr(kv.khmer, name)(21, 20000, 4)
+        g.set_unique_tracking(False)
+        g.consume_batch(mb, mo)
+        parts.append(g)
+        shards.append((mb, mo))
+    occs = []
+    for g in parts:
+        view, starts = multigpu._occupancy_view(g)
+        occs.append(view.clone())
+    total = 0
+    for r in range(3):
+        lower = torch.zeros_like(occs[0])
+        for q in range(r):
+            lower |= occs[q]
+        torch.cuda.synchronize()
+        occ = (c_void_p * 4)(*[lower.data_ptr() + 4 * int(starts[t]) for t in range(4)])
+        n = c_uint64()
+        mb, mo = shards[r]
+        check(lib().kv_unique_batch(parts[r]._h, occ, mb.ctypes.data, mo.ctypes.data, len(mo) - 1, kv.khmer.MEM_HOST, 0, 0, None, 0,
+                                    0, byref(n)))
+        total += n.value
+    assert total == c.n_unique_kmers()
