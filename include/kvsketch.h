@@ -255,7 +255,7 @@ int kv_consume_batch_span(kv_sketch *s, struct kv_peer_sync *ps, const uint8_t *
 /* n_unique_kmers (kevlar/count.py:84 logs it) when the reads of one sample are sharded over R ranks in file
  * order.  After every rank has counted its shard into a ZEROED partial sketch:
  *   kv_sketch_occupancy   device pointers to the sketch's per-table occupancy bitmaps (1 bit per bucket, LSB
- *                         first; refreshed from the counters by the call; owned by the sketch);
+ *                         first; the refresh from the counters is ENQUEUED on kv_stream; owned by the sketch);
  *   the caller ORs the bitmaps of all LOWER ranks into scratch bitmaps of its own (rank 0: all zero);
  *   kv_unique_batch       the first-touch passes over THIS rank's reads with those bitmaps as the occupied set
  *                         (they are updated as the batch's chunks go by) -> this rank's share of n_unique;
@@ -263,8 +263,12 @@ int kv_consume_batch_span(kv_sketch *s, struct kv_peer_sync *ps, const uint8_t *
 int kv_sketch_occupancy(kv_sketch *s, uint32_t **dev_words_out, uint64_t *n_words_out);
 int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occupied, const uint8_t *bases, const uint64_t *offsets,
                     uint64_t n_reads, int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
-                    int consume_masked, uint64_t *n_unique_out);
+                    int consume_masked, uint64_t *n_unique_out, uint64_t *dev_n_unique_out);
 int kv_sketch_set_unique(kv_sketch *s, uint64_t n_unique);
+/* Stream-ordered forms (no host synchronisation; everything runs on the device's kv_stream): kv_sketch_occupancy
+ * only enqueues the refresh; kv_unique_batch with n_unique_out == NULL leaves this rank's share in
+ * *dev_n_unique_out (device memory); kv_sketch_set_unique_dev copies the final number from device memory. */
+int kv_sketch_set_unique_dev(kv_sketch *s, const uint64_t *dev_n_unique);
 
 /* CUDA IPC plumbing for kv_sketch_merge_peers: export this sketch's flat allocation
  * (64-byte handle) / map a peer's.  */

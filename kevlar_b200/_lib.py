@@ -71,8 +71,9 @@ SYMBOLS = [
     ('kv_sketch_shard_info', c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64)]),
     ('kv_sketch_save_part', c_int, [_P, c_char_p, c_int, c_int, c_uint64]),
     ('kv_sketch_occupancy', c_int, [_P, POINTER(_P), POINTER(c_uint64)]),
-    ('kv_unique_batch', c_int, [_P, POINTER(_P), _P, _P, c_uint64, c_int, c_int, c_int, _P, c_int, c_int, POINTER(c_uint64)]),
+    ('kv_unique_batch', c_int, [_P, POINTER(_P), _P, _P, c_uint64, c_int, c_int, c_int, _P, c_int, c_int, POINTER(c_uint64), _P]),
     ('kv_sketch_set_unique', c_int, [_P, c_uint64]),
+    ('kv_sketch_set_unique_dev', c_int, [_P, _P]),
     ('kv_sketch_create_span', c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64), c_int, c_int, c_int, c_uint64, POINTER(_P),
                                       POINTER(c_int), _P]),
     ('kv_sketch_span_attach', c_int, [_P, c_int, POINTER(c_int), _P]),

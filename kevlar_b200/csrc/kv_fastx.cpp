@@ -59,6 +59,7 @@ struct kv_reader {
     std::vector<char> buf;
     size_t pos = 0, end = 0;
     bool eof = false;
+    std::string io_error;            // set by the producer: the input ended because of an I/O / inflate error
     uint64_t num_reads = 0;
     // a FASTA record whose end (next header or EOF) has not been seen yet
     bool fasta_open = false;
@@ -83,9 +84,19 @@ static void producer_main(kv_reader *r)
         }
         if (!b) { b = new Block(); b->data.resize(KV_BLOCK); }
         long got = r->gz ? (long)gzread(r->gz, b->data.data(), (unsigned)KV_BLOCK) : (long)read(r->fd, b->data.data(), KV_BLOCK);
+        // a read error or a damaged / truncated gzip stream is an ERROR, not the end of the file: khmer's
+        // ReadParser raises there, and a sketch built from part of the input would be silently wrong
+        std::string problem;
+        if (got < 0) problem = r->gz ? "gzip stream is damaged" : "read error";
+        else if (got == 0 && r->gz) {
+            int zerr = Z_OK;
+            const char *msg = gzerror(r->gz, &zerr);
+            if (zerr != Z_OK && zerr != Z_STREAM_END) problem = msg && *msg ? msg : "gzip stream is truncated or damaged";
+        }
         std::unique_lock<std::mutex> lk(r->mu);
-        if (got <= 0) {   // end of input (a damaged stream ends the file where it breaks, like before)
+        if (got <= 0) {
             r->spare.push_back(b);
+            r->io_error = problem;
             r->input_done = true;
             r->cv_full.notify_all();
             return;
@@ -273,6 +284,14 @@ extern "C" int kv_reader_next(kv_reader *r, uint64_t max_bases, const uint8_t **
         } else if (r->fasta_open) {
             r->fasta_seq.append(line, len);
         }
+    }
+    if (r->eof) {
+        std::string problem;
+        {
+            std::unique_lock<std::mutex> lk(r->mu);
+            problem = r->io_error;
+        }
+        if (!problem.empty()) return kv_fail_public(KV_EIO, "%s: %s", r->path.c_str(), problem.c_str());
     }
     *bases = r->bases.data();
     *offsets = r->offsets.data();

@@ -1020,6 +1020,14 @@ extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int
                 cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "H2D copy failed"); break; }
         }
     }
+    if (rc == KV_OK && bits == 8 && big) {
+        // khmer's use_bigcount: counts above 255 live in a map behind the tables; kevlar never sets it
+        // (Counttable has no bigcount) -- refuse rather than load saturated 255s in their place
+        uint64_t n_big = 0;
+        if (fread(&n_big, 8, 1, f) == 1 && n_big)
+            rc = kv_fail(KV_EIO, "%s: the file carries %llu bigcount entries (khmer use_bigcount), which this sketch type does not hold",
+                         path, (unsigned long long)n_big);
+    }
     fclose(f);
     if (rc != KV_OK) { cudaFree(s->flat); cudaFree(s->state); cudaFree(s->d_unique); delete s; return rc; }
     s->state_stale = true;
@@ -2060,7 +2068,6 @@ extern "C" int kv_sketch_occupancy(kv_sketch *s, uint32_t **dev_words_out, uint6
         dim3 grid(kv_grid_for(ctx, words, 16), (unsigned)s->n_tables);
         if (s->bits == 8) LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_all_kernel<8>, grid, 256, v);
         else LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_occ_rebuild_all_kernel<4>, grid, 256, v);
-        CU(cudaStreamSynchronize(ctx->compute));
     }
     for (int t = 0; t < s->n_tables; t++) {
         // a bit table IS its occupancy bitmap (same bit order); its allocation is padded to 256 bytes
@@ -2085,13 +2092,28 @@ extern "C" int kv_sketch_set_unique(kv_sketch *s, uint64_t n_unique)
     return KV_OK;
 }
 
+extern "C" int kv_sketch_set_unique_dev(kv_sketch *s, const uint64_t *dev_n_unique)
+{
+    if (!s || !dev_n_unique) return kv_fail(KV_EINVAL, "null argument");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->d_unique, dev_n_unique, 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    s->unique_valid = true;
+    return KV_OK;
+}
+
 extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occupied, const uint8_t *bases, const uint64_t *offsets,
                                uint64_t n_reads, int where, int num_bands, int band, const kv_sketch *mask,
-                               int mask_threshold, int consume_masked, uint64_t *n_unique_out)
+                               int mask_threshold, int consume_masked, uint64_t *n_unique_out, uint64_t *dev_n_unique_out)
 {
-    if (!like || !dev_occupied || !n_unique_out) return kv_fail(KV_EINVAL, "null argument");
-    *n_unique_out = 0;
-    if (n_reads == 0) return KV_OK;
+    if (!like || !dev_occupied || (!n_unique_out && !dev_n_unique_out)) return kv_fail(KV_EINVAL, "null argument");
+    if (n_unique_out) *n_unique_out = 0;
+    if (n_reads == 0) {
+        if (dev_n_unique_out) CU(cudaMemset(dev_n_unique_out, 0, 8));
+        return KV_OK;
+    }
     if (!bases || !offsets) return kv_fail(KV_EINVAL, "null batch pointers");
     KV_TRY(kv_check_mask(like, mask));
     uint64_t lo = 0, hi = 0;
@@ -2102,7 +2124,11 @@ extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occup
     CU(cudaSetDevice(like->device));
     KvBatch b;
     KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
-    if (b.total == 0) { kv_stage_done(ctx, &b); return KV_OK; }
+    if (b.total == 0) {
+        kv_stage_done(ctx, &b);
+        if (dev_n_unique_out) CU(cudaMemsetAsync(dev_n_unique_out, 0, 8, ctx->compute));
+        return KV_OK;
+    }
     // the view the first-touch kernels see: `like`'s geometry, the caller's bitmaps as the occupied set
     KvView v = kv_view(like);
     v.bits = 8;   // (kv_bucket_empty reads occ[] for counters and the table itself for bit tables: always occ[] here)
@@ -2142,9 +2168,12 @@ extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occup
         }
     }
     kv_stage_done(ctx, &b);
-    CU(cudaMemcpyAsync(ctx->h_counters + 7, d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
-    CU(cudaStreamSynchronize(ctx->compute));
-    *n_unique_out = ctx->h_counters[7];
+    if (dev_n_unique_out) CU(cudaMemcpyAsync(dev_n_unique_out, d_unique, 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    if (n_unique_out) {
+        CU(cudaMemcpyAsync(ctx->h_counters + 7, d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        *n_unique_out = ctx->h_counters[7];
+    }
     return KV_OK;
 }
 

@@ -242,6 +242,7 @@ class NativeFastxReader(object):
         self._h = ctypes.c_void_p()
         _lib.check(_lib.lib().kv_reader_open(str(filename).encode(), ctypes.byref(self._h)))
         self._records = None   # record-at-a-time iteration state: (batch, next index)
+        self._stash = []       # batches parsed ahead by an abandoned batches() generator: the next consumer gets them first
 
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
@@ -250,6 +251,8 @@ class NativeFastxReader(object):
 
     def _next(self, max_bases, keep_text):
         """One kv_reader_next call; copies the reader-owned buffers into numpy / bytes."""
+        if self._stash:
+            return self._stash.pop(0)
         c = ctypes
         bases, offs, names, noffs, quals, qoffs, isfq = (c.c_void_p() for _ in range(7))
         n = c.c_uint64()
@@ -274,7 +277,7 @@ class NativeFastxReader(object):
         """Batches in file order.  With ``prefetch`` a helper thread parses one batch ahead, so the
         parsing of batch i+1 overlaps whatever the consumer does with batch i (typically waiting
         for the GPU inside a ctypes call, which releases the GIL).  A generator that is abandoned
-        early gives back nothing it has not yielded except the one batch parsed ahead."""
+        early hands the batch it had parsed ahead to whoever iterates the parser next."""
         if not prefetch or os.environ.get('KV_NO_PREFETCH'):
             while True:
                 with self._lock:
@@ -308,11 +311,16 @@ class NativeFastxReader(object):
                 yield item
         finally:
             stop.set()
-            while worker.is_alive():   # unblock a pending put, then let the thread see the flag
+            leftover = []
+            while worker.is_alive() or not ahead.empty():   # unblock a pending put, then let the thread see the flag
                 try:
-                    ahead.get(timeout=0.05)
+                    item = ahead.get(timeout=0.05)
                 except queue.Empty:
-                    pass
+                    continue
+                if isinstance(item, SeqBatch):
+                    leftover.append(item)   # parsed and counted but never yielded: keep it for the next consumer
+            with self._lock:
+                self._stash = leftover + self._stash
 
     def __iter__(self):
         while True:

@@ -350,45 +350,56 @@ def _occupancy_view(sketch):
 
 
 def unique_across_ranks(sketches, batches, where=_lib.MEM_HOST, num_bands=None, band=None, mask=None, threshold=0,
-                        consume_masked=False, group=None):
+                        consume_masked=False, group=None, store=True):
     """khmer's n_unique_kmers for samples whose reads are sharded contiguously over the ranks (rank order = file
     order).  COLLECTIVE; call it after every rank has counted its shards into its zeroed partial `sketches`
     and BEFORE the merge.  Each rank ORs the occupancy bitmaps of all lower ranks' partial sketches and re-runs
     the first-touch passes over its own reads with that as the occupied set (kv_unique_batch); the sum over the
     ranks is the number the reference logs (kevlar/count.py:84).  `batches` = one (bases, offsets) per sketch, in
-    the form `consume_batch` takes for `where`.  Returns one number per sketch."""
+    the form `consume_batch` takes for `where`.
+
+    Everything is enqueued on the library's stream -- the torch ops and the NCCL collectives run under it too --
+    so the host never waits.  Returns a device tensor (int64, one entry per sketch) holding the totals; with
+    `store` they are also copied into the sketches (valid once the stream has drained; a merge enqueued later on
+    does not disturb them)."""
     import torch
     td = dist()
     world = td.get_world_size(group) if td.is_initialized() else 1
     rank = td.get_rank(group) if td.is_initialized() else 0
-    lowers = []
-    for sketch in sketches:
-        mine, starts = _occupancy_view(sketch)
-        lower = torch.zeros_like(mine)
+    device = sketches[0].device
+    dev = torch.device('cuda', device)
+    stream = torch.cuda.ExternalStream(_lib.stream_ptr(device), device=dev)
+    keep = []
+    with torch.cuda.stream(stream):
+        totals = torch.zeros(len(sketches), dtype=torch.int64, device=dev)
+        for i, (sketch, (bases, offsets)) in enumerate(zip(sketches, batches)):
+            mine, starts = _occupancy_view(sketch)
+            lower = torch.zeros_like(mine)
+            if world > 1:
+                gathered = [torch.empty_like(mine) for _ in range(world)]
+                td.all_gather(gathered, mine, group=group)
+                for q in range(rank):
+                    lower |= gathered[q]
+                keep.append(gathered)
+            keep.append(lower)
+            occ = (c_void_p * len(starts))(*[lower.data_ptr() + 4 * st for st in starts])
+            if where == _lib.MEM_HOST:
+                bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+                bptr, optr, n_reads = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1
+            else:
+                bptr, (optr, n_reads) = bases, offsets
+            check(lib().kv_unique_batch(sketch._h, occ, bptr, optr, n_reads, where, int(num_bands or 0), int(band or 0),
+                                        mask._h if mask is not None else None, int(threshold), int(bool(consume_masked)),
+                                        None, totals.data_ptr() + 8 * i))
         if world > 1:
-            gathered = [torch.empty_like(mine) for _ in range(world)]
-            td.all_gather(gathered, mine, group=group)
-            for q in range(rank):
-                lower |= gathered[q]
-            del gathered
-        lowers.append((lower, starts))
-    torch.cuda.synchronize(torch.device('cuda', sketches[0].device))
-    shares = []
-    for sketch, (lower, starts), (bases, offsets) in zip(sketches, lowers, batches):
-        occ = (c_void_p * len(starts))(*[lower.data_ptr() + 4 * st for st in starts])
-        if where == _lib.MEM_HOST:
-            bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
-            bptr, optr, n_reads = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1
-        else:
-            bptr, (optr, n_reads) = bases, offsets
-        n = c_uint64()
-        check(lib().kv_unique_batch(sketch._h, occ, bptr, optr, n_reads, where, int(num_bands or 0), int(band or 0),
-                                    mask._h if mask is not None else None, int(threshold), int(bool(consume_masked)), byref(n)))
-        shares.append(n.value)
-    total = torch.tensor(shares, dtype=torch.int64, device=torch.device('cuda', sketches[0].device))
-    if world > 1:
-        td.all_reduce(total, op=td.ReduceOp.SUM, group=group)
-    return [int(x) for x in total.tolist()]
+            td.all_reduce(totals, op=td.ReduceOp.SUM, group=group)
+        if store:
+            for i, sketch in enumerate(sketches):
+                check(lib().kv_sketch_set_unique_dev(sketch._h, totals.data_ptr() + 8 * i))
+        # the scratch tensors must outlive the kernels that read them: hand them to the stream
+        for tensor in [totals] + [t for item in keep for t in (item if isinstance(item, list) else [item])]:
+            tensor.record_stream(stream)
+    return totals
 
 
 def count_sharded(sketches, batches, how='p2p', where=_lib.MEM_HOST, num_bands=None, band=None, mask=None, threshold=0,
@@ -410,14 +421,15 @@ def count_sharded(sketches, batches, how='p2p', where=_lib.MEM_HOST, num_bands=N
     for sketch, (bases, offsets) in zip(sketches, batches):
         sketch.set_unique_tracking(False)
         sketch.consume_batch(bases, offsets, wait=False, **kw)
-    uniques = unique_across_ranks(sketches, batches, group=group, **kw) if exact_unique else None
+    totals = unique_across_ranks(sketches, batches, group=group, store=False, **kw) if exact_unique else None
     if how != 'p2p':
         _lib.sync(sketches[0].device)
     merge_sketches(sketches, how=how, group=group)
-    if uniques is not None:
-        _lib.sync(sketches[0].device)
-        for sketch, n_unique in zip(sketches, uniques):
-            check(lib().kv_sketch_set_unique(sketch._h, n_unique))
+    if totals is not None:   # after the merge, which marks the sketches' own counter as stale
+        if how != 'p2p':
+            _lib.sync(sketches[0].device)
+        for i, sketch in enumerate(sketches):
+            check(lib().kv_sketch_set_unique_dev(sketch._h, totals.data_ptr() + 8 * i))
 
 
 def gather_hits(hits, read_base, group=None):

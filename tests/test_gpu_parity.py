@@ -1174,6 +1174,7 @@ def test_unique_across_shards_on_one_gpu(kv, oracle, name, monkeypatch):
     occs = []
     for g in parts:
         view, starts = multigpu._occupancy_view(g)
+        kv._lib.sync(g.device)
         occs.append(view.clone())
     total = 0
     for r in range(3):
@@ -1185,6 +1186,6 @@ def test_unique_across_shards_on_one_gpu(kv, oracle, name, monkeypatch):
         n = c_uint64()
         mb, mo = shards[r]
         check(lib().kv_unique_batch(parts[r]._h, occ, mb.ctypes.data, mo.ctypes.data, len(mo) - 1, kv.khmer.MEM_HOST, 0, 0, None, 0,
-                                    0, byref(n)))
+                                    0, byref(n), None))
         total += n.value
     assert total == c.n_unique_kmers()

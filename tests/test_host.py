@@ -541,3 +541,26 @@ def test_simtrio_piecewise_haplotypes_equal_sequential():
     for a, b in zip(new, old):
         for x, y in zip(a, b):
             assert len(x) == len(y) and (x == y).all()
+
+
+def test_native_reader_reports_damaged_gzip_and_keeps_prefetched_batches(tmp_path):
+    """(a) a truncated .gz must raise OSError like khmer's ReadParser instead of ending the file
+    silently; (b) a batches() generator abandoned early must not lose the batch it had parsed ahead."""
+    import gzip
+    from kevlar_b200 import fastx
+    reads = ['@r{}\nACGTACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n'.format(i) for i in range(20000)]
+    good = tmp_path / 'reads.fq.gz'
+    with gzip.open(str(good), 'wt') as fh:
+        fh.write(''.join(reads))
+    raw = open(str(good), 'rb').read()
+    bad = tmp_path / 'cut.fq.gz'
+    open(str(bad), 'wb').write(raw[:len(raw) // 2])
+    with pytest.raises(OSError):
+        for _ in fastx.NativeFastxReader(str(bad)).batches(64 << 10):
+            pass
+    parser = fastx.NativeFastxReader(str(good))
+    gen = parser.batches(100 * 32)          # 100 reads per batch, one batch parsed ahead
+    first = next(gen)
+    gen.close()
+    rest = sum(len(b) for b in parser.batches(100 * 32))
+    assert len(first) + rest == 20000 == parser.num_reads
