@@ -454,17 +454,34 @@ def load_atomic_peak(table_mb=64):
     return peaks
 
 
-def sketch_checksum(torch, sketch):
-    """64-bit checksum of a sketch's table storage, computed on the device."""
-    from kevlar_b200 import multigpu
+def sketch_checksum(torch, sketch, local_only=False):
+    """64-bit checksum of a sketch's table storage, computed on the device in 256 MB pieces.  Spanning
+    sketches with `local_only`: only the pieces that live in THIS rank's HBM (all ranks together cover the
+    sketch; nobody drags the whole thing over NVLink)."""
+    import ctypes
+    from kevlar_b200 import _lib, multigpu
     flat = multigpu.GpuSketchAdapter(sketch).flat_tensor()
-    n8 = flat.numel() // 8 * 8
-    words = flat[:n8].view(torch.int64)
+    ranges = [(0, flat.numel())]
+    if local_only:
+        nt = len(sketch.hashsizes())
+        rank, world = ctypes.c_int(), ctypes.c_int()
+        piece = (ctypes.c_uint64 * nt)()
+        _lib.check(_lib.lib().kv_sketch_span_info(sketch._h, ctypes.byref(rank), ctypes.byref(world), piece, None))
+        ranges, off = [], 0
+        for t in range(nt):
+            ranges.append((off + rank.value * piece[t], off + (rank.value + 1) * piece[t]))
+            off += piece[t] * world.value
     weights = torch.arange(1, 1025, dtype=torch.int64, device=flat.device)
-    pad = (-words.numel()) % 1024
-    if pad:
-        words = torch.cat([words, torch.zeros(pad, dtype=torch.int64, device=flat.device)])
-    return int((words.view(-1, 1024) * weights).sum().item()) ^ int(flat[n8:].sum().item())
+    total, step = 0, 256 << 20
+    for lo, hi in ranges:
+        for a in range(lo, hi, step):
+            part = flat[a:min(a + step, hi)]
+            n8 = part.numel() // 8192 * 8192
+            if n8:
+                total ^= int((part[:n8].view(torch.int64).view(-1, 1024) * weights).sum().item()) & 0xffffffffffffffff
+            if part.numel() > n8:
+                total ^= int(part[n8:].sum(dtype=torch.int64).item())
+    return total - (1 << 64) if total >= (1 << 63) else total   # as a signed 64-bit value (it travels in int64 tensors)
 
 
 def multi_rank_parity(args, runner, rank, world, torch, multigpu, phase):
@@ -782,8 +799,7 @@ def run_c4(args, rank, world, barrier, phase):
     def local_checksums():
         out = []
         for sk in sketches:
-            ptr, nbytes = sk.flat_device_buffer()
-            out.append(sketch_checksum(torch, sk))
+            out.append(sketch_checksum(torch, sk, local_only=True))
         return out
 
     trio = draw(0)
@@ -807,8 +823,11 @@ def run_c4(args, rank, world, barrier, phase):
         td.all_reduce(hits_a)
         td.all_reduce(hits_b)
     t = torch.tensor([ms_count, ms_scan], dtype=torch.float64, device=dev)
+    differs = torch.tensor([0 if sums_a == sums_b else 1], dtype=torch.int64, device=dev)   # every rank checks its own pieces
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
+        td.all_reduce(differs)
+    same_bytes = int(differs.item()) == 0
     ms_count, ms_scan = t.tolist()
     nk = n_total * (READ_LEN - K + 1)
     out = None
@@ -826,7 +845,7 @@ def run_c4(args, rank, world, barrier, phase):
                              N_TABLES, world - 1, world, N_TABLES * 2.0 * (world - 1) / max(world, 1), world - 1),
                 'novel': 'counter loads for remote pages: one 32 B sector per table touch x {}/{} of the touches'.format(world - 1, world)},
             'properties_at_full_size': {
-                'same_sketch_bytes_under_a_rotated_read_assignment': sums_a == sums_b,
+                'same_sketch_bytes_under_a_rotated_read_assignment': same_bytes,
                 'same_hit_count_under_a_rotated_read_assignment': int(hits_a.item()) == int(hits_b.item()),
                 'novel_hits_all_ranks': int(hits_a.item()), 'n_occupied': occ_a},
         }

@@ -137,11 +137,14 @@ struct KvHashParams {
     uint32_t tag0;
 };
 
+#ifndef KV_HASH_MIN_CTAS
+#define KV_HASH_MIN_CTAS 6      // resident CTAs per SM the plain hash kernel is compiled for
+#endif
 #ifndef KV_SCATTER_MIN_CTAS
-#define KV_SCATTER_MIN_CTAS 1   // resident CTAs per SM the scatter variant is compiled for
+#define KV_SCATTER_MIN_CTAS 4   // resident CTAs per SM the scatter variant is compiled for
 #endif
 template <int HASHER, int KW, bool SCATTER>
-__global__ void __launch_bounds__(KV_THREADS, SCATTER ? KV_SCATTER_MIN_CTAS : 1) kv_hash_kernel(const __grid_constant__ KvHashParams p)
+__global__ void __launch_bounds__(KV_THREADS, SCATTER ? KV_SCATTER_MIN_CTAS : KV_HASH_MIN_CTAS) kv_hash_kernel(const __grid_constant__ KvHashParams p)
 {
     __shared__ KvTileSmem sm;
     __shared__ KvTileList ls;

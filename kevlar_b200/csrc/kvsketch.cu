@@ -94,7 +94,7 @@ struct KvCtx {
     int update_path = 0;                      // 0 auto, 1 direct, 2 region-partitioned (K3b), 3 tiled (K3c)   [KV_UPDATE_PATH]
     uint64_t tile_min_bytes = 128ull << 20;   // auto: sketches at least this large take the tiled path       [KV_TILE_MIN_BYTES]
     int tile_rb = 15;                         // log2(buckets per region)                                      [KV_TILE_RB]
-    uint64_t tile_chunk_bases = 256ull << 20; // positions per chunk on the tiled path                         [KV_TILE_CHUNK_BASES]
+    uint64_t tile_chunk_bases = 512ull << 20; // positions per chunk on the tiled path (256 M with n_unique tracking) [KV_TILE_CHUNK_BASES]
     int tile_direct_below = -1;               // regions with fewer offsets are updated in place (-1: region bytes / 64)
     int tile_block_log2 = 6;                  // slab layout: slots per interleave block (-1: run-major)               [KV_TILE_BLOCK_LOG2]
     KvBuf tile_cursor, tile_slab, tile_ovf, notes;
@@ -162,6 +162,12 @@ static int kv_ctx_get(int device, KvCtx **out)
                 c.l2_window_max = (size_t)maxw;
             } else
                 cudaGetLastError();
+        }
+        if (const char *env = getenv("KV_L2_FETCH")) {
+            // L2 fetch granularity (32/64/128 B), opt-in.  Measured on 4 GB sketches and on C2
+            // (profiles/r02r_l2fetch.jsonl): no difference at any setting, so the default is left alone.
+            size_t want = (size_t)atoi(env);
+            if (want && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want) != cudaSuccess) cudaGetLastError();
         }
         if (const char *env = getenv("KV_CHUNK_BASES")) {
             uint64_t v = strtoull(env, nullptr, 10);

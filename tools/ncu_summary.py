@@ -22,10 +22,24 @@ WANT = [
     ('launch__grid_size', 'grid'),
 ]
 
+# derived columns: sectors per request (32 = perfectly scattered, 4 = one sector per 8 lanes ...) and the share
+# of every fetched sector's 32 bytes that the program actually used -- the "sector efficiency" north_star names
+DERIVED = [
+    ('ld sectors/req', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum'),
+    ('st sectors/req', 'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum'),
+    ('atom sectors/req', 'l1tex__t_sectors_pipe_lsu_mem_global_op_atom.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_atom.sum'),
+    ('red sectors/req', 'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum'),
+]
+RATIO = [
+    ('ld bytes used/sector', 'smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.ratio'),
+    ('st bytes used/sector', 'smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio'),
+]
+
 
 def main(pattern):
-    print('| kernel | ' + ' | '.join(label for _, label in WANT) + ' |')
-    print('|---|' + '---|' * len(WANT))
+    labels = [label for _, label in WANT] + [d[0] for d in DERIVED] + [r[0] for r in RATIO]
+    print('| kernel | ' + ' | '.join(labels) + ' |')
+    print('|---|' + '---|' * len(labels))
     for path in sorted(glob.glob(pattern)):
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -41,6 +55,17 @@ def main(pattern):
                         cells.append(vals[i])
                 else:
                     cells.append('-')
+            def num(metric):
+                try:
+                    return float(vals[hdr.index(metric)].replace(',', ''))
+                except (ValueError, IndexError):
+                    return None
+            for _, sectors, requests in DERIVED:
+                a, b = num(sectors), num(requests)
+                cells.append('{:.2f}'.format(a / b) if a is not None and b else '-')
+            for _, metric in RATIO:
+                a = num(metric)
+                cells.append('{:.1f} B'.format(a) if a is not None else '-')
             print('| `{}` ({}) | '.format(name, os.path.basename(path)) + ' | '.join(cells) + ' |')
 
 
