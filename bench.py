@@ -63,6 +63,8 @@ def parse_args():
                          "spanning sketches (tables spread over all GPUs, exchange fused into the apply kernel)")
     ap.add_argument('--reads-per-sample', type=int, default=READS_PER_SAMPLE)
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
+    ap.add_argument('--no-overlap', action='store_true', help="N > 1: merge all sketches after the last sample instead of "
+                    "merging each sample's sketch on the merge lane while the next sample is counted")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-variants', action='store_true')
     ap.add_argument('--no-c3', action='store_true', help='skip the config-3 (100 Mbp, 3 x 4 GB sketches) part')
@@ -392,7 +394,7 @@ class GpuTrio(object):
         # N = 1: tracked consume.  N > 1: untracked consume of this rank's shards, the exact n_unique_kmers of the
         # sharded stream (occupancy exchange + first-touch passes), then the merge
         self.multigpu.count_sharded(self.sketches, batches, how=self.args.merge, where=khmer.MEM_DEVICE if resident else khmer.MEM_HOST,
-                                    exact_unique=not self.args.no_unique)
+                                    exact_unique=not self.args.no_unique, overlap=not self.args.no_overlap)
         if resident:
             b, o = self.dev[0]
             hits, flags, _ = khmer.novel_batch(self.sketches[:1], self.sketches[1:], b.data_ptr(),
@@ -561,8 +563,14 @@ def run_c3(args, rank, world, barrier, phase):
     state = {}
 
     def count(trio_slice, tracked=False):
-        for sk, (b, o) in zip(sketches, trio_slice):
+        for sk in sketches:
             sk.clear()
+        if world > 1 and not tracked:
+            # each sample's merge runs on the merge lane while the next sample is being counted
+            multigpu.count_sharded(sketches, [(b.data_ptr(), (o.data_ptr(), o.numel() - 1)) for b, o in trio_slice],
+                                   how='p2p', where=khmer.MEM_DEVICE, exact_unique=False, overlap=not args.no_overlap)
+            return
+        for sk, (b, o) in zip(sketches, trio_slice):
             sk.set_unique_tracking(tracked)
             sk.consume_batch(b.data_ptr(), (o.data_ptr(), o.numel() - 1), where=khmer.MEM_DEVICE, wait=False)
         if world > 1:
@@ -713,7 +721,8 @@ def run_c3(args, rank, world, barrier, phase):
         out = {
             'workload': 'C3: synthetic 100 Mbp trio at 30x = {} reads x {} bp per sample (drawn on the device), k={}, 3 x {:.0f} GB '
                         '8-bit Counttable with {} tables (HBM-resident); reads sharded over {} rank(s) (strong scaling), partial '
-                        'sketches merged by the one-pass p2p all-reduce, novel scan shard-local'.format(
+                        'sketches merged by the one-pass p2p all-reduce (each sample\'s merge under the next sample\'s count), '
+                        'novel scan shard-local'.format(
                             n_total, READ_LEN, K, args.c3_memory / 1e9, N_TABLES, world),
             'scaling': 'strong', 'steps': args.c3_steps, 'kmers_per_step': 4 * nk_all,
             'value': 4 * nk_all / (ms_step / 1e3), 'unit': 'k-mers/s', 'ms_per_step': ms_step,
@@ -726,15 +735,24 @@ def run_c3(args, rank, world, barrier, phase):
                       'frac_of_hbm_model': nk_all / (ms_scan / 1e3) * (32.0 * 3 * N_TABLES + lfrac) / (peak * 1e9),
                       'kernel_ms_rank0': kern_scan},
             'roofline_update': {
-                'kernel': 'kv_part_apply_kernel<8> (+ partition) / kv_increment_kernel<8>', 'bound': 'hbm',
-                'achieved': 64.0 * N_TABLES * 3 * nk_sample / ((upd_ms + prof_count['partition'][0]) / 1e3) / 1e9,
+                'kernel': 'kv_hash_kernel<scatter> + kv_tile_apply_kernel<8> (tiled update path, K3c)', 'bound': 'hbm',
+                'achieved': 64.0 * N_TABLES * 3 * nk_sample / ((upd_ms + prof_count['hash'][0] + prof_count['partition'][0]) / 1e3) / 1e9,
                 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
-                'note': 'algorithmic 64 B x 4 tables per k-mer over the update kernels of rank 0 (partition + apply)'},
+                'apply_only_GBps': 64.0 * N_TABLES * 3 * nk_sample / (upd_ms / 1e3) / 1e9,
+                'note': 'algorithmic 64 B x 4 tables per k-mer (SURVEY 8d: one sector read + written per table touch) over '
+                        'ALL update kernels of rank 0: the hash kernel, which also files every update as a 2-byte offset in '
+                        'its region slab, and the apply kernel, which streams each region through shared memory once; '
+                        '`apply_only_GBps` is the same bytes over the apply kernel alone (it beats the sector model because '
+                        'a region is read and written once however many updates it takes)'},
             'roofline_novel': {
                 'kernel': 'kv_novel_kernel', 'bound': 'hbm',
                 'achieved': (32.0 * 3 * N_TABLES + lfrac) * nk_sample / (nov_ms / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                 'peak_source': peak_src},
             'merge': {'ms_per_step': ms_merge, 'share_of_count': ms_merge / ms_count if ms_count else None,
+                      'overlapped_with_counting': bool(world > 1 and not args.no_overlap),
+                      'note': 'kernel time of the merge class on rank 0 (barriers + all-reduce kernels); with overlap each '
+                              "sample's merge runs on the merge lane under the next sample's count, so only part of it is "
+                              'exposed in count.ms',
                       'bytes_in_plus_out_per_rank': 2 * 3 * flat_bytes * (world - 1) / world,
                       'nvlink_GBps_per_rank': (2 * 3 * flat_bytes * (world - 1) / world) / (ms_merge / 1e3) / 1e9 if ms_merge else None},
             'properties_at_full_size': props,

@@ -54,6 +54,7 @@ extern "C" {
 #define KV_ECUDA (-4)     /* CUDA runtime error                -> RuntimeError */
 #define KV_ENODEVICE (-5) /* no usable CUDA device             -> RuntimeError */
 #define KV_EOVERFLOW (-6) /* output buffer too small           -> RuntimeError */
+#define KV_ESTATE (-7)    /* a shortcut's precondition does not hold; the call changed nothing -> caller takes the general path */
 
 typedef struct kv_sketch kv_sketch;
 
@@ -264,6 +265,12 @@ int kv_sketch_occupancy(kv_sketch *s, uint32_t **dev_words_out, uint64_t *n_word
 int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occupied, const uint8_t *bases, const uint64_t *offsets,
                     uint64_t n_reads, int where, int num_bands, int band, const kv_sketch *mask, int mask_threshold,
                     int consume_masked, uint64_t *n_unique_out, uint64_t *dev_n_unique_out);
+/* kv_unique_batch for the batch that kv_consume_batch counted into `like` LAST on this device, straight from the
+ * hashes that call left in the device scratch: no second host-to-device copy of the reads, no second hash.
+ * Applies when that batch fitted one chunk and nothing has used the scratch since; otherwise KV_ESTATE and
+ * nothing was done -- call kv_unique_batch. */
+int kv_unique_last_batch(const kv_sketch *like, uint32_t *const *dev_occupied, uint64_t *n_unique_out,
+                         uint64_t *dev_n_unique_out);
 int kv_sketch_set_unique(kv_sketch *s, uint64_t n_unique);
 /* Stream-ordered forms (no host synchronisation; everything runs on the device's kv_stream): kv_sketch_occupancy
  * only enqueues the refresh; kv_unique_batch with n_unique_out == NULL leaves this rank's share in
@@ -291,6 +298,16 @@ int kv_peer_sync_connect(kv_peer_sync *ps, int peer_rank, const uint8_t handle[6
 int kv_peer_barrier(kv_peer_sync *ps);
 int kv_peer_sync_status(kv_peer_sync *ps);
 int kv_peer_sync_destroy(kv_peer_sync *ps);
+/* The merge lane: a second stream per device for the peer-to-peer merge, so that the merge of one sample's sketch
+ * crosses NVLink while the next sample is being counted (kevlar count runs once per sample: three independent
+ * sketches per trio, kevlar/workflows/mark-I/Snakefile).  kv_merge_fork(device): work enqueued on the merge lane
+ * from now on starts after everything enqueued on kv_stream so far; until kv_merge_join(device) -- which makes
+ * kv_stream wait for the lane -- kv_sketch_allreduce_peers / kv_sketch_merge_peers launch on the lane.
+ * kv_peer_barrier follows its object: kv_peer_sync_set_lane(ps, 1) binds all barriers of `ps` to the lane (use
+ * one object per lane: barriers of one object must execute in the order they were enqueued). */
+int kv_peer_sync_set_lane(kv_peer_sync *ps, int lane);
+int kv_merge_fork(int device);
+int kv_merge_join(int device);
 
 /* khmer.ReadParser(filename) (kevlar/count.py:40, kevlar/__init__.py:125-128): FASTA/FASTQ, plain or
  * gzip.  kv_reader_next parses at least one and at most ~max_bases bases' worth of records, in

@@ -24,6 +24,7 @@ KV_ENOMEM = -3
 KV_ECUDA = -4
 KV_ENODEVICE = -5
 KV_EOVERFLOW = -6
+KV_ESTATE = -7
 
 READ_SKIPPED = 1
 READ_DISCARDED = 2
@@ -72,6 +73,7 @@ SYMBOLS = [
     ('kv_sketch_save_part', c_int, [_P, c_char_p, c_int, c_int, c_uint64]),
     ('kv_sketch_occupancy', c_int, [_P, POINTER(_P), POINTER(c_uint64)]),
     ('kv_unique_batch', c_int, [_P, POINTER(_P), _P, _P, c_uint64, c_int, c_int, c_int, _P, c_int, c_int, POINTER(c_uint64), _P]),
+    ('kv_unique_last_batch', c_int, [_P, POINTER(_P), POINTER(c_uint64), _P]),
     ('kv_sketch_set_unique', c_int, [_P, c_uint64]),
     ('kv_sketch_set_unique_dev', c_int, [_P, _P]),
     ('kv_sketch_create_span', c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64), c_int, c_int, c_int, c_uint64, POINTER(_P),
@@ -86,6 +88,9 @@ SYMBOLS = [
     ('kv_peer_barrier', c_int, [_P]),
     ('kv_peer_sync_status', c_int, [_P]),
     ('kv_peer_sync_destroy', c_int, [_P]),
+    ('kv_peer_sync_set_lane', c_int, [_P, c_int]),
+    ('kv_merge_fork', c_int, [c_int]),
+    ('kv_merge_join', c_int, [c_int]),
     ('kv_hash_batch_dev', c_int, [c_int, c_int, _P, _P, c_uint64, c_int, c_int, c_int, c_int, _P, _P, c_uint64,
                                   POINTER(c_uint64), POINTER(c_uint64)]),
     ('kv_add_hashes_dev', c_int, [_P, _P, _P, c_uint64]),

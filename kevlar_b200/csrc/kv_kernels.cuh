@@ -957,6 +957,19 @@ __global__ void __launch_bounds__(256) kv_first_compact_kernel(const __grid_cons
     if (lane == 0 && n_new) atomicAdd(n_unique, (unsigned long long)n_new);
 }
 
+// pass A of table 0 over stored hashes (kv_unique_last_batch; otherwise this runs inside kv_hash_kernel)
+__global__ void __launch_bounds__(256) kv_first_min0_kernel(const __grid_constant__ KvView v, uint32_t *__restrict__ first, uint32_t tag,
+                                                            const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ valid,
+                                                            uint64_t n)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        if (!((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u)) continue;
+        uint64_t bin;
+        if (kv_bin(v, 0, __ldg(hashes + g), bin) && kv_bucket_empty(v, 0, bin)) atomicMin(first + bin, tag | (uint32_t)g);
+    }
+}
+
 // pass A of table t over the list
 __global__ void __launch_bounds__(256) kv_first_min_list_kernel(const __grid_constant__ KvView v, int t, uint32_t *__restrict__ first,
                                                                 uint32_t tag, const uint64_t *__restrict__ list_h,
@@ -1225,24 +1238,63 @@ __device__ __forceinline__ uint32_t kv_sat_merge_word(uint32_t a, uint32_t b, in
     return lo | (hi << 4);
 }
 
-template <bool PUSH>
-__global__ void kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec, int bits, KvPeers peers)
+// Every thread keeps 4 to 8 loads over NVLink in flight: U vectors x NP peers, all issued -- unconditionally, so
+// that the compiler cannot serialise them behind predicates -- before the first one is used.  EXACT: the sketch has
+// exactly NP peers (worlds up to 8: one instantiation per peer count); otherwise peers are taken in groups of NP = 8
+// and a short last group re-reads its last peer and discards the copy.  A load over NVLink takes a few microseconds:
+// with one in flight per thread the 8-rank merge ran at a third of the link rate (profiles/r02o_bench_n8.json:
+// 306 GB/s in + 306 GB/s out per rank), and on the merge lane (kv_merge_fork) the kernel gets only a couple of
+// CTAs per SM, so the depth has to come from each thread.  Vectors past the end are clamped for the loads and
+// skipped by the stores.
+template <bool PUSH, int NP, int U, bool EXACT>
+__global__ void __launch_bounds__(256) kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec, int bits,
+                                                             const __grid_constant__ KvPeers peers)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        uint4 acc = local[i];
-        for (int p = 0; p < peers.n; p++) {
-            uint4 o = peers.peer[p][i];
-            acc.x = kv_sat_merge_word(acc.x, o.x, bits);
-            acc.y = kv_sat_merge_word(acc.y, o.y, bits);
-            acc.z = kv_sat_merge_word(acc.z, o.z, bits);
-            acc.w = kv_sat_merge_word(acc.w, o.w, bits);
+    const int n_peers = EXACT ? NP : peers.n;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += stride * U) {
+        uint64_t idx[U];
+        uint4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            idx[u] = i < n_vec ? i : n_vec - 1;
+            acc[u] = local[idx[u]];
         }
-        local[i] = acc;
-        // all-reduce in one pass: this rank owns the slice, so it also stores the finished
-        // vector into every peer's table (nobody else reads or writes this slice anywhere)
-        if (PUSH)
-            for (int p = 0; p < peers.n; p++) peers.peer[p][i] = acc;
+        for (int p0 = 0; p0 < n_peers; p0 += NP) {
+            uint4 o[U][NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                const uint4 *src = peers.peer[EXACT ? j : (p0 + j < n_peers ? p0 + j : n_peers - 1)];
+#pragma unroll
+                for (int u = 0; u < U; u++) o[u][j] = src[idx[u]];
+            }
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                if (!EXACT && p0 + j >= n_peers) break;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    acc[u].x = kv_sat_merge_word(acc[u].x, o[u][j].x, bits);
+                    acc[u].y = kv_sat_merge_word(acc[u].y, o[u][j].y, bits);
+                    acc[u].z = kv_sat_merge_word(acc[u].z, o[u][j].z, bits);
+                    acc[u].w = kv_sat_merge_word(acc[u].w, o[u][j].w, bits);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (i0 + (uint64_t)u * stride >= n_vec) break;
+            local[idx[u]] = acc[u];
+            // all-reduce in one pass: this rank owns the slice, so it also stores the finished
+            // vector into every peer's table (nobody else reads or writes this slice anywhere)
+            if (PUSH) {
+                if (EXACT) {
+#pragma unroll
+                    for (int p = 0; p < NP; p++) peers.peer[p][idx[u]] = acc[u];
+                } else
+                    for (int p = 0; p < n_peers; p++) peers.peer[p][idx[u]] = acc[u];
+            }
+        }
     }
 }
 

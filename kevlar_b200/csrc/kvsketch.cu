@@ -83,6 +83,12 @@ struct KvCtx {
     bool ready = false;
     std::mutex mu;
     cudaStream_t compute = nullptr, copy = nullptr;
+    // the merge lane: between kv_merge_fork and kv_merge_join the peer-to-peer merge kernels (and the barriers of
+    // lane-1 kv_peer_sync objects) run on `merge` next to whatever `compute` does meanwhile
+    cudaStream_t merge = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool forked = false;
+    int merge_lane_ctas = 1;                  // CTAs per SM of a merge kernel that runs next to the counting   [KV_MERGE_LANE_CTAS]
     KvSlot slot[2];
     int next_slot = 0;
     KvBuf tile_first, hashes, valid, fresh, first, hits, flags, discard, misc, added, part_items, part_small, hist;
@@ -117,6 +123,9 @@ struct KvCtx {
     size_t l2_persist = 0;     // bytes of L2 set aside for persisting accesses
     size_t l2_window_max = 0;
     uint64_t chunk_bases = 64ull << 20;
+    // the batch whose hashes + valid bits still sit in `hashes` / `valid` (kv_unique_last_batch): set by a
+    // single-chunk kv_consume_batch, dropped by whatever claims the scratch next
+    struct { const kv_sketch *sketch = nullptr; uint64_t serial = 0, npos = 0; } last_hashed;
 };
 
 static KvCtx g_ctx[16];
@@ -139,6 +148,15 @@ static int kv_ctx_get(int device, KvCtx **out)
         c.device = device;
         CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        {   // the merge lane outranks the compute stream: its few CTAs are placed as soon as slots free up
+            // instead of queueing behind the half a million CTAs of a hash kernel
+            int least = 0, greatest = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CU(cudaStreamCreateWithPriority(&c.merge, cudaStreamNonBlocking, greatest));
+            if (const char *env = getenv("KV_MERGE_LANE_CTAS")) c.merge_lane_ctas = std::max(1, atoi(env));
+        }
+        CU(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
         for (auto &s : c.slot) {
             CU(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -218,22 +236,32 @@ static int kv_buf_ensure(KvBuf &b, size_t need)
     return KV_OK;
 }
 
-#define LAUNCH_C(cls, ctx, kern, grid, block, ...)                         \
+// every user of the hash scratch takes it through here: what an earlier batch left there is gone
+static int kv_hash_scratch(KvCtx *ctx, uint64_t n_pos, bool want_hashes = true)
+{
+    ctx->last_hashed.sketch = nullptr;
+    if (want_hashes) KV_TRY(kv_buf_ensure(ctx->hashes, n_pos * 8));
+    return kv_buf_ensure(ctx->valid, (n_pos / 32 + 1) * 4);
+}
+
+#define LAUNCH_S(cls, ctx, strm, kern, grid, block, ...)                   \
     do {                                                                   \
         auto kfn_ = kern;                                                  \
+        cudaStream_t st_ = (strm);                                         \
         cudaEvent_t e0_ = nullptr, e1_ = nullptr;                          \
         if ((ctx)->profiling) {                                            \
             cudaEventCreate(&e0_); cudaEventCreate(&e1_);                  \
-            cudaEventRecord(e0_, (ctx)->compute);                          \
+            cudaEventRecord(e0_, st_);                                     \
         }                                                                  \
-        kfn_<<<(grid), (block), 0, (ctx)->compute>>>(__VA_ARGS__);         \
+        kfn_<<<(grid), (block), 0, st_>>>(__VA_ARGS__);                    \
         if ((ctx)->profiling) {                                            \
-            cudaEventRecord(e1_, (ctx)->compute);                          \
+            cudaEventRecord(e1_, st_);                                     \
             (ctx)->prof_events.push_back({cls, {e0_, e1_}});               \
         }                                                                  \
         (ctx)->launches++;                                                 \
         CU(cudaGetLastError());                                            \
     } while (0)
+#define LAUNCH_C(cls, ctx, kern, grid, block, ...) LAUNCH_S(cls, ctx, (ctx)->compute, kern, grid, block, __VA_ARGS__)
 #define LAUNCH(ctx, kern, grid, block, ...) LAUNCH_C(KV_PROF_OTHER, ctx, kern, grid, block, __VA_ARGS__)
 
 // Mark [ptr, ptr+bytes) as the persisting L2 window of the compute stream (nullptr: none).
@@ -503,6 +531,8 @@ extern "C" int kv_sketch_destroy(kv_sketch *s)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(ctx->compute));
+    CU(cudaStreamSynchronize(ctx->merge));
+    if (ctx->last_hashed.sketch == s) ctx->last_hashed.sketch = nullptr;
     if (s->span) kv_span_free(s);
     if (s->flat) cudaFree(s->flat);
     if (s->state) cudaFree(s->state);
@@ -1528,14 +1558,15 @@ static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *o
     if (!s) return kv_fail(KV_EINVAL, "null sketch");
     if (n_kmers_out) *n_kmers_out = 0;
     if (s->span && !span_sync) return kv_fail(KV_EINVAL, "spanning sketches are updated with kv_consume_batch_span (collective)");
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(s->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->last_hashed.sketch = nullptr;   // whatever this call does, the scratch no longer describes "the last batch"
     if (n_reads == 0 && !span_sync) return KV_OK;
     if (n_reads && (!bases || !offsets)) return kv_fail(KV_EINVAL, "null batch pointers");
     KV_TRY(kv_check_mask(s, mask));
     uint64_t lo = 0, hi = 0;
     if (num_bands > 0) KV_TRY(kv_band_interval(num_bands, band, &lo, &hi));
-    KvCtx *ctx;
-    KV_TRY(kv_ctx_get(s->device, &ctx));
-    std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(s->device));
     KvBatch b;
     memset(&b, 0, sizeof b);
@@ -1551,8 +1582,7 @@ static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *o
     const uint64_t chunk_tiles = chunk_limit / KV_TILE;
     const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
     const bool need_hashes = !plan.on || s->track_unique;
-    if (need_hashes) KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
-    KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    KV_TRY(kv_hash_scratch(ctx, chunk_pos, need_hashes));
     const KvView sv = kv_view(s);
     const uint64_t own_chunks = (b.n_tiles + chunk_tiles - 1) / chunk_tiles;
     if (span_sync && own_chunks > n_chunks)
@@ -1611,6 +1641,10 @@ static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *o
         s->state_stale = true;   // the hot bitmap of the in-place path is not maintained here
     }
     kv_stage_done(ctx, &b);
+    if (total_chunks == 1 && need_hashes && !span_sync) {   // hashes + valid bits of the whole batch stay in the scratch
+        ctx->last_hashed.sketch = s;
+        ctx->last_hashed.npos = std::min<uint64_t>(chunk_tiles * KV_TILE, b.total);
+    }
     if (n_kmers_out) {
         CU(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 8, cudaMemcpyDeviceToHost, ctx->compute));
         CU(cudaStreamSynchronize(ctx->compute));
@@ -1905,8 +1939,7 @@ extern "C" int kv_hash_kmers(int hasher, int ksize, const uint8_t *kmers, uint64
     KV_TRY(kv_stage(ctx, kmers, offs.data(), n, KV_MEM_HOST, 0, &b));
     CU(cudaStreamSynchronize(ctx->copy));   // offs is a local
     const uint64_t npos = b.n_tiles * KV_TILE;
-    KV_TRY(kv_buf_ensure(ctx->hashes, npos * 8));
-    KV_TRY(kv_buf_ensure(ctx->valid, (npos / 32 + 1) * 4));
+    KV_TRY(kv_hash_scratch(ctx, npos));
     KV_TRY(kv_buf_ensure(ctx->misc, n * 9));
     KvHashParams p;
     memset(&p, 0, sizeof p);
@@ -1977,8 +2010,7 @@ extern "C" int kv_kmer_counts_batch(const kv_sketch *s, const uint8_t *bases, co
     KV_TRY(kv_stage(ctx, bases, offsets, n_reads, where, 0, &b));
     if (!b.total) { kv_stage_done(ctx, &b); return KV_OK; }
     const uint64_t npos = b.n_tiles * KV_TILE;
-    KV_TRY(kv_buf_ensure(ctx->hashes, npos * 8));
-    KV_TRY(kv_buf_ensure(ctx->valid, (npos / 32 + 1) * 4));
+    KV_TRY(kv_hash_scratch(ctx, npos));
     KV_TRY(kv_buf_ensure(ctx->misc, b.total * 2));
     KvHashParams p;
     memset(&p, 0, sizeof p);
@@ -2030,8 +2062,7 @@ extern "C" int kv_abund_dist_batch(const kv_sketch *counts, kv_sketch *tracking,
     const uint64_t chunk_limit = std::min<uint64_t>(ctx->chunk_bases, (0xfffffff0ull / (uint64_t)tracking->n_tables) / KV_TILE * KV_TILE);
     const uint64_t chunk_tiles = chunk_limit / KV_TILE;
     const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
-    KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
-    KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    KV_TRY(kv_hash_scratch(ctx, chunk_pos));
     for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
         uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
         uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
@@ -2148,8 +2179,7 @@ extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occup
     const uint64_t chunk_limit = std::min<uint64_t>(ctx->chunk_bases, 1ull << KV_POS_BITS);
     const uint64_t chunk_tiles = chunk_limit / KV_TILE;
     const uint64_t chunk_pos = std::min<uint64_t>(chunk_limit, b.n_tiles * KV_TILE);
-    KV_TRY(kv_buf_ensure(ctx->hashes, chunk_pos * 8));
-    KV_TRY(kv_buf_ensure(ctx->valid, (chunk_pos / 32 + 1) * 4));
+    KV_TRY(kv_hash_scratch(ctx, chunk_pos));
     for (uint64_t t0 = 0; t0 < b.n_tiles; t0 += chunk_tiles) {
         const uint64_t nt = std::min(chunk_tiles, b.n_tiles - t0);
         const uint64_t npos = std::min<uint64_t>(nt * KV_TILE, b.total - t0 * KV_TILE);
@@ -2174,6 +2204,48 @@ extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occup
         }
     }
     kv_stage_done(ctx, &b);
+    if (dev_n_unique_out) CU(cudaMemcpyAsync(dev_n_unique_out, d_unique, 8, cudaMemcpyDeviceToDevice, ctx->compute));
+    if (n_unique_out) {
+        CU(cudaMemcpyAsync(ctx->h_counters + 7, d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        *n_unique_out = ctx->h_counters[7];
+    }
+    return KV_OK;
+}
+
+// The same passes over the batch that kv_consume_batch counted into `like` LAST on this device, when its hashes
+// and valid bits are still in the device scratch (one chunk, nothing hashed since): no second copy of the reads
+// to the device, no second MurmurHash -- table 0's pass A runs as a plain pass over the stored hashes.
+// KV_ESTATE when the scratch holds something else; the caller then falls back to kv_unique_batch.
+extern "C" int kv_unique_last_batch(const kv_sketch *like, uint32_t *const *dev_occupied, uint64_t *n_unique_out,
+                                    uint64_t *dev_n_unique_out)
+{
+    if (!like || !dev_occupied || (!n_unique_out && !dev_n_unique_out)) return kv_fail(KV_EINVAL, "null argument");
+    if (n_unique_out) *n_unique_out = 0;
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(like->device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(like->device));
+    if (ctx->last_hashed.sketch != like || !ctx->last_hashed.npos)
+        return kv_fail(KV_ESTATE, "the hashes of the last batch counted into this sketch are no longer in the device scratch");
+    const uint64_t npos = ctx->last_hashed.npos;
+    if (npos > (1ull << KV_POS_BITS)) return kv_fail(KV_ESTATE, "batch too long for one first-touch chunk");
+    KvView v = kv_view(like);
+    v.bits = 8;   // always occ[] (see kv_unique_batch)
+    for (int t = 0; t < like->n_tables; t++) {
+        if (!dev_occupied[t]) return kv_fail(KV_EINVAL, "null occupancy bitmap for table %d", t);
+        v.occ[t] = dev_occupied[t];
+    }
+    unsigned long long *d_unique = ctx->counters + 7;
+    CU(cudaMemsetAsync(d_unique, 0, sizeof(unsigned long long), ctx->compute));
+    const uint64_t *d_hashes = (const uint64_t *)ctx->hashes.p;
+    const uint32_t *d_valid = (const uint32_t *)ctx->valid.p;
+    KvFreshPre pre;
+    KV_TRY(kv_fresh_prepare(ctx, like, v, ctx->unique_fuse0, &pre, false));
+    if (pre.fused0)
+        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min0_kernel, kv_grid_for(ctx, npos), 256, v, (uint32_t *)ctx->first.p, pre.tag0,
+                 d_hashes, d_valid, npos);
+    KV_TRY(kv_count_fresh(ctx, like, v, pre, d_hashes, d_valid, npos, nullptr, nullptr, d_unique));
     if (dev_n_unique_out) CU(cudaMemcpyAsync(dev_n_unique_out, d_unique, 8, cudaMemcpyDeviceToDevice, ctx->compute));
     if (n_unique_out) {
         CU(cudaMemcpyAsync(ctx->h_counters + 7, d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -2238,10 +2310,28 @@ static int kv_merge_peers_impl(kv_sketch *s, void *const *peer_flat, int n_peers
     peers.n = n_peers;
     for (int i = 0; i < n_peers; i++) peers.peer[i] = (uint4 *)((uint8_t *)peer_flat[i] + byte_lo);
     uint64_t n_vec = (byte_hi - byte_lo) / 16;
-    if (push)
-        LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel<true>, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
-    else
-        LAUNCH_C(KV_PROF_MERGE, ctx, kv_merge_peers_kernel<false>, kv_grid_for(ctx, n_vec, 16), 256, (uint4 *)(s->flat + byte_lo), n_vec, s->bits, peers);
+    // on the merge lane the kernel shares the SMs with the counting of the next sample: a few CTAs per SM are
+    // enough to keep the links busy (8 loads in flight per thread) and leave the rest of the machine alone
+    cudaStream_t lane = ctx->forked ? ctx->merge : ctx->compute;
+    const int vecs = n_peers > 7 ? 1 : std::min(4, std::max(1, 8 / n_peers));   // vectors per thread and iteration (U below)
+    const unsigned grid = ctx->forked ? (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_vec + 255) / 256, (uint64_t)ctx->sm_count * ctx->merge_lane_ctas))
+                                      : kv_grid_for(ctx, (n_vec + vecs - 1) / vecs, 16);
+    uint4 *mine = (uint4 *)(s->flat + byte_lo);
+#define KV_MERGE_CASE(NP_, EXACT_)                                                                                               \
+    if (push) LAUNCH_S(KV_PROF_MERGE, ctx, lane, (kv_merge_peers_kernel<true, NP_, (NP_ <= 2 ? 4 : NP_ <= 4 ? 2 : 1), EXACT_>), grid, 256, mine, n_vec, s->bits, peers); \
+    else LAUNCH_S(KV_PROF_MERGE, ctx, lane, (kv_merge_peers_kernel<false, NP_, (NP_ <= 2 ? 4 : NP_ <= 4 ? 2 : 1), EXACT_>), grid, 256, mine, n_vec, s->bits, peers);     \
+    break;
+    switch (n_peers) {
+    case 1: KV_MERGE_CASE(1, true)
+    case 2: KV_MERGE_CASE(2, true)
+    case 3: KV_MERGE_CASE(3, true)
+    case 4: KV_MERGE_CASE(4, true)
+    case 5: KV_MERGE_CASE(5, true)
+    case 6: KV_MERGE_CASE(6, true)
+    case 7: KV_MERGE_CASE(7, true)
+    default: KV_MERGE_CASE(8, false)
+    }
+#undef KV_MERGE_CASE
     s->state_stale = true;
     s->unique_valid = false;
     return KV_OK;
@@ -2313,6 +2403,7 @@ struct kv_peer_sync {
     void *peer[KV_MAX_RANKS];   // mapped peer arrays
     uint32_t epoch;
     unsigned long long timeout_ns;
+    int lane;                   // 0: barriers on the compute stream; 1: on the merge lane (kv_peer_sync_set_lane)
 };
 
 extern "C" int kv_peer_sync_create(int device, int rank, int world, kv_peer_sync **out, uint8_t handle_out[64])
@@ -2363,7 +2454,8 @@ static int kv_peer_barrier_locked(KvCtx *ctx, kv_peer_sync *ps)
     }
     f.mine = ps->flags; f.rank = ps->rank; f.world = ps->world;
     ps->epoch++;
-    LAUNCH_C(KV_PROF_MERGE, ctx, kv_peer_barrier_kernel, 1, 32, f, ps->epoch, ps->timeout_ns, ps->timed_out);
+    LAUNCH_S(KV_PROF_MERGE, ctx, ps->lane ? ctx->merge : ctx->compute, kv_peer_barrier_kernel, 1, 32, f, ps->epoch, ps->timeout_ns,
+             ps->timed_out);
     return KV_OK;
 }
 
@@ -2382,7 +2474,44 @@ extern "C" int kv_peer_barrier(kv_peer_sync *ps)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ps->device));
     ps->epoch++;
-    LAUNCH_C(KV_PROF_MERGE, ctx, kv_peer_barrier_kernel, 1, 32, f, ps->epoch, ps->timeout_ns, ps->timed_out);
+    LAUNCH_S(KV_PROF_MERGE, ctx, ps->lane ? ctx->merge : ctx->compute, kv_peer_barrier_kernel, 1, 32, f, ps->epoch, ps->timeout_ns,
+             ps->timed_out);
+    return KV_OK;
+}
+
+extern "C" int kv_peer_sync_set_lane(kv_peer_sync *ps, int lane)
+{
+    if (!ps || lane < 0 || lane > 1) return kv_fail(KV_EINVAL, "lane is 0 (compute stream) or 1 (merge lane)");
+    ps->lane = lane;
+    return KV_OK;
+}
+
+// Merge lane.  kv_merge_fork: whatever is enqueued on the compute stream so far (the sample just counted) must
+// finish before anything enqueued on the merge lane from now on; until kv_merge_join the peer-to-peer merge
+// kernels go to the merge lane, so the merge of sample i crosses NVLink while sample i+1 is being counted.
+// Fork may be called repeatedly (once per sample); kv_merge_join makes the compute stream wait for the lane.
+extern "C" int kv_merge_fork(int device)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    CU(cudaEventRecord(ctx->ev_fork, ctx->compute));
+    CU(cudaStreamWaitEvent(ctx->merge, ctx->ev_fork, 0));
+    ctx->forked = true;
+    return KV_OK;
+}
+
+extern "C" int kv_merge_join(int device)
+{
+    KvCtx *ctx;
+    KV_TRY(kv_ctx_get(device, &ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(device));
+    if (!ctx->forked) return KV_OK;
+    CU(cudaEventRecord(ctx->ev_join, ctx->merge));
+    CU(cudaStreamWaitEvent(ctx->compute, ctx->ev_join, 0));
+    ctx->forked = false;
     return KV_OK;
 }
 
@@ -2394,6 +2523,7 @@ extern "C" int kv_peer_sync_status(kv_peer_sync *ps)
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ps->device));
     unsigned flag = 0;
+    CU(cudaStreamSynchronize(ctx->merge));
     CU(cudaMemcpyAsync(&flag, ps->timed_out, sizeof flag, cudaMemcpyDeviceToHost, ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     if (flag) return kv_fail(KV_ECUDA, "a device-side barrier timed out waiting for a peer rank (KV_PEER_TIMEOUT_MS)");

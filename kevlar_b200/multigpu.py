@@ -191,12 +191,13 @@ def release_p2p(sketches, group=None):
         td.barrier(group=group)
 
 
-_PEER_SYNC = {}   # (device, group id) -> kv_peer_sync handle with every peer connected
+_PEER_SYNC = {}   # (device, group id, lane) -> kv_peer_sync handle with every peer connected
 
 
-def _peer_sync(device, group=None):
-    """This rank's device-side barrier object (created and connected once per device and group)."""
-    key = (device, id(group))
+def _peer_sync(device, group=None, lane=0):
+    """This rank's device-side barrier object (created and connected once per device, group and lane; lane 1 =
+    the merge lane of kv_merge_fork, whose barriers must not interleave with those of the compute stream)."""
+    key = (device, id(group), lane)
     if key in _PEER_SYNC:
         return _PEER_SYNC[key]
     td = dist()
@@ -208,13 +209,15 @@ def _peer_sync(device, group=None):
     for r, h in enumerate(handles):
         if r != rank:
             check(lib().kv_peer_sync_connect(ps, r, (ctypes.c_uint8 * 64)(*h)))
+    if lane:
+        check(lib().kv_peer_sync_set_lane(ps, lane))
     _PEER_SYNC[key] = ps
     return ps
 
 
 def peer_sync_status(device=None):
     """Drain the compute stream and raise if a device-side barrier gave up waiting for a peer."""
-    for (dev, _), ps in _PEER_SYNC.items():
+    for (dev, _, _), ps in _PEER_SYNC.items():
         if device is None or dev == device:
             check(lib().kv_peer_sync_status(ps))
 
@@ -246,7 +249,7 @@ def shutdown(sketches=(), destroy_group=True):
             td.destroy_process_group()
 
 
-def merge_p2p(sketches, group=None, host_barriers=False):
+def merge_p2p(sketches, group=None, host_barriers=False, lane=0):
     """Peer-to-peer merge with no NCCL on the data path.  Ranks exchange CUDA IPC handles of
     their table storage once; then, for all sketches together, rank r owns byte slice(r) of every
     table: it loads that slice from every peer over NVLink, folds it into its own table and
@@ -259,7 +262,10 @@ def merge_p2p(sketches, group=None, host_barriers=False):
       host_barriers=True (how='p2p_host'):  two phases, reduce-scatter (kv_sketch_merge_peers)
                 then all-gather (kv_sketch_copy_from_peer pulls slice(p) from peer p), separated
                 by stream syncs + process-group barriers -- for ranks that may reach the merge
-                more than KV_PEER_TIMEOUT_MS apart, or more than 16 ranks."""
+                more than KV_PEER_TIMEOUT_MS apart, or more than 16 ranks.
+
+    `lane=1` (after kv_merge_fork, device-side barriers only): barriers and merge kernels run on the library's
+    merge lane instead of its compute stream."""
     td = dist()
     if not isinstance(sketches, (list, tuple)):
         sketches = [sketches]
@@ -275,7 +281,7 @@ def merge_p2p(sketches, group=None, host_barriers=False):
             yield sk, pr, nbytes
 
     if not host_barriers:
-        sync = _peer_sync(device, group)
+        sync = _peer_sync(device, group, lane)
         check(lib().kv_peer_barrier(sync))            # every partial table is complete
         for sk, pr, nbytes in slices():
             lo, hi = slice_bounds(nbytes, rank, world)
@@ -349,6 +355,46 @@ def _occupancy_view(sketch):
     return _device_words(base, total, sketch.device, sketch), starts
 
 
+def _unique_share(sketch, batch, total_ptr, keep, kw, group, world, rank, from_scratch):
+    """Enqueue THIS rank's share of one sketch's n_unique_kmers (a device int64 at `total_ptr`): all-gather of the
+    occupancy bitmaps, OR of the lower ranks', first-touch passes over this rank's reads.  `from_scratch`: try the
+    hashes the consume call left on the device first (kv_unique_last_batch)."""
+    import torch
+    td = dist()
+    bases, offsets = batch
+    mine, starts = _occupancy_view(sketch)
+    lower = torch.zeros_like(mine)
+    if world > 1:
+        gathered = torch.empty((world, mine.numel()), dtype=mine.dtype, device=mine.device)
+        td.all_gather_into_tensor(gathered, mine, group=group)
+        for q in range(rank):
+            lower |= gathered[q]
+        keep.append(gathered)
+    keep.append(lower)
+    occ = (c_void_p * len(starts))(*[lower.data_ptr() + 4 * st for st in starts])
+    if from_scratch:
+        rc = lib().kv_unique_last_batch(sketch._h, occ, None, total_ptr)
+        if rc != _lib.KV_ESTATE:
+            check(rc)
+            return
+    where = kw['where']
+    if where == _lib.MEM_HOST:
+        bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
+        bptr, optr, n_reads = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1
+    else:
+        bptr, (optr, n_reads) = bases, offsets
+    mask = kw['mask']
+    check(lib().kv_unique_batch(sketch._h, occ, bptr, optr, n_reads, where, int(kw['num_bands'] or 0), int(kw['band'] or 0),
+                                mask._h if mask is not None else None, int(kw['threshold']), int(bool(kw['consume_masked'])),
+                                None, total_ptr))
+
+
+def _retire(tensors, stream):
+    """Scratch tensors must outlive the kernels that read them: hand them to the stream."""
+    for tensor in tensors:
+        tensor.record_stream(stream)
+
+
 def unique_across_ranks(sketches, batches, where=_lib.MEM_HOST, num_bands=None, band=None, mask=None, threshold=0,
                         consume_masked=False, group=None, store=True):
     """khmer's n_unique_kmers for samples whose reads are sharded contiguously over the ranks (rank order = file
@@ -356,7 +402,7 @@ def unique_across_ranks(sketches, batches, where=_lib.MEM_HOST, num_bands=None, 
     and BEFORE the merge.  Each rank ORs the occupancy bitmaps of all lower ranks' partial sketches and re-runs
     the first-touch passes over its own reads with that as the occupied set (kv_unique_batch); the sum over the
     ranks is the number the reference logs (kevlar/count.py:84).  `batches` = one (bases, offsets) per sketch, in
-    the form `consume_batch` takes for `where`.
+    the form `consume_batch` took for `where` -- for each sketch the batch counted into it LAST.
 
     Everything is enqueued on the library's stream -- the torch ops and the NCCL collectives run under it too --
     so the host never waits.  Returns a device tensor (int64, one entry per sketch) holding the totals; with
@@ -369,67 +415,76 @@ def unique_across_ranks(sketches, batches, where=_lib.MEM_HOST, num_bands=None, 
     device = sketches[0].device
     dev = torch.device('cuda', device)
     stream = torch.cuda.ExternalStream(_lib.stream_ptr(device), device=dev)
+    kw = dict(num_bands=num_bands, band=band, mask=mask, threshold=threshold, consume_masked=consume_masked, where=where)
     keep = []
     with torch.cuda.stream(stream):
         totals = torch.zeros(len(sketches), dtype=torch.int64, device=dev)
-        for i, (sketch, (bases, offsets)) in enumerate(zip(sketches, batches)):
-            mine, starts = _occupancy_view(sketch)
-            lower = torch.zeros_like(mine)
-            if world > 1:
-                gathered = [torch.empty_like(mine) for _ in range(world)]
-                td.all_gather(gathered, mine, group=group)
-                for q in range(rank):
-                    lower |= gathered[q]
-                keep.append(gathered)
-            keep.append(lower)
-            occ = (c_void_p * len(starts))(*[lower.data_ptr() + 4 * st for st in starts])
-            if where == _lib.MEM_HOST:
-                bases, offsets = _lib.as_u8(bases), _lib.as_u64(offsets)
-                bptr, optr, n_reads = bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1
-            else:
-                bptr, (optr, n_reads) = bases, offsets
-            check(lib().kv_unique_batch(sketch._h, occ, bptr, optr, n_reads, where, int(num_bands or 0), int(band or 0),
-                                        mask._h if mask is not None else None, int(threshold), int(bool(consume_masked)),
-                                        None, totals.data_ptr() + 8 * i))
+        for i, (sketch, batch) in enumerate(zip(sketches, batches)):
+            _unique_share(sketch, batch, totals.data_ptr() + 8 * i, keep, kw, group, world, rank, from_scratch=True)
         if world > 1:
             td.all_reduce(totals, op=td.ReduceOp.SUM, group=group)
         if store:
             for i, sketch in enumerate(sketches):
                 check(lib().kv_sketch_set_unique_dev(sketch._h, totals.data_ptr() + 8 * i))
-        # the scratch tensors must outlive the kernels that read them: hand them to the stream
-        for tensor in [totals] + [t for item in keep for t in (item if isinstance(item, list) else [item])]:
-            tensor.record_stream(stream)
+        _retire([totals] + keep, stream)
     return totals
 
 
 def count_sharded(sketches, batches, how='p2p', where=_lib.MEM_HOST, num_bands=None, band=None, mask=None, threshold=0,
-                  consume_masked=False, exact_unique=True, group=None):
+                  consume_masked=False, exact_unique=True, group=None, overlap=True):
     """`kevlar count` of one or more samples on all ranks (plan A): THIS rank's contiguous shard of each sample's
     reads goes into the matching sketch (which must be empty), the partial sketches are merged, and -- with
     `exact_unique` -- every merged sketch reports the reference's n_unique_kmers.  COLLECTIVE.  `sketches` /
-    `batches` may be single objects or equally long lists."""
+    `batches` may be single objects or equally long lists.
+
+    With `exact_unique` each sample's share of n_unique_kmers is taken right after its shard has been counted,
+    while the shard's hashes are still on the device (kv_unique_last_batch: the reads are copied and hashed
+    once); a shard too long for one chunk goes through kv_unique_batch instead.
+
+    `overlap` (several samples, how='p2p'): the merge of sample i runs on the merge lane (kv_merge_fork) while
+    sample i+1 is being counted -- each sample's sketch is independent, so only the last merge is exposed."""
+    import torch
     single = not isinstance(sketches, (list, tuple))
     if single:
         sketches, batches = [sketches], [batches]
     td = dist()
     world = td.get_world_size(group) if td.is_initialized() else 1
+    rank = td.get_rank(group) if td.is_initialized() else 0
     kw = dict(num_bands=num_bands, band=band, mask=mask, threshold=threshold, consume_masked=consume_masked, where=where)
     if world == 1:
         for sketch, (bases, offsets) in zip(sketches, batches):
             sketch.consume_batch(bases, offsets, wait=False, **kw)
         return
-    for sketch, (bases, offsets) in zip(sketches, batches):
-        sketch.set_unique_tracking(False)
-        sketch.consume_batch(bases, offsets, wait=False, **kw)
-    totals = unique_across_ranks(sketches, batches, group=group, store=False, **kw) if exact_unique else None
-    if how != 'p2p':
-        _lib.sync(sketches[0].device)
-    merge_sketches(sketches, how=how, group=group)
+    device = sketches[0].device
+    dev = torch.device('cuda', device)
+    stream = torch.cuda.ExternalStream(_lib.stream_ptr(device), device=dev)
+    totals, keep = None, []
+    pipelined = overlap and how == 'p2p' and world <= 16 and len(sketches) > 1
+    with torch.cuda.stream(stream):
+        if exact_unique:
+            totals = torch.zeros(len(sketches), dtype=torch.int64, device=dev)
+        for i, (sketch, (bases, offsets)) in enumerate(zip(sketches, batches)):
+            sketch.set_unique_tracking(False)
+            sketch.consume_batch(bases, offsets, wait=False, **kw)
+            if exact_unique:
+                _unique_share(sketch, (bases, offsets), totals.data_ptr() + 8 * i, keep, kw, group, world, rank, from_scratch=True)
+            if pipelined:
+                check(lib().kv_merge_fork(device))
+                merge_p2p([sketch], group, lane=1)
+        if exact_unique:
+            td.all_reduce(totals, op=td.ReduceOp.SUM, group=group)
+    if pipelined:
+        check(lib().kv_merge_join(device))
+    else:
+        if how != 'p2p':
+            _lib.sync(device)
+        merge_sketches(sketches, how=how, group=group)
     if totals is not None:   # after the merge, which marks the sketches' own counter as stale
         if how != 'p2p':
-            _lib.sync(sketches[0].device)
+            _lib.sync(device)
         for i, sketch in enumerate(sketches):
             check(lib().kv_sketch_set_unique_dev(sketch._h, totals.data_ptr() + 8 * i))
+        _retire([totals] + keep, stream)
 
 
 def gather_hits(hits, read_base, group=None):

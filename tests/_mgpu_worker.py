@@ -91,6 +91,41 @@ def main():
             multigpu.peer_sync_status()
             multigpu.release_p2p([g])
             del g
+    # ---- the whole trio in one call: each sample's merge runs on the merge lane while the next sample is being
+    # counted (kv_merge_fork / kv_merge_join); twice over the same sketches (clear in between), with and without
+    # the exact n_unique_kmers, then the shard-local novel scan on the merged sketches
+    for cls in (() if only else ('Counttable', 'SmallCounttable')):
+        trio_g = [getattr(kv.khmer, cls)(25, 30000, 4) for _ in samples]
+        trio_c = [getattr(ko, cls)(25, 30000, 4) for _ in samples]
+        shards = []
+        for seqs, c in zip(samples, trio_c):
+            bases, offs = ko.reads_to_batch(seqs)
+            shards.append(multigpu.shard_batch(bases, offs, rank, world))
+            c.consume_batch(bases, offs)
+        for exact in (True, False, True):
+            for g in trio_g:
+                g.clear()
+            multigpu.count_sharded(trio_g, shards, exact_unique=exact)
+            for si, (g, c) in enumerate(zip(trio_g, trio_c)):
+                if exact and g.n_unique_kmers() != c.n_unique_kmers():
+                    failures.append('pipelined count_sharded {} sample {}: n_unique {} != {} on rank {}'.format(
+                        cls, si, g.n_unique_kmers(), c.n_unique_kmers(), rank))
+                for t in range(4):
+                    if g.table_bytes(t) != c.table_bytes(t):
+                        failures.append('pipelined count_sharded {} sample {} table {} differs on rank {} (exact={})'.format(
+                            cls, si, t, rank, exact))
+        bases, offs = ko.reads_to_batch(samples[0])
+        lo, _ = multigpu.shard_bounds(len(samples[0]), rank, world)
+        hits, flags, _ = kv.khmer.novel_batch(trio_g[:1], trio_g[1:], shards[0][0], shards[0][1], 6, 1)
+        allhits = multigpu.gather_hits(hits, lo)
+        ohits, _ = ko.novel_batch(trio_c[:1], trio_c[1:], bases, offs, 6, 1)
+        allhits = allhits[np.lexsort((allhits['offset'], allhits['read']))]
+        if len(allhits) != len(ohits) or not (allhits['offset'] == ohits['offset']).all() or \
+                not (allhits['abund'][:, :3] == ohits['abund'][:, :3]).all():
+            failures.append('pipelined count_sharded {}: novel hits differ ({} vs {})'.format(cls, len(allhits), len(ohits)))
+        multigpu.peer_sync_status()
+        multigpu.release_p2p(trio_g)
+        del trio_g
     import tempfile
     shared = os.environ.get('KV_TEST_SHARED_DIR') or tempfile.gettempdir()
     # ---- plan B, second design: spanning sketches (tables spread over the HBM of all ranks, updates exchanged

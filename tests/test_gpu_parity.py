@@ -1189,3 +1189,45 @@ def test_unique_across_shards_on_one_gpu(kv, oracle, name, monkeypatch):
                                     0, byref(n), None))
         total += n.value
     assert total == c.n_unique_kmers()
+
+
+@pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'])
+def test_unique_from_the_hashes_left_on_the_device(kv, oracle, name):
+    """kv_unique_last_batch: the same shares as kv_unique_batch, taken from the hashes the consume call left in
+    the device scratch (no second copy of the reads, no second hash); KV_ESTATE -- and nothing done -- once
+    another batch has been hashed."""
+    torch = pytest.importorskip('torch')
+    from ctypes import byref, c_uint64, c_void_p
+    from kevlar_b200 import multigpu
+    from kevlar_b200._lib import KV_ESTATE, check, lib
+    reads = random_reads(71, 2500, 30, 140) + [b'ACGTTGCAAGGCTTAACCGGTTAAACCCGGGTTTACGT'] * 300 + random_reads(72, 500, 30, 140)
+    reads[17] = b'ACGTNNACGT' * 5          # cleaned like everything else
+    reads[18] = b'ACGT'                     # shorter than k
+    bases, offs = oracle.reads_to_batch(reads)
+    c = getattr(oracle, name)(21, 20000, 4)
+    c.consume_batch(bases, offs)
+    parts, occs, total = [], [], 0
+    for r in range(3):
+        mb, mo = multigpu.shard_batch(bases, offs, r, 3)
+        g = getattr(kv.khmer, name)(21, 20000, 4)
+        g.set_unique_tracking(False)
+        g.consume_batch(mb, mo)
+        view, starts = multigpu._occupancy_view(g)
+        lower = torch.zeros_like(view)
+        for q in range(r):
+            lower |= occs[q]
+        torch.cuda.synchronize()
+        occ = (c_void_p * 4)(*[lower.data_ptr() + 4 * int(starts[t]) for t in range(4)])
+        n, n_again = c_uint64(), c_uint64()
+        check(lib().kv_unique_last_batch(g._h, occ, byref(n), None))
+        check(lib().kv_unique_batch(g._h, occ, mb.ctypes.data, mo.ctypes.data, len(mo) - 1, kv.khmer.MEM_HOST, 0, 0, None, 0, 0,
+                                    byref(n_again), None))
+        assert n.value == n_again.value, r
+        if parts:   # the scratch now holds shard r: an earlier sketch cannot use the shortcut
+            stale = c_uint64(123)
+            assert lib().kv_unique_last_batch(parts[0]._h, occ, byref(stale), None) == KV_ESTATE
+        kv._lib.sync(g.device)
+        occs.append(view.clone())
+        parts.append(g)
+        total += n.value
+    assert total == c.n_unique_kmers()
