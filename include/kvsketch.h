@@ -103,7 +103,8 @@ int kv_sketch_stats(kv_sketch *s, uint64_t *n_occupied, uint64_t *n_unique, int 
 
 /* Turn the exact n_unique_kmers bookkeeping on/off (default on; costs two extra passes per
  * table over each batch and a scratch array of 4 bytes per bucket of the LARGEST table, shared
- * per device). */
+ * per device).  on = 2, "deferred": off, but a consume that fits one chunk already runs table 0's
+ * first-touch pass inside its hash kernel, for the kv_unique_last_batch that follows (multi-GPU counts). */
 int kv_sketch_set_unique_tracking(kv_sketch *s, int on);
 
 /* Raw table storage, for collectives that the host runs over it (torch.distributed/NCCL)

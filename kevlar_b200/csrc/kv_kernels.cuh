@@ -1241,11 +1241,12 @@ __device__ __forceinline__ uint32_t kv_sat_merge_word(uint32_t a, uint32_t b, in
 // Every thread keeps 4 to 8 loads over NVLink in flight: U vectors x NP peers, all issued -- unconditionally, so
 // that the compiler cannot serialise them behind predicates -- before the first one is used.  EXACT: the sketch has
 // exactly NP peers (worlds up to 8: one instantiation per peer count); otherwise peers are taken in groups of NP = 8
-// and a short last group re-reads its last peer and discards the copy.  A load over NVLink takes a few microseconds:
-// with one in flight per thread the 8-rank merge ran at a third of the link rate (profiles/r02o_bench_n8.json:
-// 306 GB/s in + 306 GB/s out per rank), and on the merge lane (kv_merge_fork) the kernel gets only a couple of
-// CTAs per SM, so the depth has to come from each thread.  Vectors past the end are clamped for the loads and
-// skipped by the stores.
+// and a short last group re-reads its last peer and discards the copy.  The depth comes from each thread because on
+// the merge lane (kv_merge_fork) the kernel gets one CTA per SM.  Measured at 8 ranks, 3 x 4 GB sketches: 10.5 GB
+// read from and 10.5 GB stored to the peers per rank in 34 ms -- every link direction carries the read responses of
+// one side plus the stores of the other, 614 GB/s per direction, about what NVLink 5 delivers in practice; the wide
+// single-load version of round 1 reached the same rate with 16x the CTAs (profiles/r02_notes.md, section 4).
+// Vectors past the end are clamped for the loads and skipped by the stores.
 template <bool PUSH, int NP, int U, bool EXACT>
 __global__ void __launch_bounds__(256) kv_merge_peers_kernel(uint4 *__restrict__ local, uint64_t n_vec, int bits,
                                                              const __grid_constant__ KvPeers peers)

@@ -125,7 +125,7 @@ struct KvCtx {
     uint64_t chunk_bases = 64ull << 20;
     // the batch whose hashes + valid bits still sit in `hashes` / `valid` (kv_unique_last_batch): set by a
     // single-chunk kv_consume_batch, dropped by whatever claims the scratch next
-    struct { const kv_sketch *sketch = nullptr; uint64_t serial = 0, npos = 0; } last_hashed;
+    struct { const kv_sketch *sketch = nullptr; uint64_t npos = 0; bool pass_a = false; uint32_t tag0 = 0; } last_hashed;
 };
 
 static KvCtx g_ctx[16];
@@ -330,6 +330,7 @@ struct kv_sketch {
     uint64_t hot_base[KV_TABLES_DEV]; // first bit of each table inside the hot bitmap
     uint64_t state_words;
     bool track_unique, unique_valid;
+    bool defer_unique;                // not tracked, but a single-chunk consume runs table 0's first-touch pass A so that kv_unique_last_batch need not
     bool state_stale;                 // tables were written behind the kernels' back: rebuild the hot bitmap before the next update
     uint64_t n_unique;                // host copy, updated at stats time
     unsigned long long *d_unique;     // device accumulator
@@ -578,7 +579,8 @@ extern "C" int kv_sketch_info(const kv_sketch *s, int *hasher, int *bits, int *k
 extern "C" int kv_sketch_set_unique_tracking(kv_sketch *s, int on)
 {
     if (!s) return kv_fail(KV_EINVAL, "null sketch");
-    s->track_unique = on != 0;
+    s->track_unique = on == 1;
+    s->defer_unique = on == 2;
     return KV_OK;
 }
 
@@ -1280,7 +1282,8 @@ static int kv_first_tag(KvCtx *ctx, uint32_t *tag)
 
 // Before the chunk is hashed: which buckets are empty right now (= at chunk start), the first[] scratch,
 // and -- when table 0 fits first[] -- the tag under which the hash kernel runs table 0's pass A.
-static int kv_fresh_prepare(KvCtx *ctx, const kv_sketch *s, const KvView &v, bool may_fuse, KvFreshPre *pre, bool rebuild_occ = true)
+static int kv_fresh_prepare(KvCtx *ctx, const kv_sketch *s, const KvView &v, bool may_fuse, KvFreshPre *pre, bool rebuild_occ = true,
+                            const uint32_t *done_tag0 = nullptr)
 {
     uint64_t maxsize = 0;
     for (int t = 0; t < s->n_tables; t++) maxsize = std::max(maxsize, s->sizes[t]);
@@ -1301,7 +1304,10 @@ static int kv_fresh_prepare(KvCtx *ctx, const kv_sketch *s, const KvView &v, boo
     pre->range = range;
     pre->fused0 = may_fuse && s->sizes[0] <= range && s->sizes[0] > 0;
     pre->tag0 = 0;
-    if (pre->fused0) KV_TRY(kv_first_tag(ctx, &pre->tag0));
+    if (pre->fused0) {
+        if (done_tag0) pre->tag0 = *done_tag0;   // table 0's pass A already ran under this tag (deferred n_unique)
+        else KV_TRY(kv_first_tag(ctx, &pre->tag0));
+    }
     return KV_OK;
 }
 
@@ -1589,6 +1595,8 @@ static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *o
         return kv_fail(KV_EINVAL, "this rank's batch needs %llu chunks, the collective call announced %llu",
                        (unsigned long long)own_chunks, (unsigned long long)n_chunks);
     const uint64_t total_chunks = span_sync ? n_chunks : own_chunks;
+    bool deferred_pass_a = false;
+    uint32_t deferred_tag0 = 0;
     for (uint64_t ci = 0; ci < total_chunks; ci++) {
         const uint64_t t0 = ci * chunk_tiles;
         if (t0 >= b.n_tiles) {   // collective call, nothing left here: take part in the exchange with empty slabs
@@ -1616,6 +1624,19 @@ static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *o
             }
             KV_TRY(kv_fresh_prepare(ctx, s, sv, ctx->unique_fuse0, &pre));
             if (pre.fused0) { p.track0 = 1; p.first0 = (uint32_t *)ctx->first.p; p.tag0 = pre.tag0; p.sk = sv; }
+        } else if (s->defer_unique && total_chunks == 1 && !plan.on && ctx->unique_fuse0) {
+            // deferred n_unique (kv_unique_last_batch will follow): table 0's pass A rides along in the hash kernel now.
+            // Which buckets the OTHER ranks occupy is not known yet, but the owner of a bucket -- the first position of
+            // this batch that touches it -- does not depend on that; the later passes only ask whether the bucket counts.
+            if (s->state_stale) {
+                KV_TRY(kv_state_rebuild_locked(ctx, s));
+                s->state_stale = false;
+            }
+            KV_TRY(kv_fresh_prepare(ctx, s, sv, true, &pre));
+            if (pre.fused0) {
+                p.track0 = 1; p.first0 = (uint32_t *)ctx->first.p; p.tag0 = pre.tag0; p.sk = sv;
+                deferred_pass_a = true; deferred_tag0 = pre.tag0;
+            }
         }
         if (plan.on) {
             p.scatter = 1; p.ti = plan.ti; p.sk = sv;
@@ -1644,6 +1665,8 @@ static int kv_consume_impl(kv_sketch *s, const uint8_t *bases, const uint64_t *o
     if (total_chunks == 1 && need_hashes && !span_sync) {   // hashes + valid bits of the whole batch stay in the scratch
         ctx->last_hashed.sketch = s;
         ctx->last_hashed.npos = std::min<uint64_t>(chunk_tiles * KV_TILE, b.total);
+        ctx->last_hashed.pass_a = deferred_pass_a;
+        ctx->last_hashed.tag0 = deferred_tag0;
     }
     if (n_kmers_out) {
         CU(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -2241,10 +2264,12 @@ extern "C" int kv_unique_last_batch(const kv_sketch *like, uint32_t *const *dev_
     const uint64_t *d_hashes = (const uint64_t *)ctx->hashes.p;
     const uint32_t *d_valid = (const uint32_t *)ctx->valid.p;
     KvFreshPre pre;
-    KV_TRY(kv_fresh_prepare(ctx, like, v, ctx->unique_fuse0, &pre, false));
-    if (pre.fused0)
+    const bool pass_a_done = ctx->last_hashed.pass_a;
+    KV_TRY(kv_fresh_prepare(ctx, like, v, ctx->unique_fuse0, &pre, false, pass_a_done ? &ctx->last_hashed.tag0 : nullptr));
+    if (pre.fused0 && !pass_a_done)
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min0_kernel, kv_grid_for(ctx, npos), 256, v, (uint32_t *)ctx->first.p, pre.tag0,
                  d_hashes, d_valid, npos);
+    ctx->last_hashed.sketch = nullptr;   // first[] is about to be reused for the other tables: the shortcut works once
     KV_TRY(kv_count_fresh(ctx, like, v, pre, d_hashes, d_valid, npos, nullptr, nullptr, d_unique));
     if (dev_n_unique_out) CU(cudaMemcpyAsync(dev_n_unique_out, d_unique, 8, cudaMemcpyDeviceToDevice, ctx->compute));
     if (n_unique_out) {

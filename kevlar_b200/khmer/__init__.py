@@ -101,7 +101,10 @@ class _Sketch(object):
         check(lib().kv_sketch_clear(self._h))
 
     def set_unique_tracking(self, on):
-        check(lib().kv_sketch_set_unique_tracking(self._h, int(bool(on))))
+        """True / False: the exact n_unique_kmers bookkeeping of every consume.  'deferred': not tracked, but a
+        consume that fits one chunk prepares the first-touch passes that `multigpu.count_sharded` runs once the
+        other ranks' occupancy is known (kv_unique_last_batch)."""
+        check(lib().kv_sketch_set_unique_tracking(self._h, 2 if on == 'deferred' else int(bool(on))))
 
     def table_bytes(self, t):
         """Raw khmer-layout bytes of table t (D2H copy)."""

@@ -464,7 +464,7 @@ def count_sharded(sketches, batches, how='p2p', where=_lib.MEM_HOST, num_bands=N
         if exact_unique:
             totals = torch.zeros(len(sketches), dtype=torch.int64, device=dev)
         for i, (sketch, (bases, offsets)) in enumerate(zip(sketches, batches)):
-            sketch.set_unique_tracking(False)
+            sketch.set_unique_tracking('deferred' if exact_unique else False)
             sketch.consume_batch(bases, offsets, wait=False, **kw)
             if exact_unique:
                 _unique_share(sketch, (bases, offsets), totals.data_ptr() + 8 * i, keep, kw, group, world, rank, from_scratch=True)

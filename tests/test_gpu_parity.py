@@ -1191,11 +1191,12 @@ def test_unique_across_shards_on_one_gpu(kv, oracle, name, monkeypatch):
     assert total == c.n_unique_kmers()
 
 
+@pytest.mark.parametrize('mode', [False, 'deferred'])
 @pytest.mark.parametrize('name', ['Counttable', 'SmallCounttable', 'Nodetable', 'Countgraph'])
-def test_unique_from_the_hashes_left_on_the_device(kv, oracle, name):
+def test_unique_from_the_hashes_left_on_the_device(kv, oracle, name, mode):
     """kv_unique_last_batch: the same shares as kv_unique_batch, taken from the hashes the consume call left in
     the device scratch (no second copy of the reads, no second hash); KV_ESTATE -- and nothing done -- once
-    another batch has been hashed."""
+    another batch has been hashed.  'deferred': the consume call has already run table 0's first-touch pass."""
     torch = pytest.importorskip('torch')
     from ctypes import byref, c_uint64, c_void_p
     from kevlar_b200 import multigpu
@@ -1210,7 +1211,7 @@ def test_unique_from_the_hashes_left_on_the_device(kv, oracle, name):
     for r in range(3):
         mb, mo = multigpu.shard_batch(bases, offs, r, 3)
         g = getattr(kv.khmer, name)(21, 20000, 4)
-        g.set_unique_tracking(False)
+        g.set_unique_tracking(mode)
         g.consume_batch(mb, mo)
         view, starts = multigpu._occupancy_view(g)
         lower = torch.zeros_like(view)
