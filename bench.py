@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument('--no-unique', action='store_true', help='skip the exact n_unique_kmers bookkeeping')
     ap.add_argument('--no-overlap', action='store_true', help="N > 1: merge all sketches after the last sample instead of "
                     "merging each sample's sketch on the merge lane while the next sample is counted")
+    ap.add_argument('--no-files', action='store_true', help='N = 1: skip the file-based path (FASTQ files -> sketch files -> augmented FASTQ)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-variants', action='store_true')
     ap.add_argument('--no-c3', action='store_true', help='skip the config-3 (100 Mbp, 3 x 4 GB sketches) part')
@@ -924,6 +925,64 @@ def run_c5(args, rank, world, trio0, barrier, phase):
     return out
 
 
+def run_files(args, trio0, phase):
+    """The FILE-based path at N = 1 (SURVEY 8d "to last sketch byte on host"): the C2 trio written as three FASTQ files,
+    `kevlar count` per sample (native reader -> GPU -> 64 MB sketch file), then `kevlar novel` from the case file and
+    the three sketch files to an augmented FASTQ.  In-process calls of the CLI mains; wall clock."""
+    import shutil
+    import tempfile
+    import kevlar_b200
+    from kevlar_b200 import cli, count, fastx, novel
+    tmp = tempfile.mkdtemp(prefix='kv_files_')
+    names = ['proband', 'mother', 'father']
+    try:
+        for name, (b, o) in zip(names, trio0):
+            reads = b.reshape(-1, READ_LEN)
+            qual = b'I' * READ_LEN
+            with open(os.path.join(tmp, name + '.fq'), 'wb') as fh:
+                fh.write(b''.join(b'@r%d\n%s\n+\n%s\n' % (i, reads[i].tobytes(), qual) for i in range(len(reads))))
+        files = [os.path.join(tmp, n + '.fq') for n in names]
+        text_bytes = sum(os.path.getsize(f) for f in files)
+        saved = kevlar_b200.logstream
+        kevlar_b200.logstream = open(os.devnull, 'w')
+        best_parse = None
+        for _ in range(3):
+            t = time.perf_counter()
+            n = sum(len(batch) for batch in fastx.NativeFastxReader(files[0]).batches(64 << 20, prefetch=False))
+            dt = time.perf_counter() - t
+            best_parse = dt if best_parse is None else min(best_parse, dt)
+        assert n == len(trio0[0][1]) - 1
+
+        def once():
+            t0 = time.perf_counter()
+            for name, f in zip(names, files):
+                a = cli.parser().parse_args(['count', '--memory', str(int(MEMORY)), '-k', str(K), os.path.join(tmp, name + '.ct'), f])
+                count.main(a)
+            t1 = time.perf_counter()
+            a = cli.parser().parse_args(['novel', '--case', files[0], '--case-counts', os.path.join(tmp, 'proband.ct'),
+                                         '--control-counts', os.path.join(tmp, 'mother.ct'), os.path.join(tmp, 'father.ct'),
+                                         '-k', str(K), '--case-min', str(CASE_MIN), '--ctrl-max', str(CTRL_MAX),
+                                         '-o', os.path.join(tmp, 'novel.augfastq')])
+            novel.main(a)
+            return t1 - t0, time.perf_counter() - t1
+        once()
+        t_count, t_novel = min((once() for _ in range(2)), key=sum)
+        kevlar_b200.logstream = saved
+        nk = kmers_per_step(trio0)
+        out = {'workload': 'C2 trio as three FASTQ files ({:.0f} MB of text): kevlar count x3 (parse -> GPU -> 64 MB sketch file each), '
+                           'kevlar novel (3 sketch files + case FASTQ -> augmented FASTQ); in-process CLI mains, files in {}'.format(
+                               text_bytes / 1e6, tempfile.gettempdir()),
+               'value': nk / (t_count + t_novel), 'unit': 'k-mers/s', 'count_x3_seconds': t_count, 'novel_seconds': t_novel,
+               'reader': {'threads_env': os.environ.get('KV_READER_THREADS', 'default: min(8, cores / local ranks)'),
+                          'cores': os.cpu_count(), 'seconds_per_file': best_parse,
+                          'text_GBps': os.path.getsize(files[0]) / best_parse / 1e9,
+                          'kmers_per_s': (nk / 4) / best_parse}}
+        phase('file-based path done')
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_ours(args):
     t_start = time.perf_counter()
     import torch
@@ -1022,6 +1081,9 @@ def measure(args, rank, world, barrier, phase, live):
         trio0 = trio if rank == 0 else None
         c5 = run_c5(args, rank, world, trio0, barrier, phase)
         phase('c5: banded chain done')
+    files = None
+    if world == 1 and not args.no_files and not runner.sharded and not getattr(runner, 'span', False):
+        files = run_files(args, trio, phase)
     if getattr(runner, 'span', False):
         runner.sketches = []
         for sp in runner.spans:
@@ -1122,6 +1184,8 @@ def measure(args, rank, world, barrier, phase, live):
         line['c4'] = c4
     if c5 is not None:
         line['c5'] = c5
+    if files is not None:
+        line['e2e_file'] = files
 
     if world == 1 and not args.no_cpu_baseline:
         from oracle import khmer_oracle as ko

@@ -326,6 +326,17 @@ int kv_reader_next(kv_reader *r, uint64_t max_bases, const uint8_t **bases, cons
                    const uint64_t **qual_offsets, const uint8_t **is_fastq);
 int kv_reader_num_reads(const kv_reader *r, uint64_t *n);
 int kv_reader_close(kv_reader *r);
+/* The same with batches the caller keeps: kv_reader_next_batch hands out a batch object (*out = NULL at the end
+ * of the input) whose arrays (kv_batch_arrays, same meaning as the outputs of kv_reader_next) stay valid until
+ * kv_batch_release -- also across further kv_reader_next_batch calls and after kv_reader_close -- so a consumer
+ * can pass them to kv_consume_batch / kv_novel_batch without copying while the next batch is being parsed.
+ * Released batches are recycled by their reader.  kv_batch_release may be called from any thread.
+ * Plain files are memory-mapped and parsed by KV_READER_THREADS threads (default min(8, cores / LOCAL_WORLD_SIZE)). */
+typedef struct kv_batch kv_batch;
+int kv_reader_next_batch(kv_reader *r, uint64_t max_bases, int keep_text, kv_batch **out);
+int kv_batch_arrays(const kv_batch *b, const uint8_t **bases, const uint64_t **offsets, uint64_t *n_reads, const char **names,
+                    const uint64_t **name_offsets, const char **quals, const uint64_t **qual_offsets, const uint8_t **is_fastq);
+int kv_batch_release(kv_batch *b);
 
 /* Measurement fixture, no reference counterpart in the product path: wgsim-style synthetic reads
  * drawn on the device (the recipe of kevlar/tests/data/minitrio/README: fixed-length reads from a

@@ -105,6 +105,10 @@ SYMBOLS = [
                                POINTER(_P), POINTER(_P), POINTER(_P)]),
     ('kv_reader_num_reads', c_int, [_P, POINTER(c_uint64)]),
     ('kv_reader_close', c_int, [_P]),
+    ('kv_reader_next_batch', c_int, [_P, c_uint64, c_int, POINTER(_P)]),
+    ('kv_batch_arrays', c_int, [_P, POINTER(_P), POINTER(_P), POINTER(c_uint64), POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P),
+                                POINTER(_P)]),
+    ('kv_batch_release', c_int, [_P]),
     ('kv_synth_reads', c_int, [c_int, POINTER(_P), POINTER(c_uint64), c_int, c_uint64, c_uint64, ctypes.c_uint32,
                                ctypes.c_double, c_uint64, _P, _P]),
     ('kv_stream', c_int, [c_int, POINTER(_P)]),

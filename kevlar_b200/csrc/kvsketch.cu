@@ -10,9 +10,14 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <cuda.h>   // driver API types only; entry points are fetched with cudaGetDriverEntryPoint (libcuda is never linked)
 
@@ -223,6 +228,53 @@ static int kv_io_stage(KvCtx *ctx, uint8_t **out)
     *out = ctx->h_stage;
     return KV_OK;
 }
+
+// Sketch files are table bytes behind a small header, and production sketches are 4-72 GB (kevlar docs/tutorial.rst:51):
+// one thread moves ~2 GB/s through the page cache, so the chunks that pass through the pinned staging buffer are read /
+// written by several threads at once (pread / pwrite at their file offsets; KV_IO_THREADS, default min(8, cores / local
+// ranks)), and the buffer is used in two halves so that the device copy of one chunk overlaps the file I/O of the other.
+static int kv_io_threads()
+{
+    static int n = 0;
+    if (!n) {
+        unsigned hw = std::thread::hardware_concurrency();
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        n = (int)std::max(1u, std::min(8u, (hw ? hw : 1u) / (unsigned)ranks));
+        if (const char *e = getenv("KV_IO_THREADS")) n = std::max(1, std::min(64, atoi(e)));
+    }
+    return n;
+}
+
+struct KvFileJob {   // file I/O of one chunk, running on its own threads until join()
+    std::vector<std::thread> workers;
+    std::atomic<bool> failed{false};
+    void start(int fd, uint8_t *buf, size_t n, uint64_t off, bool write)
+    {
+        const size_t min_part = 4u << 20;
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)kv_io_threads(), (n + min_part - 1) / min_part));
+        const size_t step = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+        for (int i = 0; i < parts; i++) {
+            const size_t lo = std::min(n, (size_t)i * step), hi = std::min(n, lo + step);
+            if (lo == hi) continue;
+            workers.emplace_back([this, fd, buf, off, lo, hi, write] {
+                size_t done = lo;
+                while (done < hi) {
+                    ssize_t got = write ? pwrite(fd, buf + done, hi - done, (off_t)(off + done)) : pread(fd, buf + done, hi - done, (off_t)(off + done));
+                    if (got <= 0) { failed = true; return; }   // error, or (reading) the file ends early
+                    done += (size_t)got;
+                }
+            });
+        }
+    }
+    bool join()
+    {
+        for (std::thread &t : workers) t.join();
+        workers.clear();
+        return !failed;
+    }
+    ~KvFileJob() { join(); }
+};
 
 static int kv_buf_ensure(KvBuf &b, size_t need)
 {
@@ -938,34 +990,45 @@ extern "C" int kv_sketch_save(kv_sketch *s, const char *path)
     CU(cudaSetDevice(s->device));
     uint64_t occ = 0;
     KV_TRY(kv_occupied_locked(ctx, s, &occ));
-    FILE *f = fopen(path, "wb");
-    if (!f) return kv_fail(KV_EIO, "cannot open %s for writing", path);
-    uint8_t version = 4, type = s->bits == 8 ? 1 : (s->bits == 4 ? 7 : 2);
-    fwrite("OXLI", 1, 4, f);
-    fwrite(&version, 1, 1, f);
-    fwrite(&type, 1, 1, f);
-    if (s->bits == 8) { uint8_t big = 0; fwrite(&big, 1, 1, f); }
-    uint32_t k = (uint32_t)s->ksize;
-    uint8_t nt = (uint8_t)s->n_tables;
-    fwrite(&k, 4, 1, f);
-    fwrite(&nt, 1, 1, f);
-    fwrite(&occ, 8, 1, f);
-    const size_t CH = KV_IO_STAGE;
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return kv_fail(KV_EIO, "cannot open %s for writing", path);
+    // header: "OXLI", version, type, [use_bigcount], k, n_tables, n_occupied; then per table its size and its bytes
+    uint8_t head[32];
+    size_t hn = 0;
+    auto put = [&](const void *p, size_t n) { memcpy(head + hn, p, n); hn += n; };
+    const uint8_t version = 4, type = s->bits == 8 ? 1 : (s->bits == 4 ? 7 : 2), big = 0, nt = (uint8_t)s->n_tables;
+    const uint32_t k = (uint32_t)s->ksize;
+    put("OXLI", 4); put(&version, 1); put(&type, 1);
+    if (s->bits == 8) put(&big, 1);
+    put(&k, 4); put(&nt, 1); put(&occ, 8);
+    uint64_t pos = 0;
+    int rc = KV_OK;
+    auto put_small = [&](const void *p, size_t n) {
+        if (rc == KV_OK && pwrite(fd, p, n, (off_t)pos) != (ssize_t)n) rc = kv_fail(KV_EIO, "short write to %s", path);
+        pos += n;
+    };
+    put_small(head, hn);
     uint8_t *stage = nullptr;
-    int rc = kv_io_stage(ctx, &stage);
-    if (rc != KV_OK) { fclose(f); return rc; }
+    if (rc == KV_OK) rc = kv_io_stage(ctx, &stage);
+    const size_t CH = KV_IO_STAGE / 2;
+    KvFileJob job[2];
+    int half = 0;
     for (int t = 0; t < s->n_tables && rc == KV_OK; t++) {
-        fwrite(&s->sizes[t], 8, 1, f);
-        for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
-            size_t n = (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o);
-            if (kv_table_d2h(ctx, s, t, o, stage, n) != cudaSuccess ||
+        put_small(&s->sizes[t], 8);
+        for (uint64_t o = 0; o < s->nbytes[t] && rc == KV_OK; o += CH, half ^= 1) {
+            const size_t n = (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o);
+            uint8_t *buf = stage + (size_t)half * CH;
+            if (!job[half].join()) { rc = kv_fail(KV_EIO, "write error on %s", path); break; }   // this half is free again
+            if (kv_table_d2h(ctx, s, t, o, buf, n) != cudaSuccess ||
                 cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "D2H copy failed"); break; }
-            if (fwrite(stage, 1, n, f) != n) { rc = kv_fail(KV_EIO, "short write to %s", path); break; }
+            job[half].start(fd, buf, n, pos + o, true);
         }
+        pos += s->nbytes[t];
     }
-    if (rc == KV_OK && s->bits == 8) { uint64_t nbig = 0; fwrite(&nbig, 8, 1, f); }
-    if (rc == KV_OK && ferror(f)) rc = kv_fail(KV_EIO, "write error on %s", path);
-    fclose(f);
+    for (int h = 0; h < 2; h++)
+        if (!job[h].join() && rc == KV_OK) rc = kv_fail(KV_EIO, "write error on %s", path);
+    if (s->bits == 8) { const uint64_t nbig = 0; put_small(&nbig, 8); }
+    if (close(fd) != 0 && rc == KV_OK) rc = kv_fail(KV_EIO, "write error on %s", path);
     return rc;
 }
 
@@ -1046,17 +1109,36 @@ extern "C" int kv_sketch_load(const char *path, int hasher, int expect_bits, int
     KvCtx *ctx;
     kv_ctx_get(device, &ctx);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t CH = KV_IO_STAGE;
+    const size_t CH = KV_IO_STAGE / 2;
     uint8_t *stage = nullptr;
     rc = kv_io_stage(ctx, &stage);
-    for (int t = 0; t < nt && rc == KV_OK; t++) {
-        fseek(f, data_pos[t], SEEK_SET);
-        for (uint64_t o = 0; o < s->nbytes[t]; o += CH) {
-            size_t n = (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o);
-            if (fread(stage, 1, n, f) != n) { rc = kv_fail(KV_EIO, "%s: truncated file", path); break; }
-            if (cudaMemcpyAsync(s->flat + s->toff[t] + o, stage, n, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
-                cudaStreamSynchronize(ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "H2D copy failed"); break; }
+    {   // chunk i+1 is read from the file (several threads) while chunk i travels to the device
+        struct Chunk { int t; uint64_t o; size_t n; };
+        std::vector<Chunk> chunks;
+        for (int t = 0; t < nt; t++)
+            for (uint64_t o = 0; o < s->nbytes[t]; o += CH) chunks.push_back({t, o, (size_t)std::min<uint64_t>(CH, s->nbytes[t] - o)});
+        KvFileJob job[2];
+        cudaEvent_t sent[2] = {nullptr, nullptr};
+        const int fd = fileno(f);
+        for (size_t i = 0; i <= chunks.size() && rc == KV_OK; i++) {
+            if (i < chunks.size()) {
+                const int h = (int)(i & 1);
+                if (sent[h] && cudaEventSynchronize(sent[h]) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "H2D copy failed"); break; }
+                job[h].start(fd, stage + (size_t)h * CH, chunks[i].n, (uint64_t)data_pos[chunks[i].t] + chunks[i].o, false);
+            }
+            if (i > 0) {
+                const int h = (int)((i - 1) & 1);
+                const Chunk &c = chunks[i - 1];
+                if (!job[h].join()) { rc = kv_fail(KV_EIO, "%s: truncated file", path); break; }
+                if (!sent[h] && cudaEventCreateWithFlags(&sent[h], cudaEventDisableTiming) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "cannot create an event"); break; }
+                if (cudaMemcpyAsync(s->flat + s->toff[c.t] + c.o, stage + (size_t)h * CH, c.n, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
+                    cudaEventRecord(sent[h], ctx->compute) != cudaSuccess) { rc = kv_fail(KV_ECUDA, "H2D copy failed"); break; }
+            }
         }
+        job[0].join(); job[1].join();
+        if (cudaStreamSynchronize(ctx->compute) != cudaSuccess && rc == KV_OK) rc = kv_fail(KV_ECUDA, "H2D copy failed");
+        for (int h = 0; h < 2; h++)
+            if (sent[h]) cudaEventDestroy(sent[h]);
     }
     if (rc == KV_OK && bits == 8 && big) {
         // khmer's use_bigcount: counts above 255 live in a map behind the tables; kevlar never sets it

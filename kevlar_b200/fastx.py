@@ -228,6 +228,29 @@ class FastxReader(object):
 
 
 
+class _BatchLease(object):
+    """Keeps a native batch (kv_batch) on loan while numpy views of its arrays are alive."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._handle = lib, handle
+
+    def view(self, address, count, typestr):
+        if not count:
+            return np.empty(0, dtype=np.dtype(typestr))
+
+        class _Memory(object):
+            pass
+        memory = _Memory()
+        memory.lease = self
+        memory.__array_interface__ = {'shape': (int(count),), 'typestr': typestr, 'data': (int(address), True), 'version': 3}
+        return np.asarray(memory)
+
+    def __del__(self):
+        handle, self._handle = getattr(self, '_handle', None), None
+        if handle is not None and handle.value and self._lib._lib is not None:
+            self._lib._lib.kv_batch_release(handle)
+
+
 class NativeFastxReader(object):
     """The same interface on top of the native parser in libkvsketch.so (kv_reader_*: a read-ahead
     thread doing the file I/O / inflate, memchr record splitting straight into the batch arrays);
@@ -250,25 +273,30 @@ class NativeFastxReader(object):
             self._lib._lib.kv_reader_close(h)
 
     def _next(self, max_bases, keep_text):
-        """One kv_reader_next call; copies the reader-owned buffers into numpy / bytes."""
+        """One kv_reader_next_batch call.  The batch's sequence bytes and offsets are numpy VIEWS of the native
+        batch (no copy): the batch stays on loan until the last view is garbage-collected, then goes back to the
+        reader for reuse.  Header / quality text (novel path only) is copied into bytes objects."""
         if self._stash:
             return self._stash.pop(0)
         c = ctypes
+        handle = c.c_void_p()
+        self._lib.check(self._lib.lib().kv_reader_next_batch(self._h, int(max_bases), int(bool(keep_text)), c.byref(handle)))
+        if not handle.value:
+            return None
+        lease = _BatchLease(self._lib, handle)
         bases, offs, names, noffs, quals, qoffs, isfq = (c.c_void_p() for _ in range(7))
         n = c.c_uint64()
         text = (c.byref(names), c.byref(noffs), c.byref(quals), c.byref(qoffs), c.byref(isfq)) if keep_text else (None,) * 5
-        self._lib.check(self._lib.lib().kv_reader_next(self._h, int(max_bases), c.byref(bases), c.byref(offs), c.byref(n), *text))
+        self._lib.check(self._lib.lib().kv_batch_arrays(handle, c.byref(bases), c.byref(offs), c.byref(n), *text))
         n = n.value
-        if n == 0:
-            return None
-        offsets = np.ctypeslib.as_array(c.cast(offs, c.POINTER(c.c_uint64)), shape=(n + 1,)).copy()
+        offsets = lease.view(offs.value, n + 1, '<u8')
         total = int(offsets[-1])
-        b = np.ctypeslib.as_array(c.cast(bases, c.POINTER(c.c_uint8)), shape=(max(total, 1),))[:total].copy()
+        b = lease.view(bases.value, total, '|u1')
         packed = None
         if keep_text:
-            no = np.ctypeslib.as_array(c.cast(noffs, c.POINTER(c.c_uint64)), shape=(n + 1,)).copy()
-            qo = np.ctypeslib.as_array(c.cast(qoffs, c.POINTER(c.c_uint64)), shape=(n + 1,)).copy()
-            fq = np.ctypeslib.as_array(c.cast(isfq, c.POINTER(c.c_uint8)), shape=(n,)).copy()
+            no = lease.view(noffs.value, n + 1, '<u8').copy()
+            qo = lease.view(qoffs.value, n + 1, '<u8').copy()
+            fq = lease.view(isfq.value, n, '|u1').copy()
             packed = (c.string_at(names, int(no[-1])), no, c.string_at(quals, int(qo[-1])), qo, fq)
         self.num_reads += n
         return SeqBatch(b, offsets, packed=packed)

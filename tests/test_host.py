@@ -269,6 +269,57 @@ def test_native_reader_large_inputs(tmp_path):
         del reader
 
 
+@pytest.mark.parametrize('threads,slice_bytes', [(1, 8 << 20), (4, 64), (7, 1000), (3, 70000)])
+def test_native_reader_parallel_slices(tmp_path, monkeypatch, threads, slice_bytes):
+    """Plain files are mapped and parsed slice by slice on several threads; slices must start at record
+    boundaries.  Quality strings that start with '@', '>' or '+', sequences of length 0, CRLF, blank lines,
+    multi-line FASTA, a FASTQ file that turns into FASTA half-way, junk before the first record: the same
+    records as the pure-Python reader and as the serial native path (KV_READER_NO_MMAP), whatever the slicing
+    and the batch size."""
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b'ACGTN', dtype=np.uint8)
+    qchars = np.frombuffer(b'@>+I#5', dtype=np.uint8)
+
+    def fastq(n, crlf=False):
+        out = []
+        for i in range(n):
+            ln = int(rng.integers(0, 60))
+            seq = letters[rng.integers(0, 5, size=ln)].tobytes()
+            qual = qchars[rng.integers(0, 6, size=ln)].tobytes()
+            eol = b'\r\n' if crlf and i % 3 == 0 else b'\n'
+            out.append(b'@r%d x\n' % i + seq + eol + b'+\n' + qual + eol + (b'\n' if i % 17 == 0 else b''))
+        return b''.join(out)
+
+    def fasta(n):
+        out = []
+        for i in range(n):
+            out.append(b'>c%d\n' % i)
+            for _ in range(int(rng.integers(0, 4))):
+                out.append(letters[rng.integers(0, 5, size=int(rng.integers(1, 50)))].tobytes() + b'\n')
+        return b''.join(out)
+
+    files = {'a.fq': fastq(3000, crlf=True), 'b.fa': fasta(2000), 'c.fq': fastq(1500) + fasta(300) + fastq(5),
+             'd.fq': b'\n\n' + fastq(800)[:-1], 'e.txt': b'junk line\n' + fastq(50), 'f.fq': b'@only\nACGT\n+\nIIII'}
+    for name, text in files.items():
+        path = tmp_path / name
+        path.write_bytes(text)
+        want = [(r.name, r.sequence, r.quality) for r in fastx.FastxReader(str(path))]
+        monkeypatch.setenv('KV_READER_NO_MMAP', '1')
+        serial = [(r.name, r.sequence, r.quality) for r in fastx.NativeFastxReader(str(path))]
+        monkeypatch.delenv('KV_READER_NO_MMAP')
+        assert serial == want, name
+        monkeypatch.setenv('KV_READER_THREADS', str(threads))
+        monkeypatch.setenv('KV_READER_SLICE_BYTES', str(slice_bytes))
+        got = [(r.name, r.sequence, r.quality) for r in fastx.NativeFastxReader(str(path))]
+        assert got == want, name
+        for max_bases in (1, 500, 64 << 20):
+            reader = fastx.NativeFastxReader(str(path))
+            seqs = []
+            for batch in reader.batches(max_bases):
+                seqs.extend(batch.bases[int(batch.offsets[i]):int(batch.offsets[i + 1])].tobytes().decode() for i in range(len(batch)))
+            assert seqs == [w[1] for w in want] and reader.num_reads == len(want), (name, max_bases)
+
+
 def test_fastx_reader_shared_by_threads():
     """kevlar/count.py:40-77: several consumers drain one parser; every read exactly once."""
     reader = kv.khmer.ReadParser(golden_data('trio1/case1.fq.gz'))
