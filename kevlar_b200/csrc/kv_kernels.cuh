@@ -902,6 +902,8 @@ __global__ void __launch_bounds__(256) kv_occ_rebuild_all_kernel(const __grid_co
 // seg_cnt[seg] -- no global counter that a million warps would fight over.
 #define KV_SEG_LOG2 12
 
+#define KV_COMPACT_U 4   // positions per thread and iteration: their random loads are in flight together
+
 template <bool FUSED0>
 __global__ void __launch_bounds__(256) kv_first_compact_kernel(const __grid_constant__ KvView v, const uint32_t *__restrict__ first,
                                                                const uint64_t *__restrict__ hashes,
@@ -918,36 +920,55 @@ __global__ void __launch_bounds__(256) kv_first_compact_kernel(const __grid_cons
         if (threadIdx.x == 0) s_cur = 0;
         __syncthreads();
         const uint64_t base = seg << KV_SEG_LOG2;
-        for (unsigned off = threadIdx.x; off < (1u << KV_SEG_LOG2); off += 256) {
-            const uint64_t g = base + off;
-            bool keep = g < total && (!valid || ((__ldg(valid + (g >> 5)) >> (g & 31)) & 1u));
-            bool is_new = false;
-            uint64_t h = 0;
-            if (keep) {
-                h = __ldcs(hashes + g);
-                if (FUSED0) {
-                    uint64_t bin;
-                    if (kv_bin(v, 0, h, bin) && kv_bucket_empty(v, 0, bin)) {
-                        const uint32_t owner = __ldcg(first + bin) & KV_POS_MASK;   // this position took part in pass A
-                        if (owner == (uint32_t)g) is_new = true;
-                        else if (__ldg(hashes + owner) == h) keep = false;           // repeat of an earlier occurrence
-                    }
+        for (unsigned off0 = threadIdx.x; off0 < (1u << KV_SEG_LOG2); off0 += 256 * KV_COMPACT_U) {
+            // the chain per position is hash -> (occupancy bit, first[bin]) -> hash of the bucket's owner: each stage is
+            // issued for all KV_COMPACT_U positions before the next one looks at the results
+            uint64_t g[KV_COMPACT_U], h[KV_COMPACT_U], bin[KV_COMPACT_U];
+            bool keep[KV_COMPACT_U], is_new[KV_COMPACT_U], mine[KV_COMPACT_U];
+            uint32_t owner[KV_COMPACT_U];
+#pragma unroll
+            for (int u = 0; u < KV_COMPACT_U; u++) {
+                g[u] = base + off0 + 256u * u;
+                keep[u] = g[u] < total && (!valid || ((__ldg(valid + (g[u] >> 5)) >> (g[u] & 31)) & 1u));
+                is_new[u] = false;
+                mine[u] = false;
+                h[u] = keep[u] ? __ldcs(hashes + g[u]) : 0;
+            }
+            if (FUSED0) {
+#pragma unroll
+                for (int u = 0; u < KV_COMPACT_U; u++) {
+                    mine[u] = keep[u] && kv_bin(v, 0, h[u], bin[u]);
+                    owner[u] = mine[u] ? __ldcg(first + bin[u]) & KV_POS_MASK : 0;   // (speculative: only empty buckets took part in pass A)
                 }
+#pragma unroll
+                for (int u = 0; u < KV_COMPACT_U; u++) mine[u] = mine[u] && kv_bucket_empty(v, 0, bin[u]);
+                uint64_t oh[KV_COMPACT_U];
+#pragma unroll
+                for (int u = 0; u < KV_COMPACT_U; u++) {
+                    is_new[u] = mine[u] && owner[u] == (uint32_t)g[u];
+                    oh[u] = mine[u] && !is_new[u] ? __ldg(hashes + owner[u]) : ~h[u];
+                }
+#pragma unroll
+                for (int u = 0; u < KV_COMPACT_U; u++)
+                    if (oh[u] == h[u]) keep[u] = false;   // repeat of an earlier occurrence
             }
-            const unsigned new_bal = __ballot_sync(0xffffffffu, is_new);
-            const unsigned keep_bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0 && g < ((total + 31) & ~(uint64_t)31)) {
-                fresh[g >> 5] = new_bal;
-                n_new += __popc(new_bal);
-            }
-            if (keep_bal) {
-                unsigned wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&s_cur, (unsigned)__popc(keep_bal));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (keep) {
-                    const uint64_t slot = base + wbase + __popc(keep_bal & ((1u << lane) - 1u));
-                    list_h[slot] = h;
-                    list_p[slot] = (uint32_t)g;
+#pragma unroll
+            for (int u = 0; u < KV_COMPACT_U; u++) {
+                const unsigned new_bal = __ballot_sync(0xffffffffu, is_new[u]);
+                const unsigned keep_bal = __ballot_sync(0xffffffffu, keep[u]);
+                if (lane == 0 && g[u] < ((total + 31) & ~(uint64_t)31)) {
+                    fresh[g[u] >> 5] = new_bal;
+                    n_new += __popc(new_bal);
+                }
+                if (keep_bal) {
+                    unsigned wbase = 0;
+                    if (lane == 0) wbase = atomicAdd(&s_cur, (unsigned)__popc(keep_bal));
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    if (keep[u]) {
+                        const uint64_t slot = base + wbase + __popc(keep_bal & ((1u << lane) - 1u));
+                        list_h[slot] = h[u];
+                        list_p[slot] = (uint32_t)g[u];
+                    }
                 }
             }
         }
@@ -970,7 +991,8 @@ __global__ void __launch_bounds__(256) kv_first_min0_kernel(const __grid_constan
     }
 }
 
-// pass A of table t over the list
+// pass A of table t over the list (KV_LIST_U entries per thread and iteration: their occupancy loads are in flight together)
+#define KV_LIST_U 4
 __global__ void __launch_bounds__(256) kv_first_min_list_kernel(const __grid_constant__ KvView v, int t, uint32_t *__restrict__ first,
                                                                 uint32_t tag, const uint64_t *__restrict__ list_h,
                                                                 const uint32_t *__restrict__ list_p,
@@ -980,10 +1002,23 @@ __global__ void __launch_bounds__(256) kv_first_min_list_kernel(const __grid_con
     for (uint64_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
         const uint32_t cnt = seg_cnt[seg];
         const uint64_t base = seg << KV_SEG_LOG2;
-        for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
-            uint64_t bin;
-            if (kv_bin(v, t, __ldg(list_h + base + i), bin) && bin - bin_lo < bin_n && kv_bucket_empty(v, t, bin))
-                atomicMin(first + (bin - bin_lo), tag | __ldg(list_p + base + i));
+        for (uint32_t i0 = threadIdx.x; i0 < cnt; i0 += 256 * KV_LIST_U) {
+            uint64_t bin[KV_LIST_U];
+            uint32_t pos[KV_LIST_U];
+            bool hit[KV_LIST_U];
+#pragma unroll
+            for (int u = 0; u < KV_LIST_U; u++) {
+                const uint32_t i = i0 + 256u * u;
+                hit[u] = i < cnt;
+                const uint64_t h = hit[u] ? __ldg(list_h + base + i) : 0;
+                pos[u] = hit[u] ? __ldg(list_p + base + i) : 0;
+                hit[u] = hit[u] && kv_bin(v, t, h, bin[u]) && bin[u] - bin_lo < bin_n;
+            }
+#pragma unroll
+            for (int u = 0; u < KV_LIST_U; u++) hit[u] = hit[u] && kv_bucket_empty(v, t, bin[u]);
+#pragma unroll
+            for (int u = 0; u < KV_LIST_U; u++)
+                if (hit[u]) atomicMin(first + (bin[u] - bin_lo), tag | pos[u]);
         }
     }
 }
@@ -1000,14 +1035,27 @@ __global__ void __launch_bounds__(256) kv_first_own_list_kernel(const __grid_con
     for (uint64_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
         const uint32_t cnt = seg_cnt[seg];
         const uint64_t base = seg << KV_SEG_LOG2;
-        for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
-            uint64_t bin;
-            const uint32_t g = __ldg(list_p + base + i);
-            if (kv_bin(v, t, __ldg(list_h + base + i), bin) && bin - bin_lo < bin_n && kv_bucket_empty(v, t, bin) &&
-                __ldcg(first + (bin - bin_lo)) == (tag | g)) {
-                const uint32_t bit = 1u << (g & 31);
-                n_new += !(atomicOr(fresh + (g >> 5), bit) & bit);
+        for (uint32_t i0 = threadIdx.x; i0 < cnt; i0 += 256 * KV_LIST_U) {
+            uint64_t bin[KV_LIST_U];
+            uint32_t pos[KV_LIST_U], rec[KV_LIST_U];
+            bool hit[KV_LIST_U];
+#pragma unroll
+            for (int u = 0; u < KV_LIST_U; u++) {
+                const uint32_t i = i0 + 256u * u;
+                hit[u] = i < cnt;
+                const uint64_t h = hit[u] ? __ldg(list_h + base + i) : 0;
+                pos[u] = hit[u] ? __ldg(list_p + base + i) : 0;
+                hit[u] = hit[u] && kv_bin(v, t, h, bin[u]) && bin[u] - bin_lo < bin_n;
+                rec[u] = hit[u] ? __ldcg(first + (bin[u] - bin_lo)) : 0;   // (speculative: only empty buckets took part in pass A)
             }
+#pragma unroll
+            for (int u = 0; u < KV_LIST_U; u++) hit[u] = hit[u] && kv_bucket_empty(v, t, bin[u]);
+#pragma unroll
+            for (int u = 0; u < KV_LIST_U; u++)
+                if (hit[u] && rec[u] == (tag | pos[u])) {
+                    const uint32_t bit = 1u << (pos[u] & 31);
+                    n_new += !(atomicOr(fresh + (pos[u] >> 5), bit) & bit);
+                }
         }
     }
     n_new = __reduce_add_sync(0xffffffffu, n_new);
