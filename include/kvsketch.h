@@ -331,7 +331,9 @@ int kv_reader_close(kv_reader *r);
  * kv_batch_release -- also across further kv_reader_next_batch calls and after kv_reader_close -- so a consumer
  * can pass them to kv_consume_batch / kv_novel_batch without copying while the next batch is being parsed.
  * Released batches are recycled by their reader.  kv_batch_release may be called from any thread.
- * Plain files are memory-mapped and parsed by KV_READER_THREADS threads (default min(8, cores / LOCAL_WORLD_SIZE)). */
+ * Plain files are memory-mapped and parsed by KV_READER_THREADS threads (default min(8, cores / LOCAL_WORLD_SIZE));
+ * BGZF (bgzip) files are mapped too and their blocks inflated by the same threads; an ordinary gzip stream is
+ * inflated by one read-ahead thread. */
 typedef struct kv_batch kv_batch;
 int kv_reader_next_batch(kv_reader *r, uint64_t max_bases, int keep_text, kv_batch **out);
 int kv_batch_arrays(const kv_batch *b, const uint8_t **bases, const uint64_t **offsets, uint64_t *n_reads, const char **names,

@@ -320,6 +320,57 @@ def test_native_reader_parallel_slices(tmp_path, monkeypatch, threads, slice_byt
             assert seqs == [w[1] for w in want] and reader.num_reads == len(want), (name, max_bases)
 
 
+def _bgzf(text, block=5000, level=6):
+    """`text` as a BGZF (bgzip) file: independent gzip members with the 'BC' block-size subfield, then the empty
+    end-of-file block."""
+    import struct
+    import zlib
+    out = []
+    for i in list(range(0, len(text), block)) + [None]:
+        chunk = b'' if i is None else text[i:i + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        data = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(data) + 8 - 1
+        out.append(b'\x1f\x8b\x08\x04' + b'\0' * 4 + b'\0\xff' + struct.pack('<H', 6) + b'BC' + struct.pack('<HH', 2, bsize) + data +
+                   struct.pack('<II', zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    return b''.join(out)
+
+
+@pytest.mark.parametrize('threads,slice_bytes', [(1, 8 << 20), (5, 3000), (4, 40000)])
+def test_native_reader_bgzf_blocks_in_parallel(tmp_path, monkeypatch, threads, slice_bytes):
+    """bgzip files: the blocks are inflated by the reader's thread pool window by window (records straddle block
+    and window boundaries) and parsed by the same parallel parser; same records as Python's gzip module gives the
+    pure-Python reader.  A flipped bit in a block is an error, not a short file."""
+    import gzip
+    rng = np.random.default_rng(8)
+    letters = np.frombuffer(b'ACGTN', dtype=np.uint8)
+    fq = b''.join(b'@read%d\n%s\n+\n%s\n' % (i, letters[rng.integers(0, 5, size=n)].tobytes(), b'@' * n)
+                  for i, n in enumerate(rng.integers(0, 300, size=4000)))
+    fa = b''.join(b'>seq%d\n' % i + b''.join(letters[rng.integers(0, 5, size=60)].tobytes() + b'\n' for _ in range(int(rng.integers(0, 400))))
+                  for i in range(40))
+    monkeypatch.setenv('KV_READER_THREADS', str(threads))
+    monkeypatch.setenv('KV_READER_SLICE_BYTES', str(slice_bytes))
+    for name, text in (('a.fq.gz', fq), ('b.fa.gz', fa), ('c.fq.gz', fq[:20000] + fa[:30000]), ('d.txt.gz', b'junk\n' + fq[:5000])):
+        path = tmp_path / name
+        path.write_bytes(_bgzf(text))
+        assert gzip.open(str(path)).read() == text
+        want = [(r.name, r.sequence, r.quality) for r in fastx.FastxReader(str(path))]
+        got = [(r.name, r.sequence, r.quality) for r in fastx.NativeFastxReader(str(path))]
+        assert got == want and len(want) > 5, name
+        reader = fastx.NativeFastxReader(str(path))
+        seqs = []
+        for batch in reader.batches(20000):
+            seqs.extend(batch.bases[int(batch.offsets[i]):int(batch.offsets[i + 1])].tobytes().decode() for i in range(len(batch)))
+        assert seqs == [w[1] for w in want], name
+    good = _bgzf(fq)
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x10
+    (tmp_path / 'bad.fq.gz').write_bytes(bytes(bad))
+    with pytest.raises(OSError):
+        for _ in fastx.NativeFastxReader(str(tmp_path / 'bad.fq.gz')).batches(1 << 20):
+            pass
+
+
 def test_fastx_reader_shared_by_threads():
     """kevlar/count.py:40-77: several consumers drain one parser; every read exactly once."""
     reader = kv.khmer.ReadParser(golden_data('trio1/case1.fq.gz'))
