@@ -902,9 +902,10 @@ __global__ void __launch_bounds__(256) kv_occ_rebuild_all_kernel(const __grid_co
 // seg_cnt[seg] -- no global counter that a million warps would fight over.
 #define KV_SEG_LOG2 12
 
-#define KV_COMPACT_U 4   // positions per thread and iteration: their random loads are in flight together
-
-template <bool FUSED0>
+// KV_COMPACT_U = positions per thread and iteration, their random loads in flight together, first[] fetched before
+// the occupancy bit is known.  4 for a sample counted into its own sketch (most buckets empty at chunk start; C2 at
+// N = 1: 401 -> 351 us); 1 when another rank's occupancy is the occupied set or a merge shares the GPU (the host picks).
+template <bool FUSED0, int KV_COMPACT_U>
 __global__ void __launch_bounds__(256) kv_first_compact_kernel(const __grid_constant__ KvView v, const uint32_t *__restrict__ first,
                                                                const uint64_t *__restrict__ hashes,
                                                                const uint32_t *__restrict__ valid, uint64_t total,
@@ -991,8 +992,9 @@ __global__ void __launch_bounds__(256) kv_first_min0_kernel(const __grid_constan
     }
 }
 
-// pass A of table t over the list (KV_LIST_U entries per thread and iteration: their occupancy loads are in flight together)
-#define KV_LIST_U 4
+// pass A of table t over the list (KV_LIST_U entries per thread and iteration, their occupancy loads in flight together;
+// 4 or 1 like KV_COMPACT_U above)
+template <int KV_LIST_U>
 __global__ void __launch_bounds__(256) kv_first_min_list_kernel(const __grid_constant__ KvView v, int t, uint32_t *__restrict__ first,
                                                                 uint32_t tag, const uint64_t *__restrict__ list_h,
                                                                 const uint32_t *__restrict__ list_p,
@@ -1024,6 +1026,7 @@ __global__ void __launch_bounds__(256) kv_first_min_list_kernel(const __grid_con
 }
 
 // pass B of table t over the list: whoever is recorded in first[] is new (counted once over all tables)
+template <int KV_LIST_U>
 __global__ void __launch_bounds__(256) kv_first_own_list_kernel(const __grid_constant__ KvView v, int t, const uint32_t *__restrict__ first,
                                                                 uint32_t tag, const uint64_t *__restrict__ list_h,
                                                                 const uint32_t *__restrict__ list_p,

@@ -1397,7 +1397,7 @@ static int kv_fresh_prepare(KvCtx *ctx, const kv_sketch *s, const KvView &v, boo
 // of new positions in ctx->fresh.  dist_counts != NULL: also histogram dist_counts.get(h) over them.
 static int kv_count_fresh(KvCtx *ctx, const kv_sketch *s, const KvView &v, const KvFreshPre &pre, const uint64_t *d_hashes,
                           const uint32_t *d_valid, uint64_t n, const kv_sketch *dist_counts = nullptr,
-                          unsigned long long *d_hist = nullptr, unsigned long long *d_unique = nullptr)
+                          unsigned long long *d_hist = nullptr, unsigned long long *d_unique = nullptr, bool own_occupancy = true)
 {
     if (!d_unique) d_unique = s->d_unique;
     if (n > (1ull << KV_POS_BITS)) return kv_fail(KV_EINVAL, "internal: n_unique chunk larger than 2^%d positions", KV_POS_BITS);
@@ -1412,22 +1412,35 @@ static int kv_count_fresh(KvCtx *ctx, const kv_sketch *s, const KvView &v, const
     uint32_t *list_p = (uint32_t *)ctx->list_p.p;
     const unsigned grid = kv_grid_for(ctx, n);
     const unsigned sgrid = (unsigned)std::min<uint64_t>(n_segs, (uint64_t)ctx->sm_count * 8);
-    if (pre.fused0)
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_compact_kernel<true>, sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, fresh,
-                 list_h, list_p, seg_cnt, d_unique);
-    else
-        LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_compact_kernel<false>, sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, fresh,
-                 list_h, list_p, seg_cnt, d_unique);
+    // The unrolled kernels (4 positions per thread, first[] loaded before the occupancy bit is known) pay when most
+    // buckets are empty at chunk start -- a sample counted into its own sketch.  With another rank's occupancy as
+    // the occupied set (kv_unique_batch / kv_unique_last_batch) most of those early loads are wasted, and next to a
+    // merge on the merge lane their registers cost residency: C2 at N = 2, step 10.27 ms unrolled, 9.23 ms plain.
+    const bool wide = own_occupancy && !ctx->forked;
+#define KV_COMPACT_LAUNCH(FUSED_, U_)                                                                                             \
+    LAUNCH_C(KV_PROF_UNIQUE, ctx, (kv_first_compact_kernel<FUSED_, U_>), sgrid, 256, v, (const uint32_t *)first, d_hashes, d_valid, n, \
+             fresh, list_h, list_p, seg_cnt, d_unique)
+    if (pre.fused0) { if (wide) KV_COMPACT_LAUNCH(true, 4); else KV_COMPACT_LAUNCH(true, 1); }
+    else { if (wide) KV_COMPACT_LAUNCH(false, 4); else KV_COMPACT_LAUNCH(false, 1); }
+#undef KV_COMPACT_LAUNCH
     for (int t = pre.fused0 ? 1 : 0; t < s->n_tables; t++)
         for (uint64_t lo = 0; lo < s->sizes[t]; lo += pre.range) {
             const uint64_t nb = std::min(pre.range, s->sizes[t] - lo);
             uint32_t tag;
             KV_TRY(kv_first_tag(ctx, &tag));
-            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_list_kernel, sgrid, 256, v, t, first, tag, (const uint64_t *)list_h,
-                     (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb);
-            LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_own_list_kernel, sgrid, 256, v, t, (const uint32_t *)first, tag,
-                     (const uint64_t *)list_h, (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb, fresh,
-                     d_unique);
+            if (wide) {
+                LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_list_kernel<4>, sgrid, 256, v, t, first, tag, (const uint64_t *)list_h,
+                         (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb);
+                LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_own_list_kernel<4>, sgrid, 256, v, t, (const uint32_t *)first, tag,
+                         (const uint64_t *)list_h, (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb, fresh,
+                         d_unique);
+            } else {
+                LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min_list_kernel<1>, sgrid, 256, v, t, first, tag, (const uint64_t *)list_h,
+                         (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb);
+                LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_own_list_kernel<1>, sgrid, 256, v, t, (const uint32_t *)first, tag,
+                         (const uint64_t *)list_h, (const uint32_t *)list_p, (const uint32_t *)seg_cnt, n_segs, lo, nb, fresh,
+                         d_unique);
+            }
         }
     if (dist_counts)
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_abund_dist_kernel, grid, 256, kv_view(dist_counts), d_hashes, (const uint32_t *)fresh, n,
@@ -2300,7 +2313,7 @@ extern "C" int kv_unique_batch(const kv_sketch *like, uint32_t *const *dev_occup
         if (pre.fused0) { p.track0 = 1; p.first0 = (uint32_t *)ctx->first.p; p.tag0 = pre.tag0; p.sk = v; }
         if (like->hasher == KV_HASH_TWOBIT) KV_TRY(kv_launch_hash<KV_HASH_TWOBIT>(ctx, p, (unsigned)nt));
         else KV_TRY(kv_launch_hash<KV_HASH_MURMUR>(ctx, p, (unsigned)nt));
-        KV_TRY(kv_count_fresh(ctx, like, v, pre, p.hashes, p.valid, npos, nullptr, nullptr, d_unique));
+        KV_TRY(kv_count_fresh(ctx, like, v, pre, p.hashes, p.valid, npos, nullptr, nullptr, d_unique, false));
         if (t0 + chunk_tiles < b.n_tiles) {   // later chunks of this rank must see this chunk's buckets as occupied
             const uint64_t n_segs = (npos + (1u << KV_SEG_LOG2) - 1) >> KV_SEG_LOG2;
             const unsigned sgrid = (unsigned)std::min<uint64_t>(n_segs, (uint64_t)ctx->sm_count * 8);
@@ -2352,7 +2365,7 @@ extern "C" int kv_unique_last_batch(const kv_sketch *like, uint32_t *const *dev_
         LAUNCH_C(KV_PROF_UNIQUE, ctx, kv_first_min0_kernel, kv_grid_for(ctx, npos), 256, v, (uint32_t *)ctx->first.p, pre.tag0,
                  d_hashes, d_valid, npos);
     ctx->last_hashed.sketch = nullptr;   // first[] is about to be reused for the other tables: the shortcut works once
-    KV_TRY(kv_count_fresh(ctx, like, v, pre, d_hashes, d_valid, npos, nullptr, nullptr, d_unique));
+    KV_TRY(kv_count_fresh(ctx, like, v, pre, d_hashes, d_valid, npos, nullptr, nullptr, d_unique, false));
     if (dev_n_unique_out) CU(cudaMemcpyAsync(dev_n_unique_out, d_unique, 8, cudaMemcpyDeviceToDevice, ctx->compute));
     if (n_unique_out) {
         CU(cudaMemcpyAsync(ctx->h_counters + 7, d_unique, 8, cudaMemcpyDeviceToHost, ctx->compute));
