@@ -242,15 +242,16 @@ def cpu_step(ko, trio, threads, shape=('Counttable', MEMORY / N_TABLES)):
     return time.perf_counter() - t0, hits, counted, sks
 
 
-def reference_python_novel(ko, trio, max_reads=1500):
+def reference_python_novel(ko, trio, max_reads=1500, sks=None):
     """The reference's REAL novel loop shape (kevlar/novel.py:123-169: a Python loop over reads and over
     k-mers with one `get` per sample and k-mer, single-threaded) over the oracle's khmer-shaped
     objects, on the first `max_reads` proband reads.  Returns (k-mers/s, reads used)."""
-    sks = []
-    for bases, offs in trio:
-        sk = ko.Counttable(K, MEMORY / N_TABLES, N_TABLES)
-        sk.consume_batch(bases, offs, threads=os.cpu_count() or 1)
-        sks.append(sk)
+    if sks is None:
+        sks = []
+        for bases, offs in trio:
+            sk = ko.Counttable(K, MEMORY / N_TABLES, N_TABLES)
+            sk.consume_batch(bases, offs, threads=os.cpu_count() or 1)
+            sks.append(sk)
     bases, offs = trio[0]
     n = min(max_reads, len(offs) - 1)
     seqs = [bases[int(offs[i]):int(offs[i + 1])].tobytes().decode() for i in range(n)]
@@ -1205,6 +1206,12 @@ def measure(args, rank, world, barrier, phase, live):
         line['parity_vs_oracle'] = 'bit-exact (3 sketches, {} hits)'.format(len(ohits)) if same else 'MISMATCH'
         if not same:
             raise SystemExit('bench.py: GPU results differ from the oracle')
+        # the reference's REAL novel path beside the multi-threaded C one -- a single-threaded Python loop
+        py_rate, py_reads = reference_python_novel(ko, trio, sks=osk)
+        line['cpu_baseline']['reference_python_novel_loop'] = {
+            'value': py_rate, 'unit': 'k-mers/s', 'cores': 1,
+            'sample': 'kevlar/novel.py:123-169 as the reference runs it (one get() per sample and k-mer from Python) over the '
+                      'oracle sketches, first {} proband reads'.format(py_reads)}
     if parity_n is not None:
         line['parity_vs_oracle'] = parity_n[1]
         if not parity_n[0]:
