@@ -13,7 +13,6 @@ its quirk: band 1 reports nothing, band b keeps low bits b-2 -- SURVEY App. B.1)
         --case proband.fq --control mother.fq --control father.fq -k 31 --memory 500K --out-prefix run1
 """
 import argparse
-import os
 import sys
 
 import kevlar_b200
