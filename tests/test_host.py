@@ -391,7 +391,7 @@ def test_native_reader_agrees_with_python_reader_on_line_soup(tmp_path, monkeypa
                       st.booleans())
     counter = [0]
 
-    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=150, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
     @given(files)
     def check(spec):
         chunks, eol, final_newline = spec
